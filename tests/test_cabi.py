@@ -1,0 +1,70 @@
+"""The C-ABI shared library loads and exports every symbol include/zkb200.h declares. CPU only:
+no compute call is made unless a GPU is present (there is no CPU fallback to call)."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def zkb():
+    import zkb200
+
+    zkb200.build()
+    return zkb200
+
+
+def declared_symbols():
+    src = open(os.path.join(ROOT, "include", "zkb200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(zkb_[a-z_0-9]+)\s*\(", src)))
+
+
+def test_header_symbols_are_exported(zkb):
+    syms = declared_symbols()
+    assert len(syms) >= 15
+    L = ctypes.CDLL(zkb.LIB_PATH)
+    for s in syms:
+        assert hasattr(L, s), f"{s} declared in include/zkb200.h but not exported"
+    assert sorted(zkb.EXPORTS) == syms
+    assert "sm_100a" in zkb.version()
+
+
+def test_status_codes_match_header(zkb):
+    src = open(os.path.join(ROOT, "include", "zkb200.h")).read()
+    for code, name in zkb.STATUS.items():
+        m = re.search(name + r"\s*=\s*(-?\d+)", src)
+        assert m and int(m.group(1)) == code
+
+
+def test_malformed_common_data_is_a_parse_error(zkb):
+    # parse errors are reported before any device is touched
+    from conftest import golden_bytes
+
+    good = golden_bytes("bench_common.bin")
+    cs = np.zeros(84 * 16, dtype=np.uint64)
+    for bad in (good[:-1], good + b"\0", good[:100], b""):
+        with pytest.raises(zkb.ZkbError) as e:
+            zkb.ProverCircuit(bad if bad else b"\0", cs)
+        assert e.value.status == "ZKB_E_PARSE"
+    # unsupported gate tag (13 = RandomAccess) -> ZKB_E_UNSUPPORTED_GATE
+    tampered = bytearray(good)
+    tampered[997] = 13
+    with pytest.raises(zkb.ZkbError) as e:
+        zkb.ProverCircuit(bytes(tampered), cs)
+    assert e.value.status == "ZKB_E_UNSUPPORTED_GATE"
+
+
+def test_no_cpu_fallback(zkb):
+    if zkb.device_count() > 0:
+        pytest.skip("a GPU is present; the fail-loudly path is exercised on the CPU box")
+    with pytest.raises(zkb.ZkbError) as e:
+        zkb.poseidon_permute_batch(np.zeros((1, 12), dtype=np.uint64))
+    assert e.value.status == "ZKB_E_CUDA"
+    with pytest.raises(zkb.ZkbError) as e:
+        zkb.lde_batch(np.zeros((1, 8), dtype=np.uint64))
+    assert e.value.status == "ZKB_E_CUDA"

@@ -1,0 +1,88 @@
+"""End-to-end parity: proofs produced by the CUDA prover through the C ABI are byte-identical to the
+oracle prover's on the same witness, salts and PoW rule, and are accepted by the pinned verifier
+(SURVEY.md §8c levels L2 + L3)."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def zkb():
+    import zkb200
+
+    if zkb200.device_count() == 0:
+        pytest.fail("no CUDA device: -m gpu tests must run on the B200 box")
+    return zkb200
+
+
+def run_case(zkb, oracle, spec, zk, seed, salt_seed=77):
+    s = oracle.Synth(zk=zk, seed=seed, **spec)
+    oc = oracle.Circuit(s.common, s.const_sigma_values)
+    gc = zkb.ProverCircuit(s.common, s.const_sigma_values, is_values=True, circuit_digest=oc.digest)
+    want = oc.prove(s.wires, s.public_inputs, salt_seed=salt_seed)
+    got = gc.prove(s.wires, s.public_inputs, salt_seed=salt_seed)
+    assert len(got) == gc.proof_size == len(want)
+    assert oc.verify(got) == "", "CUDA proof rejected by the pinned verifier"
+    assert got == want, "CUDA proof bytes differ from the oracle prover"
+    return s, oc, gc, got
+
+
+@pytest.mark.parametrize("zk", [False, True])
+def test_tiny_circuit_proof_bytes(zkb, oracle, zk):
+    s, oc, gc, proof = run_case(zkb, oracle, oracle.Synth.TINY, zk, seed=5)
+    # deterministic and re-usable context
+    assert gc.prove(s.wires, s.public_inputs, salt_seed=77) == proof
+    t = gc.timings()
+    assert t["total"] > 0
+
+
+def test_voting_shaped_proof_bytes(zkb, oracle):
+    run_case(zkb, oracle, oracle.Synth.VOTING, False, seed=2)
+
+
+def test_explicit_salts(zkb, oracle):
+    s = oracle.Synth(zk=True, seed=8, **oracle.Synth.TINY)
+    oc = oracle.Circuit(s.common, s.const_sigma_values)
+    gc = zkb.ProverCircuit(s.common, s.const_sigma_values, is_values=True)
+    rng = np.random.default_rng(3)
+    salts = rng.integers(0, 0xFFFFFFFF00000001, size=(3, 4, s.n * 8), dtype=np.uint64)
+    got = gc.prove(s.wires, s.public_inputs, salts=salts)
+    assert got == oc.prove(s.wires, s.public_inputs, salts=salts)
+    assert oc.verify(got) == ""
+
+
+def test_bad_arguments(zkb, oracle):
+    s = oracle.Synth(zk=False, seed=3, **oracle.Synth.TINY)
+    gc = zkb.ProverCircuit(s.common, s.const_sigma_values, is_values=True)
+    with pytest.raises(zkb.ZkbError) as e:
+        gc.prove(s.wires, s.public_inputs[:-1])
+    assert e.value.status == "ZKB_E_ARG"
+    bad = s.public_inputs.copy()
+    bad[0] = 0xFFFFFFFF00000001
+    with pytest.raises(zkb.ZkbError) as e:
+        gc.prove(s.wires, bad)
+    assert e.value.status == "ZKB_E_ARG"
+
+
+def test_tampered_witness_gives_unverifiable_proof(zkb, oracle):
+    s = oracle.Synth(zk=False, seed=3, **oracle.Synth.TINY)
+    oc = oracle.Circuit(s.common, s.const_sigma_values)
+    gc = zkb.ProverCircuit(s.common, s.const_sigma_values, is_values=True)
+    w = s.wires.copy()
+    w[3, 2] ^= np.uint64(1)
+    got = gc.prove(w, s.public_inputs)
+    assert got == oc.prove(w, s.public_inputs)      # still bit-identical to the CPU prover ...
+    assert oc.verify(got) != ""                     # ... and, like it, not accepted
+
+
+def test_wormhole_shaped_nonzk_proof_bytes(zkb, oracle):
+    """C1': wormhole-shaped circuit, non-zk, n = 2^13 — same size as aggregator/data/dummy_proof.bin."""
+    s, oc, gc, proof = run_case(zkb, oracle, oracle.Synth.WORMHOLE, False, seed=1)
+    assert s.info["degree_bits"] == 13 and len(proof) == 132712
+
+
+def test_wormhole_shaped_zk_proof_bytes(zkb, oracle):
+    """C1: wormhole-shaped circuit, zk, n = 2^14 — same size as wormhole/bench-data/proof.bin."""
+    s, oc, gc, proof = run_case(zkb, oracle, oracle.Synth.WORMHOLE, True, seed=1)
+    assert s.info["degree_bits"] == 14 and len(proof) == 148932

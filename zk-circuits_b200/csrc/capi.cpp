@@ -1,0 +1,234 @@
+// C ABI of libzkb200.so (include/zkb200.h). No exception crosses this boundary; errors map to zkb_status.
+#include "../../include/zkb200.h"
+#include "prover.hpp"
+#include <cstring>
+#include <new>
+
+using namespace zkb;
+
+struct zkb_circuit {
+    std::unique_ptr<Circuit> impl;
+};
+
+namespace {
+thread_local std::string g_last_error;
+
+template <class F>
+int guarded(F&& f) {
+    try {
+        return f();
+    } catch (const ParseError& e) { g_last_error = e.what(); return ZKB_E_PARSE;
+    } catch (const UnsupportedError& e) { g_last_error = e.what(); return ZKB_E_UNSUPPORTED_GATE;
+    } catch (const ArgError& e) { g_last_error = e.what(); return ZKB_E_ARG;
+    } catch (const DigestError& e) { g_last_error = e.what(); return ZKB_E_DIGEST;
+    } catch (const ZetaError& e) { g_last_error = e.what(); return ZKB_E_ZETA_IN_SUBGROUP;
+    } catch (const BufferError& e) { g_last_error = e.what(); return ZKB_E_BUFFER;
+    } catch (const CudaError& e) { g_last_error = e.what(); return ZKB_E_CUDA;
+    } catch (const std::bad_alloc&) { g_last_error = "out of host memory"; return ZKB_E_ARG;
+    } catch (const std::exception& e) { g_last_error = e.what(); return ZKB_E_CUDA; }
+}
+
+void require_device(int device) {
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0)
+        throw CudaError(std::string("no CUDA device available (this library has no CPU fallback): ") + cudaGetErrorString(e));
+    if (device < 0 || device >= n) throw ArgError("bad device index");
+    cudaDeviceProp prop;
+    cuda_check(cudaGetDeviceProperties(&prop, device), "cudaGetDeviceProperties");
+    if (prop.major != 10) throw CudaError("device is not sm_100 (B200); the kernels are built for sm_100a only");
+    cuda_check(cudaSetDevice(device), "cudaSetDevice");
+    device_tables_init(device);
+}
+void check_canon(const uint64_t* v, size_t n, const char* what) {
+    for (size_t i = 0; i < n; ++i)
+        if (v[i] >= GL_P) throw ArgError(std::string(what) + ": non-canonical field element at index " + std::to_string(i));
+}
+bool is_pow2(size_t x) { return x && !(x & (x - 1)); }
+unsigned lg2(size_t x) { unsigned k = 0; while ((size_t(1) << k) < x) ++k; return k; }
+}  // namespace
+
+extern "C" {
+
+const char* zkb_version(void) { return "zkb200 0.1.0 (sm_100a)"; }
+const char* zkb_last_error(void) { return g_last_error.c_str(); }
+int zkb_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+    return n;
+}
+
+int zkb_circuit_create(const uint8_t* common_bin, size_t common_len, const uint64_t* const_sigma, int is_values,
+                       const uint64_t circuit_digest[4], int device, zkb_circuit** out) {
+    return guarded([&] {
+        if (!out) throw ArgError("out is null");
+        *out = nullptr;
+        if (!common_bin || !const_sigma) throw ArgError("null argument");
+        // parse first so that malformed inputs are reported as such even without a GPU
+        (void)parse_common_data(common_bin, common_len);
+        require_device(device);
+        auto c = std::make_unique<zkb_circuit>();
+        c->impl = std::make_unique<Circuit>(common_bin, common_len, const_sigma, is_values != 0, circuit_digest, device);
+        *out = c.release();
+        return (int)ZKB_OK;
+    });
+}
+int zkb_circuit_destroy(zkb_circuit* c) {
+    return guarded([&] { delete c; return (int)ZKB_OK; });
+}
+int zkb_circuit_verifier_only(const zkb_circuit* c, uint64_t* cap_out, size_t cap_words, uint64_t digest_out[4]) {
+    return guarded([&] {
+        if (!c) throw ArgError("circuit is null");
+        if (cap_out && cap_words < (size_t(4) << c->impl->common().cap_height)) throw BufferError(size_t(4) << c->impl->common().cap_height);
+        c->impl->verifier_only(cap_out, digest_out);
+        return (int)ZKB_OK;
+    });
+}
+size_t zkb_proof_size(const zkb_circuit* c) { return c ? c->impl->common().proof_size() : 0; }
+
+int zkb_witness_upload(zkb_circuit* c, const uint64_t* wires) {
+    return guarded([&] {
+        if (!c) throw ArgError("circuit is null");
+        c->impl->upload_witness(wires);
+        return (int)ZKB_OK;
+    });
+}
+int zkb_prove_resident(zkb_circuit* c, const uint64_t* public_inputs, size_t n_pi, const uint64_t* salts, uint64_t salt_seed,
+                       uint32_t pow_rule, uint8_t* proof_out, size_t proof_cap, size_t* proof_len) {
+    int rc = guarded([&] {
+        if (!c) throw ArgError("circuit is null");
+        size_t n = c->impl->prove_resident(public_inputs, n_pi, salts, salt_seed, pow_rule, proof_out, proof_cap);
+        if (proof_len) *proof_len = n;
+        return (int)ZKB_OK;
+    });
+    if (rc == ZKB_E_BUFFER && proof_len && c) *proof_len = c->impl->common().proof_size();
+    return rc;
+}
+int zkb_prove(zkb_circuit* c, const uint64_t* wires, const uint64_t* public_inputs, size_t n_pi, const uint64_t* salts,
+              uint64_t salt_seed, uint32_t pow_rule, uint8_t* proof_out, size_t proof_cap, size_t* proof_len) {
+    int rc = zkb_witness_upload(c, wires);
+    if (rc != ZKB_OK) return rc;
+    return zkb_prove_resident(c, public_inputs, n_pi, salts, salt_seed, pow_rule, proof_out, proof_cap, proof_len);
+}
+int zkb_last_timings(const zkb_circuit* c, float* ms_out, int cap) {
+    if (!c || !ms_out) return 0;
+    int n = cap < (int)T_COUNT ? cap : (int)T_COUNT;
+    for (int i = 0; i < n; ++i) ms_out[i] = c->impl->timings[i];
+    return n;
+}
+
+int zkb_partial_products(zkb_circuit* c, const uint64_t* wires, const uint64_t* betas, const uint64_t* gammas, uint64_t* out) {
+    return guarded([&] {
+        if (!c) throw ArgError("circuit is null");
+        c->impl->partial_products(wires, betas, gammas, out);
+        return (int)ZKB_OK;
+    });
+}
+int zkb_quotient(zkb_circuit* c, const uint64_t* wires, const uint64_t* zs_pp, const uint64_t* public_inputs, size_t n_pi,
+                 const uint64_t* betas, const uint64_t* gammas, const uint64_t* alphas, uint64_t* out) {
+    return guarded([&] {
+        if (!c) throw ArgError("circuit is null");
+        c->impl->quotient(wires, zs_pp, public_inputs, n_pi, betas, gammas, alphas, out);
+        return (int)ZKB_OK;
+    });
+}
+
+// ---- standalone stage entry points ----
+int zkb_poseidon_permute_batch(uint64_t* states, size_t count, int device) {
+    return guarded([&] {
+        if (!states && count) throw ArgError("states is null");
+        if (!count) return (int)ZKB_OK;
+        check_canon(states, count * 12, "states");
+        require_device(device);
+        DevBuf d(count * 12);
+        cuda_check(cudaMemcpy(d.get(), states, count * 96, cudaMemcpyHostToDevice), "H2D");
+        launch_poseidon_permute(d.get(), count, 0);
+        cuda_check(cudaGetLastError(), "poseidon_permute launch");
+        cuda_check(cudaMemcpy(states, d.get(), count * 96, cudaMemcpyDeviceToHost), "D2H");
+        return (int)ZKB_OK;
+    });
+}
+
+int zkb_lde_batch(const uint64_t* values, size_t ncols, size_t n, unsigned rate_bits, int from_coeffs, uint64_t* coeffs_out,
+                  uint64_t* lde_out, int device) {
+    return guarded([&] {
+        if (!ncols) return (int)ZKB_OK;                      // empty batch: nothing to do
+        if (!values) throw ArgError("values is null");
+        if (!is_pow2(n) || n < 2 || rate_bits > 4) throw ArgError("n must be a power of two >= 2 and rate_bits <= 4");
+        check_canon(values, ncols * n, "values");
+        require_device(device);
+        unsigned lg_n = lg2(n);
+        size_t N = n << rate_bits;
+        DevBuf c(ncols * n), l(lde_out ? ncols * N : 0);
+        cuda_check(cudaMemcpy(c.get(), values, ncols * n * 8, cudaMemcpyHostToDevice), "H2D");
+        if (!from_coeffs) launch_intt_natural(c.get(), n, c.get(), n, (int)ncols, lg_n, nullptr, 0);
+        if (lde_out) launch_lde(c.get(), n, l.get(), N, (int)ncols, lg_n, rate_bits, GL_GEN, 0);
+        cuda_check(cudaGetLastError(), "lde launch");
+        if (coeffs_out) cuda_check(cudaMemcpy(coeffs_out, c.get(), ncols * n * 8, cudaMemcpyDeviceToHost), "D2H coeffs");
+        if (lde_out) cuda_check(cudaMemcpy(lde_out, l.get(), ncols * N * 8, cudaMemcpyDeviceToHost), "D2H lde");
+        cuda_check(cudaDeviceSynchronize(), "sync");
+        return (int)ZKB_OK;
+    });
+}
+
+int zkb_merkle_commit(const uint64_t* leaves, size_t width, size_t num_leaves, unsigned cap_height, uint64_t* digests_out,
+                      uint64_t* cap_out, int device) {
+    return guarded([&] {
+        if (!leaves || !cap_out) throw ArgError("null argument");
+        if (!is_pow2(num_leaves) || width == 0) throw ArgError("num_leaves must be a power of two and width > 0");
+        if ((size_t(1) << cap_height) > num_leaves) throw ArgError("cap_height exceeds tree height");
+        check_canon(leaves, width * num_leaves, "leaves");
+        require_device(device);
+        DevBuf d(width * num_leaves);
+        size_t nd = merkle_digest_count(num_leaves, cap_height);
+        DevBuf dg(nd * 4);
+        cuda_check(cudaMemcpy(d.get(), leaves, width * num_leaves * 8, cudaMemcpyHostToDevice), "H2D");
+        launch_merkle_leaves(d.get(), num_leaves, (int)width, num_leaves, dg.get(), 0);
+        size_t cap_off = launch_merkle_levels(dg.get(), num_leaves, cap_height, 0);
+        cuda_check(cudaGetLastError(), "merkle launch");
+        if (digests_out) cuda_check(cudaMemcpy(digests_out, dg.get(), nd * 32, cudaMemcpyDeviceToHost), "D2H digests");
+        cuda_check(cudaMemcpy(cap_out, dg.get() + cap_off * 4, (size_t(32)) << cap_height, cudaMemcpyDeviceToHost), "D2H cap");
+        return (int)ZKB_OK;
+    });
+}
+
+int zkb_commit_batch(const uint64_t* values, size_t ncols, size_t n, unsigned rate_bits, unsigned cap_height, int reps,
+                     uint64_t* cap_out, float* times_ms, int device) {
+    return guarded([&] {
+        if (!values || !cap_out) throw ArgError("null argument");
+        if (!is_pow2(n) || n < 2 || rate_bits > 4 || !ncols) throw ArgError("bad shape");
+        if (reps < 1) reps = 1;
+        require_device(device);
+        unsigned lg_n = lg2(n);
+        size_t N = n << rate_bits;
+        if ((size_t(1) << cap_height) > N) throw ArgError("cap_height exceeds tree height");
+        DevBuf v(ncols * n), c(ncols * n), l(ncols * N);
+        size_t nd = merkle_digest_count(N, cap_height);
+        DevBuf dg(nd * 4);
+        cuda_check(cudaMemcpy(v.get(), values, ncols * n * 8, cudaMemcpyHostToDevice), "H2D");
+        cudaEvent_t e0, e1, e2;
+        cuda_check(cudaEventCreate(&e0), "event"); cuda_check(cudaEventCreate(&e1), "event"); cuda_check(cudaEventCreate(&e2), "event");
+        float t_lde = 0, t_merkle = 0;
+        size_t cap_off = 0;
+        for (int r = 0; r < reps; ++r) {
+            cuda_check(cudaEventRecord(e0, 0), "record");
+            launch_intt_natural(v.get(), n, c.get(), n, (int)ncols, lg_n, nullptr, 0);
+            launch_lde(c.get(), n, l.get(), N, (int)ncols, lg_n, rate_bits, GL_GEN, 0);
+            cuda_check(cudaEventRecord(e1, 0), "record");
+            launch_merkle_leaves(l.get(), N, (int)ncols, N, dg.get(), 0);
+            cap_off = launch_merkle_levels(dg.get(), N, cap_height, 0);
+            cuda_check(cudaEventRecord(e2, 0), "record");
+            cuda_check(cudaEventSynchronize(e2), "sync");
+            float a, b;
+            cuda_check(cudaEventElapsedTime(&a, e0, e1), "elapsed");
+            cuda_check(cudaEventElapsedTime(&b, e1, e2), "elapsed");
+            t_lde += a; t_merkle += b;
+        }
+        cudaEventDestroy(e0); cudaEventDestroy(e1); cudaEventDestroy(e2);
+        if (times_ms) { times_ms[0] = t_lde / reps; times_ms[1] = t_merkle / reps; }
+        cuda_check(cudaMemcpy(cap_out, dg.get() + cap_off * 4, (size_t(32)) << cap_height, cudaMemcpyDeviceToHost), "D2H cap");
+        return (int)ZKB_OK;
+    });
+}
+
+}  // extern "C"

@@ -1,0 +1,154 @@
+// Goldilocks field (p = 2^64 - 2^32 + 1) and its quadratic extension F_p[X]/(X^2 - 7) for sm_100a.
+// Replaces qp-plonky2-field 1.1.1 `GoldilocksField` / `QuadraticExtension` (type contract:
+// /root/reference/common/src/circuit.rs:10-12) on the device. 64-bit products are built from four
+// 32x32->64 IMAD.WIDE.U32 with 64-bit addends (no carry chains needed, see mul128), the reduction uses
+// 2^64 = 2^32 - 1 and 2^96 = -1 (mod p).
+//
+// Representation: every value handed across a kernel boundary is canonical (< p). Inside kernels the
+// "lazy" functions keep values in [0, 2^64) and canonicalise once at the end.
+#pragma once
+#include <cstdint>
+
+#if defined(__CUDACC__)
+#define ZKB_HD __host__ __device__ __forceinline__
+#define ZKB_D __device__ __forceinline__
+#else
+#define ZKB_HD inline
+#define ZKB_D inline
+#endif
+
+namespace zkb {
+
+typedef uint64_t u64;
+typedef uint32_t u32;
+
+constexpr u64 GL_P = 0xFFFFFFFF00000001ULL;
+constexpr u64 GL_EPS = 0xFFFFFFFFULL;
+constexpr u64 GL_GEN = 0xc65c18b67785d900ULL;        // multiplicative generator = coset shift
+constexpr u64 GL_TWO_ADIC_ROOT = 0x64fdd1a46201e246ULL;  // order 2^32
+constexpr u64 GL_W = 7;                               // X^2 = 7
+
+ZKB_HD u64 gl_canon(u64 a) { return a >= GL_P ? a - GL_P : a; }
+
+// a, b any u64 (value mod p); result any u64 with the same residue as a + b
+ZKB_HD u64 gl_add_lazy(u64 a, u64 b) {
+    u64 s = a + b;
+    if (s < a) {           // wrapped: add 2^64 mod p
+        s += GL_EPS;
+        if (s < GL_EPS) s += GL_EPS;
+    }
+    return s;
+}
+ZKB_HD u64 gl_sub_lazy(u64 a, u64 b) {
+    u64 d = a - b;
+    if (a < b) {           // borrowed: subtract 2^64 mod p
+        u64 e = d - GL_EPS;
+        if (d < GL_EPS) e -= GL_EPS;
+        d = e;
+    }
+    return d;
+}
+// canonical in, canonical out
+ZKB_HD u64 gl_add(u64 a, u64 b) {
+    u64 s = a + b;
+    if (s < a || s >= GL_P) s -= GL_P;
+    return s;
+}
+ZKB_HD u64 gl_sub(u64 a, u64 b) { return a >= b ? a - b : a - b + GL_P; }
+ZKB_HD u64 gl_neg(u64 a) { return a ? GL_P - a : 0; }
+
+ZKB_HD void mul128(u64 a, u64 b, u64& lo, u64& hi) {
+#if defined(__CUDA_ARCH__)
+    u32 a0 = (u32)a, a1 = (u32)(a >> 32), b0 = (u32)b, b1 = (u32)(b >> 32);
+    u64 p00 = (u64)a0 * b0;
+    u64 t = (u64)a0 * b1 + (p00 >> 32);      // cannot overflow
+    u64 t2 = (u64)a1 * b0 + (u32)t;          // cannot overflow
+    hi = (u64)a1 * b1 + (t >> 32) + (t2 >> 32);
+    lo = (t2 << 32) | (u32)p00;
+#else
+    unsigned __int128 x = (unsigned __int128)a * b;
+    lo = (u64)x;
+    hi = (u64)(x >> 64);
+#endif
+}
+
+// (hi:lo) mod p into [0, 2^64) — not necessarily canonical
+ZKB_HD u64 gl_reduce128_lazy(u64 lo, u64 hi) {
+    u64 hi_hi = hi >> 32, hi_lo = hi & GL_EPS;
+    u64 t0 = lo - hi_hi;
+    if (lo < hi_hi) t0 -= GL_EPS;
+    u64 t1 = (hi_lo << 32) - hi_lo;           // hi_lo * (2^32 - 1)
+    u64 r = t0 + t1;
+    if (r < t1) r += GL_EPS;
+    return r;
+}
+// inputs: any u64; output lazy
+ZKB_HD u64 gl_mul_lazy(u64 a, u64 b) {
+    u64 lo, hi;
+    mul128(a, b, lo, hi);
+    return gl_reduce128_lazy(lo, hi);
+}
+ZKB_HD u64 gl_mul(u64 a, u64 b) { return gl_canon(gl_mul_lazy(a, b)); }
+ZKB_HD u64 gl_sqr(u64 a) { return gl_mul(a, a); }
+
+ZKB_HD u64 gl_pow(u64 a, u64 e) {
+    u64 r = 1;
+    while (e) {
+        if (e & 1) r = gl_mul(r, a);
+        a = gl_mul(a, a);
+        e >>= 1;
+    }
+    return r;
+}
+ZKB_HD u64 gl_inv(u64 a) { return gl_pow(a, GL_P - 2); }
+inline u64 gl_root_of_unity(unsigned k) {
+    u64 r = GL_TWO_ADIC_ROOT;
+    for (unsigned i = k; i < 32; ++i) r = gl_mul(r, r);
+    return r;
+}
+
+// ---- quadratic extension, canonical components ----
+struct ext2 {
+    u64 a, b;
+};
+ZKB_HD ext2 e_make(u64 a, u64 b) { ext2 r; r.a = a; r.b = b; return r; }
+ZKB_HD ext2 e_from(u64 a) { return e_make(a, 0); }
+ZKB_HD ext2 e_add(ext2 x, ext2 y) { return e_make(gl_add(x.a, y.a), gl_add(x.b, y.b)); }
+ZKB_HD ext2 e_sub(ext2 x, ext2 y) { return e_make(gl_sub(x.a, y.a), gl_sub(x.b, y.b)); }
+ZKB_HD ext2 e_mul(ext2 x, ext2 y) {
+    u64 aa = gl_mul(x.a, y.a), bb = gl_mul(x.b, y.b);
+    u64 ab = gl_mul(x.a, y.b), ba = gl_mul(x.b, y.a);
+    return e_make(gl_add(aa, gl_mul(bb, GL_W)), gl_add(ab, ba));
+}
+ZKB_HD ext2 e_mul_base(ext2 x, u64 s) { return e_make(gl_mul(x.a, s), gl_mul(x.b, s)); }
+ZKB_HD ext2 e_inv(ext2 x) {
+    u64 norm = gl_sub(gl_sqr(x.a), gl_mul(GL_W, gl_sqr(x.b)));
+    u64 ni = gl_inv(norm);
+    return e_make(gl_mul(x.a, ni), gl_mul(gl_neg(x.b), ni));
+}
+ZKB_HD bool e_eq(ext2 x, ext2 y) { return x.a == y.a && x.b == y.b; }
+ZKB_HD ext2 e_pow2k(ext2 x, unsigned k) {
+    for (unsigned i = 0; i < k; ++i) x = e_mul(x, x);
+    return x;
+}
+ZKB_HD ext2 e_pow(ext2 x, u64 e) {
+    ext2 r = e_from(1);
+    while (e) {
+        if (e & 1) r = e_mul(r, x);
+        x = e_mul(x, x);
+        e >>= 1;
+    }
+    return r;
+}
+
+ZKB_HD u32 bitrev32(u32 x, unsigned bits) {
+#if defined(__CUDA_ARCH__)
+    return bits ? (__brev(x) >> (32 - bits)) : 0;
+#else
+    u32 r = 0;
+    for (unsigned i = 0; i < bits; ++i) r |= ((x >> i) & 1u) << (bits - 1 - i);
+    return r;
+#endif
+}
+
+}  // namespace zkb

@@ -1,0 +1,928 @@
+// sm_100a kernels for the Plonky2 proving hot path: Poseidon/Merkle (a3, a4),
+// coset LDE-NTT (a2, a5), partial products (a7), quotient (a8), openings (a9), FRI (a10-a13).
+// Integer-only; no tensor cores (nothing here is a dense contraction). Launchers are in kernels.h.
+#include "kernels.h"
+#include "poseidon.cuh"
+#include <mutex>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+namespace zkb {
+
+#define ZKB_CUDA_CHECK(x)                                                                                   \
+    do {                                                                                                    \
+        cudaError_t e_ = (x);                                                                               \
+        if (e_ != cudaSuccess)                                                                              \
+            throw std::runtime_error(std::string("CUDA error: ") + cudaGetErrorString(e_) + " at " #x);     \
+    } while (0)
+
+// ---------------------------------------------------------------------------------------------
+// device tables
+// ---------------------------------------------------------------------------------------------
+// T = 2^32-th root of unity; T^E = rootA[E & 2047] * rootB[(E >> 11) & 2047] * rootC[E >> 22]
+__device__ u64 d_rootA[2048], d_rootB[2048], d_rootC[1024];
+constexpr unsigned W_LG = 14;                       // direct twiddle table for blocks up to 2^14
+__device__ u64 d_W[1 << (W_LG - 1)];                // w_{2^14}^k
+__device__ u64 d_Winv[1 << (W_LG - 1)];             // w_{2^14}^-k
+
+ZKB_D u64 root_pow(u32 E) {
+    u64 r = gl_mul(d_rootA[E & 2047], d_rootB[(E >> 11) & 2047]);
+    return gl_mul(r, d_rootC[E >> 22]);
+}
+// w_{2^lg}^e  (e taken mod 2^lg); inverse if inv
+ZKB_D u64 root_pow_lg(unsigned lg, u32 e, bool inv) {
+    u32 E = lg == 0 ? 0u : (e << (32 - lg));
+    if (inv) E = 0u - E;
+    return root_pow(E);
+}
+
+// ---- host: regenerate the Poseidon round constants (ChaCha8, rand seed_from_u64(0)) ----
+static inline u32 rotl32(u32 x, int r) { return (x << r) | (x >> (32 - r)); }
+static void chacha8_block(const u32 key[8], u64 counter, u32 out[16]) {
+    u32 s[16] = {0x61707865, 0x3320646e, 0x79622d32, 0x6b206574};
+    for (int i = 0; i < 8; ++i) s[4 + i] = key[i];
+    s[12] = (u32)counter; s[13] = (u32)(counter >> 32); s[14] = 0; s[15] = 0;
+    u32 x[16];
+    for (int i = 0; i < 16; ++i) x[i] = s[i];
+    auto qr = [&](int a, int b, int c, int d) {
+        x[a] += x[b]; x[d] = rotl32(x[d] ^ x[a], 16);
+        x[c] += x[d]; x[b] = rotl32(x[b] ^ x[c], 12);
+        x[a] += x[b]; x[d] = rotl32(x[d] ^ x[a], 8);
+        x[c] += x[d]; x[b] = rotl32(x[b] ^ x[c], 7);
+    };
+    for (int r = 0; r < 4; ++r) {
+        qr(0, 4, 8, 12); qr(1, 5, 9, 13); qr(2, 6, 10, 14); qr(3, 7, 11, 15);
+        qr(0, 5, 10, 15); qr(1, 6, 11, 12); qr(2, 7, 8, 13); qr(3, 4, 9, 14);
+    }
+    for (int i = 0; i < 16; ++i) out[i] = x[i] + s[i];
+}
+const u64* host_round_constants() {
+    static u64 rc[P_WIDTH * P_ROUNDS];
+    static std::once_flag once;
+    std::call_once(once, [] {
+        u64 state = 0;
+        u32 key[8];
+        for (int i = 0; i < 8; ++i) {   // PCG32 seed expansion
+            state = state * 6364136223846793005ULL + 11634580027462260723ULL;
+            u32 xs = (u32)(((state >> 18) ^ state) >> 27), rot = (u32)(state >> 59);
+            key[i] = (xs >> rot) | (xs << ((32 - rot) & 31));
+        }
+        u32 blk[16];
+        int pos = 16, n = 0;
+        u64 ctr = 0;
+        auto next = [&]() { if (pos == 16) { chacha8_block(key, ctr++, blk); pos = 0; } return blk[pos++]; };
+        while (n < P_WIDTH * P_ROUNDS) {
+            u64 lo = next(), hi = next();
+            unsigned __int128 m = (unsigned __int128)(lo | (hi << 32)) * GL_P;   // uniform sample in [0, p)
+            if ((u64)m <= GL_P - 1) rc[n++] = (u64)(m >> 64);
+        }
+    });
+    return rc;
+}
+
+struct BlockNttArgs;
+struct StridedNttArgs;
+static void ntt_set_func_attributes();   // defined with the NTT kernels below
+
+void device_tables_init(int device) {
+    static std::mutex mu;
+    static std::vector<int> done;
+    std::lock_guard<std::mutex> lk(mu);
+    for (int d : done) if (d == device) return;
+    int prev = 0;
+    ZKB_CUDA_CHECK(cudaGetDevice(&prev));
+    ZKB_CUDA_CHECK(cudaSetDevice(device));
+    ZKB_CUDA_CHECK(cudaMemcpyToSymbol(c_rc, host_round_constants(), sizeof(u64) * P_WIDTH * P_ROUNDS));
+    std::vector<u64> A(2048), B(2048), C(1024);
+    u64 T = GL_TWO_ADIC_ROOT, T11 = gl_pow(T, 1u << 11), T22 = gl_pow(T, 1u << 22);
+    A[0] = B[0] = C[0] = 1;
+    for (int i = 1; i < 2048; ++i) { A[i] = gl_mul(A[i - 1], T); B[i] = gl_mul(B[i - 1], T11); }
+    for (int i = 1; i < 1024; ++i) C[i] = gl_mul(C[i - 1], T22);
+    ZKB_CUDA_CHECK(cudaMemcpyToSymbol(d_rootA, A.data(), 2048 * 8));
+    ZKB_CUDA_CHECK(cudaMemcpyToSymbol(d_rootB, B.data(), 2048 * 8));
+    ZKB_CUDA_CHECK(cudaMemcpyToSymbol(d_rootC, C.data(), 1024 * 8));
+    size_t half = size_t(1) << (W_LG - 1);
+    std::vector<u64> W(half), Wi(half);
+    u64 w = gl_root_of_unity(W_LG), wi = gl_inv(w);
+    W[0] = Wi[0] = 1;
+    for (size_t i = 1; i < half; ++i) { W[i] = gl_mul(W[i - 1], w); Wi[i] = gl_mul(Wi[i - 1], wi); }
+    ZKB_CUDA_CHECK(cudaMemcpyToSymbol(d_W, W.data(), half * 8));
+    ZKB_CUDA_CHECK(cudaMemcpyToSymbol(d_Winv, Wi.data(), half * 8));
+    ntt_set_func_attributes();
+    ZKB_CUDA_CHECK(cudaSetDevice(prev));
+    done.push_back(device);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Poseidon / Merkle
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) poseidon_permute_kernel(u64* states, size_t count) {
+    size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    u64 s[12];
+#pragma unroll
+    for (int k = 0; k < 12; ++k) s[k] = states[i * 12 + k];
+    poseidon_permute(s);
+#pragma unroll
+    for (int k = 0; k < 12; ++k) states[i * 12 + k] = gl_canon(s[k]);
+}
+void launch_poseidon_permute(u64* states, size_t count, cudaStream_t st) {
+    if (!count) return;
+    poseidon_permute_kernel<<<(unsigned)((count + 127) / 128), 128, 0, st>>>(states, count);
+}
+
+ZKB_D void store_digest(u64* digests, size_t idx, const u64* s) {
+    ulonglong2* p = reinterpret_cast<ulonglong2*>(digests + idx * 4);
+    p[0] = make_ulonglong2(gl_canon(s[0]), gl_canon(s[1]));
+    p[1] = make_ulonglong2(gl_canon(s[2]), gl_canon(s[3]));
+}
+
+// one leaf per thread; column-major reads are coalesced across the warp
+__global__ void __launch_bounds__(128) merkle_leaves_kernel(const u64* __restrict__ leaves, size_t col_stride, int width,
+                                                            size_t num_leaves, u64* __restrict__ digests) {
+    size_t l = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if (l >= num_leaves) return;
+    u64 s[12];
+#pragma unroll
+    for (int k = 0; k < 12; ++k) s[k] = 0;
+    if (width <= 4) {   // hash_or_noop: short leaves are copied, not hashed
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+            if (c < width) s[c] = leaves[(size_t)c * col_stride + l];
+        store_digest(digests, l, s);
+        return;
+    }
+    const u64* p = leaves + l;
+    int c = 0;
+    for (; c + 8 <= width; c += 8) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) s[k] = __ldg(p + (size_t)(c + k) * col_stride);
+        poseidon_permute(s);
+    }
+    if (c < width) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+            if (c + k < width) s[k] = __ldg(p + (size_t)(c + k) * col_stride);
+        poseidon_permute(s);
+    }
+    store_digest(digests, l, s);
+}
+void launch_merkle_leaves(const u64* leaves, size_t col_stride, int width, size_t num_leaves, u64* digests, cudaStream_t st) {
+    if (!num_leaves) return;
+    merkle_leaves_kernel<<<(unsigned)((num_leaves + 127) / 128), 128, 0, st>>>(leaves, col_stride, width, num_leaves, digests);
+}
+
+__global__ void __launch_bounds__(128) merkle_leaves_ext_kernel(const u64* __restrict__ a, const u64* __restrict__ b, int arity,
+                                                                size_t num_leaves, u64* __restrict__ digests) {
+    size_t l = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if (l >= num_leaves) return;
+    u64 s[12];
+#pragma unroll
+    for (int k = 0; k < 12; ++k) s[k] = 0;
+    const u64* pa = a + l * arity;
+    const u64* pb = b + l * arity;
+    int width = 2 * arity;
+    if (width <= 4) {
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+            if (c < width) s[c] = (c & 1) ? pb[c >> 1] : pa[c >> 1];
+        store_digest(digests, l, s);
+        return;
+    }
+    for (int c = 0; c < width; c += 8) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+            if (c + k < width) s[k] = (k & 1) ? pb[(c + k) >> 1] : pa[(c + k) >> 1];
+        poseidon_permute(s);
+    }
+    store_digest(digests, l, s);
+}
+void launch_merkle_leaves_ext(const u64* a, const u64* b, int arity, size_t num_leaves, u64* digests, cudaStream_t st) {
+    if (!num_leaves) return;
+    merkle_leaves_ext_kernel<<<(unsigned)((num_leaves + 127) / 128), 128, 0, st>>>(a, b, arity, num_leaves, digests);
+}
+
+// one parent per thread: parent = permute(left ‖ right ‖ 0000)[0..4]
+__global__ void __launch_bounds__(128) merkle_level_kernel(const u64* __restrict__ in, u64* __restrict__ out, size_t n_out) {
+    size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if (i >= n_out) return;
+    const ulonglong2* p = reinterpret_cast<const ulonglong2*>(in + i * 8);
+    ulonglong2 v0 = p[0], v1 = p[1], v2 = p[2], v3 = p[3];
+    u64 s[12] = {v0.x, v0.y, v1.x, v1.y, v2.x, v2.y, v3.x, v3.y, 0, 0, 0, 0};
+    poseidon_permute(s);
+    store_digest(out, i, s);
+}
+size_t merkle_level_offset(size_t num_leaves, unsigned level) {
+    size_t off = 0;
+    for (unsigned k = 0; k < level; ++k) off += num_leaves >> k;
+    return off;
+}
+size_t merkle_digest_count(size_t num_leaves, unsigned cap_height) {
+    unsigned lg = 0;
+    while ((size_t(1) << lg) < num_leaves) ++lg;
+    unsigned levels = lg >= cap_height ? lg - cap_height : 0;
+    return merkle_level_offset(num_leaves, levels + 1);
+}
+size_t launch_merkle_levels(u64* digests, size_t num_leaves, unsigned cap_height, cudaStream_t st) {
+    unsigned lg = 0;
+    while ((size_t(1) << lg) < num_leaves) ++lg;
+    size_t off = 0;
+    for (unsigned k = 0; k + cap_height < lg; ++k) {
+        size_t n_in = num_leaves >> k, n_out = n_in >> 1;
+        merkle_level_kernel<<<(unsigned)((n_out + 127) / 128), 128, 0, st>>>(digests + off * 4, digests + (off + n_in) * 4, n_out);
+        off += n_in;
+    }
+    return off;
+}
+
+// ---------------------------------------------------------------------------------------------
+// salts (documented generator shared with the oracle: oracle/prover.hpp salt_value)
+// ---------------------------------------------------------------------------------------------
+ZKB_HD u64 splitmix64_finalize(u64 z) {
+    z = (z ^ (z >> 30)) * 0xbf58476d1ce4e5b9ULL;
+    z = (z ^ (z >> 27)) * 0x94d049bb133111ebULL;
+    return z ^ (z >> 31);
+}
+__global__ void salt_fill_kernel(u64* out, size_t stride, size_t num_leaves, u64 seed, unsigned batch) {
+    size_t l = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    unsigned s = blockIdx.y;
+    if (l >= num_leaves) return;
+    u64 z = seed + 0x9e3779b97f4a7c15ULL * (u64)(batch * 4 + s + 1) + l;
+    out[(size_t)s * stride + l] = gl_canon(splitmix64_finalize(z + 0x9e3779b97f4a7c15ULL));
+}
+void launch_salt_fill(u64* out, size_t stride, size_t num_leaves, u64 seed, unsigned batch, cudaStream_t st) {
+    dim3 grid((unsigned)((num_leaves + 255) / 256), 4);
+    salt_fill_kernel<<<grid, 256, 0, st>>>(out, stride, num_leaves, seed, batch);
+}
+
+// ---------------------------------------------------------------------------------------------
+// NTT family (v0: radix-2 stages in shared memory; blocks up to 2^14, strided pass above that)
+// ---------------------------------------------------------------------------------------------
+constexpr unsigned NTT_MAX_LB = 14;
+
+struct BlockNttArgs {
+    const u64* src; size_t src_stride;
+    u64* dst; size_t dst_stride;
+    unsigned lb;           // log2 block size (block = contiguous run of 2^lb elements)
+    unsigned blocks_per_col;
+    int dit;               // 0: DIF (natural in -> bit-reversed out), 1: DIT (bit-reversed in -> natural out)
+    int inverse;           // use inverse twiddles
+    int store_bitrev;      // dst[k] = result[bitrev(k)] within the block
+    u64 scale;             // multiply every output by this (1 = skip)
+};
+
+__global__ void __launch_bounds__(1024) ntt_block_kernel(BlockNttArgs a) {
+    extern __shared__ u64 sm[];
+    const unsigned mb = 1u << a.lb;
+    const u64* src = a.src + (size_t)blockIdx.y * a.src_stride + (size_t)blockIdx.x * mb;
+    u64* dst = a.dst + (size_t)blockIdx.y * a.dst_stride + (size_t)blockIdx.x * mb;
+    for (unsigned i = threadIdx.x; i < mb; i += blockDim.x) sm[i] = src[i];
+    __syncthreads();
+    const u64* W = a.inverse ? d_Winv : d_W;
+    const unsigned half = mb >> 1;
+    if (!a.dit) {
+        for (unsigned lh = a.lb; lh-- > 0;) {
+            unsigned h = 1u << lh;
+            for (unsigned p = threadIdx.x; p < half; p += blockDim.x) {
+                unsigned j = p & (h - 1);
+                unsigned i = ((p >> lh) << (lh + 1)) + j;
+                u64 x = sm[i], y = sm[i + h];
+                u64 tw = W[j << (W_LG - 1 - lh)];
+                sm[i] = gl_add(x, y);
+                sm[i + h] = gl_mul(gl_sub(x, y), tw);
+            }
+            __syncthreads();
+        }
+    } else {
+        for (unsigned lh = 0; lh < a.lb; ++lh) {
+            unsigned h = 1u << lh;
+            for (unsigned p = threadIdx.x; p < half; p += blockDim.x) {
+                unsigned j = p & (h - 1);
+                unsigned i = ((p >> lh) << (lh + 1)) + j;
+                u64 tw = W[j << (W_LG - 1 - lh)];
+                u64 x = sm[i], y = gl_mul(sm[i + h], tw);
+                sm[i] = gl_add(x, y);
+                sm[i + h] = gl_sub(x, y);
+            }
+            __syncthreads();
+        }
+    }
+    for (unsigned i = threadIdx.x; i < mb; i += blockDim.x) {
+        u64 v = a.store_bitrev ? sm[bitrev32(i, a.lb)] : sm[i];
+        if (a.scale != 1) v = gl_mul(v, a.scale);
+        dst[i] = v;
+    }
+}
+
+struct StridedNttArgs {
+    u64* data; size_t stride;
+    unsigned lg_m;      // log2 transform size
+    unsigned lb;        // log2 of the contiguous block handled by the block kernel; this pass does h >= 2^lb
+    unsigned ltb;       // log2 tile width (consecutive elements per row)
+    int dit, inverse;
+};
+__global__ void __launch_bounds__(1024) ntt_strided_kernel(StridedNttArgs a) {
+    extern __shared__ u64 sm[];
+    const unsigned lT = a.lg_m - a.lb, T = 1u << lT, TB = 1u << a.ltb, mb = 1u << a.lb;
+    u64* col = a.data + (size_t)blockIdx.y * a.stride;
+    const unsigned b0 = blockIdx.x << a.ltb;
+    const unsigned tot = T << a.ltb;
+    for (unsigned idx = threadIdx.x; idx < tot; idx += blockDim.x) {
+        unsigned t = idx >> a.ltb, bb = idx & (TB - 1);
+        sm[idx] = col[(size_t)t * mb + b0 + bb];
+    }
+    __syncthreads();
+    const unsigned npairs = tot >> 1;
+    for (unsigned s = 0; s < lT; ++s) {
+        unsigned lg = a.dit ? s : (lT - 1 - s);          // g = 2^lg rows apart
+        unsigned g = 1u << lg;
+        unsigned lh = lg + a.lb;                         // h = g * mb
+        for (unsigned pidx = threadIdx.x; pidx < npairs; pidx += blockDim.x) {
+            unsigned bb = pidx & (TB - 1), pp = pidx >> a.ltb;
+            unsigned tj = pp & (g - 1);
+            unsigned t = ((pp >> lg) << (lg + 1)) + tj;
+            unsigned i0 = (t << a.ltb) + bb, i1 = i0 + (g << a.ltb);
+            u32 e = tj * mb + b0 + bb;                   // exponent of w_{2h}
+            u64 tw = root_pow_lg(lh + 1, e, a.inverse);
+            u64 x = sm[i0], y = sm[i1];
+            if (!a.dit) {
+                sm[i0] = gl_add(x, y);
+                sm[i1] = gl_mul(gl_sub(x, y), tw);
+            } else {
+                y = gl_mul(y, tw);
+                sm[i0] = gl_add(x, y);
+                sm[i1] = gl_sub(x, y);
+            }
+        }
+        __syncthreads();
+    }
+    for (unsigned idx = threadIdx.x; idx < tot; idx += blockDim.x) {
+        unsigned t = idx >> a.ltb, bb = idx & (TB - 1);
+        col[(size_t)t * mb + b0 + bb] = sm[idx];
+    }
+}
+
+static void ntt_set_func_attributes() {   // per device: opt in to > 48 KB dynamic shared memory
+    ZKB_CUDA_CHECK(cudaFuncSetAttribute(ntt_block_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(u64) << NTT_MAX_LB)));
+    ZKB_CUDA_CHECK(cudaFuncSetAttribute(ntt_strided_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+}
+static void run_block_pass(const BlockNttArgs& a, int ncols, cudaStream_t st) {
+    unsigned mb = 1u << a.lb;
+    unsigned threads = mb / 2 < 1024 ? (mb / 2 < 32 ? 32 : mb / 2) : 1024;
+    dim3 grid(a.blocks_per_col, (unsigned)ncols);
+    ntt_block_kernel<<<grid, threads, sizeof(u64) * mb, st>>>(a);
+}
+static void run_strided_pass(u64* data, size_t stride, int ncols, unsigned lg_m, unsigned lb, bool dit, bool inverse, cudaStream_t st) {
+    unsigned lT = lg_m - lb;
+    if (lT > 12) throw std::runtime_error("NTT size too large for the two-pass decomposition");
+    unsigned ltb = lT >= 12 ? 1 : (12 - lT);        // tile = 4096 elements (32 KB) ...
+    if (ltb < 4 && lT <= 9) ltb = 4;                // ... but keep >= 128 B per row when it fits 64 KB
+    if (ltb > lb) ltb = lb;
+    StridedNttArgs a{data, stride, lg_m, lb, ltb, dit ? 1 : 0, inverse ? 1 : 0};
+    size_t smem = sizeof(u64) << (lT + ltb);
+    dim3 grid(1u << (lb - ltb), (unsigned)ncols);
+    ntt_strided_kernel<<<grid, 1024, smem, st>>>(a);
+}
+
+// in-place bit-reversal permutation with scaling
+__global__ void bitrev_scale_kernel(u64* data, size_t stride, unsigned lg_n, u64 scale) {
+    size_t k = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if (k >= (size_t(1) << lg_n)) return;
+    u64* col = data + (size_t)blockIdx.y * stride;
+    size_t r = bitrev32((u32)k, lg_n);
+    if (k < r) {
+        u64 x = col[k], y = col[r];
+        col[k] = gl_mul(y, scale);
+        col[r] = gl_mul(x, scale);
+    } else if (k == r) {
+        col[k] = gl_mul(col[k], scale);
+    }
+}
+
+void launch_bitrev_permute(u64* data, size_t stride, int ncols, unsigned lg_n, cudaStream_t st) {
+    if (ncols <= 0) return;
+    dim3 grid((unsigned)(((size_t(1) << lg_n) + 255) / 256), (unsigned)ncols);
+    bitrev_scale_kernel<<<grid, 256, 0, st>>>(data, stride, lg_n, 1);
+}
+
+void launch_intt_natural(const u64* src, size_t src_stride, u64* dst, size_t dst_stride, int ncols, unsigned lg_n,
+                         u64* scratch, cudaStream_t st) {
+    (void)scratch;
+    if (ncols <= 0) return;
+    u64 ninv = gl_inv(u64(1) << lg_n);
+    if (lg_n <= NTT_MAX_LB) {
+        BlockNttArgs a{src, src_stride, dst, dst_stride, lg_n, 1, 0, 1, 1, ninv};
+        run_block_pass(a, ncols, st);
+        return;
+    }
+    if (src != dst)
+        ZKB_CUDA_CHECK(cudaMemcpy2DAsync(dst, dst_stride * 8, src, src_stride * 8, (size_t(8) << lg_n), ncols, cudaMemcpyDeviceToDevice, st));
+    unsigned lb = 13;
+    run_strided_pass(dst, dst_stride, ncols, lg_n, lb, false, true, st);
+    BlockNttArgs a{dst, dst_stride, dst, dst_stride, lb, 1u << (lg_n - lb), 0, 1, 0, 1};
+    run_block_pass(a, ncols, st);
+    dim3 grid((unsigned)(((size_t(1) << lg_n) + 255) / 256), (unsigned)ncols);
+    bitrev_scale_kernel<<<grid, 256, 0, st>>>(dst, dst_stride, lg_n, ninv);
+}
+
+// out[c][jb * n + k] = coeff[c][k] * (shift * w_M^j)^k, j = bitrev_r(jb)
+__global__ void lde_prescale_kernel(const u64* __restrict__ coeffs, size_t coeff_stride, u64* __restrict__ out, size_t out_stride,
+                                    int ncols, unsigned lg_n, unsigned rate_bits, u64 shift, int cols_per_group) {
+    size_t k = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    size_t n = size_t(1) << lg_n;
+    if (k >= n) return;
+    u64 sk = gl_pow(shift, k);
+    int c0 = blockIdx.y * cols_per_group, c1 = min(ncols, c0 + cols_per_group);
+    unsigned lgM = lg_n + rate_bits;
+    for (unsigned jb = 0; jb < (1u << rate_bits); ++jb) {
+        unsigned j = bitrev32(jb, rate_bits);
+        u64 m = gl_mul(sk, root_pow_lg(lgM, (u32)(((u64)j * k) & ((u64(1) << lgM) - 1)), false));
+        for (int c = c0; c < c1; ++c)
+            out[(size_t)c * out_stride + (size_t)jb * n + k] = gl_mul(coeffs[(size_t)c * coeff_stride + k], m);
+    }
+}
+
+void launch_lde(const u64* coeffs, size_t coeff_stride, u64* out, size_t out_stride, int ncols, unsigned lg_n,
+                unsigned rate_bits, u64 shift, cudaStream_t st) {
+    if (ncols <= 0) return;
+    size_t n = size_t(1) << lg_n;
+    int groups = ncols < 8 ? ncols : 8;
+    int cpg = (ncols + groups - 1) / groups;
+    dim3 grid((unsigned)((n + 127) / 128), (unsigned)((ncols + cpg - 1) / cpg));
+    lde_prescale_kernel<<<grid, 128, 0, st>>>(coeffs, coeff_stride, out, out_stride, ncols, lg_n, rate_bits, shift, cpg);
+    unsigned nblk = 1u << rate_bits;
+    if (lg_n <= NTT_MAX_LB) {
+        BlockNttArgs a{out, out_stride, out, out_stride, lg_n, nblk, 0, 0, 0, 1};
+        run_block_pass(a, ncols, st);
+    } else {
+        unsigned lb = 13;
+        // each of the 2^rate_bits coset blocks is an independent size-n transform: treat them as extra columns
+        for (unsigned jb = 0; jb < nblk; ++jb)
+            run_strided_pass(out + (size_t)jb * n, out_stride, ncols, lg_n, lb, false, false, st);
+        BlockNttArgs a{out, out_stride, out, out_stride, lb, nblk << (lg_n - lb), 0, 0, 0, 1};
+        run_block_pass(a, ncols, st);
+    }
+}
+
+// data[k] *= c0 * base^k
+__global__ void scale_pows_kernel(u64* data, size_t stride, int ncols, size_t m, u64 c0, u64 base) {
+    size_t k = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if (k >= m) return;
+    u64 f = gl_mul(c0, gl_pow(base, k));
+    for (int c = 0; c < ncols; ++c) data[(size_t)c * stride + k] = gl_mul(data[(size_t)c * stride + k], f);
+}
+
+void launch_coset_intt_bitrev(u64* data, size_t stride, int ncols, unsigned lg_m, u64 shift, cudaStream_t st) {
+    if (ncols <= 0) return;
+    unsigned lb = lg_m <= NTT_MAX_LB ? lg_m : 13;
+    BlockNttArgs a{data, stride, data, stride, lb, 1u << (lg_m - lb), 1, 1, 0, 1};
+    run_block_pass(a, ncols, st);
+    if (lg_m > lb) run_strided_pass(data, stride, ncols, lg_m, lb, true, true, st);
+    size_t m = size_t(1) << lg_m;
+    scale_pows_kernel<<<(unsigned)((m + 255) / 256), 256, 0, st>>>(data, stride, ncols, m, gl_inv(u64(1) << lg_m), gl_inv(shift));
+}
+
+
+// ---------------------------------------------------------------------------------------------
+// Partial products and Z: per-row chunk quotients, exact parallel prefix product
+// ---------------------------------------------------------------------------------------------
+struct PPArgs {
+    const u64* wires; size_t wire_stride;
+    const u64* sigmas; size_t sigma_stride;
+    const u64* k_is;
+    int num_routed, chunk, nchunks, nch;
+    unsigned lg_n;
+    u64 betas[4], gammas[4];
+    u64* chunkprod;   // [nch][nchunks][n]
+    u64* rowtot;      // [nch][n]
+    u64* prefix;      // [nch][n]
+    u64* out; size_t out_stride;
+};
+
+__global__ void __launch_bounds__(128) pp_chunk_kernel(PPArgs a) {
+    size_t n = size_t(1) << a.lg_n;
+    size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    int ch = blockIdx.y;
+    if (i >= n) return;
+    u64 beta = a.betas[ch], gamma = a.gammas[ch];
+    u64 bx = gl_mul(beta, root_pow_lg(a.lg_n, (u32)i, false));
+    u64 tot = 1;
+    for (int k = 0; k < a.nchunks; ++k) {
+        u64 num = 1, den = 1;
+        int j1 = min(a.num_routed, (k + 1) * a.chunk);
+        for (int j = k * a.chunk; j < j1; ++j) {
+            u64 w = a.wires[(size_t)j * a.wire_stride + i];
+            u64 wg = gl_add(w, gamma);
+            num = gl_mul(num, gl_add(wg, gl_mul(bx, a.k_is[j])));
+            den = gl_mul(den, gl_add(wg, gl_mul(beta, a.sigmas[(size_t)j * a.sigma_stride + i])));
+        }
+        u64 q = gl_mul(num, gl_inv(den));
+        a.chunkprod[((size_t)ch * a.nchunks + k) * n + i] = q;
+        tot = gl_mul(tot, q);
+    }
+    a.rowtot[(size_t)ch * n + i] = tot;
+}
+
+// exclusive prefix product over n rows, one CTA per challenge
+__global__ void __launch_bounds__(1024) pp_scan_kernel(PPArgs a) {
+    __shared__ u64 part[1024];
+    size_t n = size_t(1) << a.lg_n;
+    int ch = blockIdx.x;
+    const u64* in = a.rowtot + (size_t)ch * n;
+    u64* out = a.prefix + (size_t)ch * n;
+    unsigned nt = blockDim.x;
+    size_t ipt = n / nt;                 // launcher guarantees nt | n
+    size_t lo = threadIdx.x * ipt;
+    u64 p = 1;
+    for (size_t k = 0; k < ipt; ++k) p = gl_mul(p, in[lo + k]);
+    part[threadIdx.x] = p;
+    __syncthreads();
+    for (unsigned d = 1; d < nt; d <<= 1) {      // Hillis-Steele inclusive scan (exact: field mult is associative)
+        u64 v = part[threadIdx.x];
+        if (threadIdx.x >= d) v = gl_mul(v, part[threadIdx.x - d]);
+        __syncthreads();
+        part[threadIdx.x] = v;
+        __syncthreads();
+    }
+    u64 acc = threadIdx.x ? part[threadIdx.x - 1] : 1;
+    for (size_t k = 0; k < ipt; ++k) {
+        out[lo + k] = acc;
+        acc = gl_mul(acc, in[lo + k]);
+    }
+}
+
+__global__ void __launch_bounds__(128) pp_finalize_kernel(PPArgs a) {
+    size_t n = size_t(1) << a.lg_n;
+    size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    int ch = blockIdx.y;
+    if (i >= n) return;
+    u64 z = a.prefix[(size_t)ch * n + i];
+    a.out[(size_t)ch * a.out_stride + i] = z;
+    int npp = a.nchunks - 1;
+    u64 acc = z;
+    for (int k = 0; k < npp; ++k) {
+        acc = gl_mul(acc, a.chunkprod[((size_t)ch * a.nchunks + k) * n + i]);
+        a.out[(size_t)(a.nch + ch * npp + k) * a.out_stride + i] = acc;
+    }
+}
+
+size_t partial_products_scratch_words(int num_routed, int chunk, int num_challenges, unsigned lg_n) {
+    size_t nchunks = (num_routed + chunk - 1) / chunk;
+    return (size_t)num_challenges * (nchunks + 2) << lg_n;
+}
+void launch_partial_products(const u64* wires, size_t wire_stride, const u64* sigma_values, size_t sigma_stride,
+                             const u64* k_is_dev, int num_routed, int chunk, int num_challenges, const u64* betas_gammas,
+                             unsigned lg_n, u64* out, size_t out_stride, u64* scratch, cudaStream_t st) {
+    PPArgs a;
+    a.wires = wires; a.wire_stride = wire_stride; a.sigmas = sigma_values; a.sigma_stride = sigma_stride;
+    a.k_is = k_is_dev; a.num_routed = num_routed; a.chunk = chunk; a.nchunks = (num_routed + chunk - 1) / chunk;
+    a.nch = num_challenges; a.lg_n = lg_n;
+    for (int c = 0; c < num_challenges; ++c) { a.betas[c] = betas_gammas[c]; a.gammas[c] = betas_gammas[num_challenges + c]; }
+    size_t n = size_t(1) << lg_n;
+    a.chunkprod = scratch;
+    a.rowtot = scratch + (size_t)num_challenges * a.nchunks * n;
+    a.prefix = a.rowtot + (size_t)num_challenges * n;
+    a.out = out; a.out_stride = out_stride;
+    dim3 grid((unsigned)((n + 127) / 128), (unsigned)num_challenges);
+    pp_chunk_kernel<<<grid, 128, 0, st>>>(a);
+    unsigned nt = n < 1024 ? (unsigned)n : 1024;
+    pp_scan_kernel<<<num_challenges, nt, 0, st>>>(a);
+    pp_finalize_kernel<<<grid, 128, 0, st>>>(a);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Quotient: vanishing polynomial at every LDE point / Z_H, gate set interpreted from
+// the circuit's gate list (warp-uniform dispatch). Gate formulas: SURVEY App. C.1.
+// ---------------------------------------------------------------------------------------------
+constexpr u32 TAG_ARITHMETIC = 0, TAG_BASE_SUM = 2, TAG_CONSTANT = 3, TAG_NOOP = 9, TAG_POSEIDON = 11, TAG_PUBLIC_INPUT = 12;
+
+struct QuotientArgs {
+    const QuotientParams* p;
+    const u64* apow;            // [nch][nterms] powers of alpha
+    int nterms;
+    const u64* cs; size_t cs_stride;
+    const u64* w; size_t w_stride;
+    const u64* z; size_t z_stride;
+    u64* out; size_t out_stride;
+};
+
+__global__ void __launch_bounds__(128) quotient_kernel(QuotientArgs a) {
+    const QuotientParams& P = *a.p;
+    const unsigned lgN = P.lg_n + P.rate_bits;
+    const size_t N = size_t(1) << lgN;
+    size_t l = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if (l >= N) return;
+    const u32 i = bitrev32((u32)l, lgN);
+    const u32 rate_mask = (1u << P.rate_bits) - 1;
+    const size_t l_next = bitrev32((u32)((i + (1u << P.rate_bits)) & (N - 1)), lgN);
+    const u64 x = gl_mul(GL_GEN, root_pow_lg(lgN, i, false));
+    const int nch = P.num_challenges, npp = P.num_partial_products, nchunks = npp + 1, chunk = P.qdf;
+    const u64* cs = a.cs + l;
+    const u64* w = a.w + l;
+    const u64* z = a.z + l;
+    const u64* apow0 = a.apow;
+    const u64* apow1 = a.apow + a.nterms;
+    u64 acc0 = 0, acc1 = 0;      // results for challenge 0 / 1 (nch <= 2 supported)
+    int term = 0;
+    auto add_term = [&](u64 t) {
+        acc0 = gl_add(acc0, gl_mul(t, apow0[term]));
+        if (nch > 1) acc1 = gl_add(acc1, gl_mul(t, apow1[term]));
+        ++term;
+    };
+    // L0(x) (Z - 1)
+    u64 l0 = gl_mul(P.zh[i & rate_mask], gl_inv(gl_mul(gl_canon(u64(1) << P.lg_n), gl_sub(x, 1))));
+    for (int ch = 0; ch < nch; ++ch) add_term(gl_mul(l0, gl_sub(z[(size_t)ch * a.z_stride], 1)));
+    // partial product checks
+    for (int ch = 0; ch < nch; ++ch) {
+        u64 beta = P.betas[ch], gamma = P.gammas[ch];
+        u64 bx = gl_mul(beta, x);
+        u64 prev = z[(size_t)ch * a.z_stride];
+        for (int k = 0; k < nchunks; ++k) {
+            u64 next = k < npp ? z[(size_t)(nch + ch * npp + k) * a.z_stride] : a.z[(size_t)ch * a.z_stride + l_next];
+            u64 num = 1, den = 1;
+            int j1 = min(P.num_routed, (k + 1) * chunk);
+            for (int j = k * chunk; j < j1; ++j) {
+                u64 wg = gl_add(w[(size_t)j * a.w_stride], gamma);
+                num = gl_mul(num, gl_add(wg, gl_mul(bx, P.k_is[j])));
+                den = gl_mul(den, gl_add(wg, gl_mul(beta, cs[(size_t)(P.num_constants + j) * a.cs_stride])));
+            }
+            add_term(gl_sub(gl_mul(prev, num), gl_mul(next, den)));
+            prev = next;
+        }
+    }
+    // gate constraints, filtered
+    const int goff = term;
+    const int nsel = P.num_selectors;
+    for (int g = 0; g < P.num_gates; ++g) {
+        const GateDesc gd = P.gates[g];
+        u64 s = cs[(size_t)gd.selector_index * a.cs_stride];
+        u64 filter = 1;
+        for (u32 r = gd.group_lo; r < gd.group_hi; ++r)
+            if (r != gd.row) filter = gl_mul(filter, gl_sub((u64)r, s));
+        if (nsel > 1) filter = gl_mul(filter, gl_sub(0xFFFFFFFFULL, s));
+        u64 g0 = 0, g1 = 0;
+        int k = goff;
+        auto add_c = [&](u64 c) {     // c lazy
+            g0 = gl_add(g0, gl_mul(c, apow0[k]));
+            if (nch > 1) g1 = gl_add(g1, gl_mul(c, apow1[k]));
+            ++k;
+        };
+        auto W = [&](int j) { return w[(size_t)j * a.w_stride]; };
+        auto K = [&](int j) { return cs[(size_t)(nsel + j) * a.cs_stride]; };
+        switch (gd.tag) {
+            case TAG_NOOP: break;
+            case TAG_CONSTANT:
+                for (u32 j = 0; j < gd.param; ++j) add_c(gl_sub(K(j), W(j)));
+                break;
+            case TAG_PUBLIC_INPUT:
+                for (int j = 0; j < 4; ++j) add_c(gl_sub(W(j), P.pi_hash[j]));
+                break;
+            case TAG_BASE_SUM: {
+                u64 sum = 0;
+                for (int j = (int)gd.param; j-- > 0;) sum = gl_add(gl_add(sum, sum), W(1 + j));
+                add_c(gl_sub(sum, W(0)));
+                for (u32 j = 0; j < gd.param; ++j) { u64 b = W(1 + j); add_c(gl_mul(b, gl_sub(b, 1))); }
+                break;
+            }
+            case TAG_ARITHMETIC: {
+                u64 c0 = K(0), c1 = K(1);
+                for (u32 j = 0; j < gd.param; ++j) {
+                    u64 prod = gl_mul(gl_mul(W(4 * j), W(4 * j + 1)), c0);
+                    add_c(gl_sub(W(4 * j + 3), gl_add(prod, gl_mul(W(4 * j + 2), c1))));
+                }
+                break;
+            }
+            case TAG_POSEIDON: {
+                u64 swap = W(24);
+                add_c(gl_mul(swap, gl_sub(swap, 1)));
+                u64 st[12];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    u64 lhs = W(j), rhs = W(j + 4), d = W(25 + j);
+                    add_c(gl_sub(gl_mul(swap, gl_sub(rhs, lhs)), d));
+                    st[j] = gl_add(lhs, d);
+                    st[j + 4] = gl_sub(rhs, d);
+                }
+#pragma unroll
+                for (int j = 8; j < 12; ++j) st[j] = W(j);
+                int rc = 0;
+#pragma unroll 1
+                for (int r = 0; r < P_HALF_FULL; ++r) {
+#pragma unroll
+                    for (int j = 0; j < 12; ++j) st[j] = gl_add_lazy(st[j], c_rc[rc + j]);
+                    if (r != 0) {
+#pragma unroll
+                        for (int j = 0; j < 12; ++j) {
+                            u64 sin = W(29 + 12 * (r - 1) + j);
+                            add_c(gl_sub_lazy(st[j], sin));
+                            st[j] = sin;
+                        }
+                    }
+#pragma unroll
+                    for (int j = 0; j < 12; ++j) st[j] = gl_sbox7(st[j]);
+                    mds_layer(st);
+                    rc += 12;
+                }
+#pragma unroll 1
+                for (int r = 0; r < P_PARTIAL; ++r) {
+#pragma unroll
+                    for (int j = 0; j < 12; ++j) st[j] = gl_add_lazy(st[j], c_rc[rc + j]);
+                    u64 sin = W(65 + r);
+                    add_c(gl_sub_lazy(st[0], sin));
+                    st[0] = gl_sbox7(sin);
+                    mds_layer(st);
+                    rc += 12;
+                }
+#pragma unroll 1
+                for (int r = 0; r < P_HALF_FULL; ++r) {
+#pragma unroll
+                    for (int j = 0; j < 12; ++j) st[j] = gl_add_lazy(st[j], c_rc[rc + j]);
+#pragma unroll
+                    for (int j = 0; j < 12; ++j) {
+                        u64 sin = W(87 + 12 * r + j);
+                        add_c(gl_sub_lazy(st[j], sin));
+                        st[j] = sin;
+                    }
+#pragma unroll
+                    for (int j = 0; j < 12; ++j) st[j] = gl_sbox7(st[j]);
+                    mds_layer(st);
+                    rc += 12;
+                }
+#pragma unroll
+                for (int j = 0; j < 12; ++j) add_c(gl_sub_lazy(st[j], W(12 + j)));
+                break;
+            }
+            default: break;   // rejected on the host (ZKB_E_UNSUPPORTED_GATE)
+        }
+        acc0 = gl_add(acc0, gl_mul(filter, g0));
+        if (nch > 1) acc1 = gl_add(acc1, gl_mul(filter, g1));
+    }
+    u64 zi = P.zh_inv[i & rate_mask];
+    a.out[l] = gl_mul(acc0, zi);
+    if (nch > 1) a.out[a.out_stride + l] = gl_mul(acc1, zi);
+}
+
+void launch_quotient(const QuotientParams* params_dev, const QuotientParams& ph, const u64* apow_dev, int nterms,
+                     const u64* cs_lde, size_t cs_stride, const u64* wires_lde, size_t w_stride, const u64* zs_lde,
+                     size_t z_stride, u64* out, size_t out_stride, cudaStream_t st) {
+    QuotientArgs a{params_dev, apow_dev, nterms, cs_lde, cs_stride, wires_lde, w_stride, zs_lde, z_stride, out, out_stride};
+    size_t N = size_t(1) << (ph.lg_n + ph.rate_bits);
+    quotient_kernel<<<(unsigned)((N + 127) / 128), 128, 0, st>>>(a);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Openings (a9): P(z) = sum_k c_k z^k for many polynomials at one extension point
+// ---------------------------------------------------------------------------------------------
+__global__ void ext_powers_kernel(ext2 z, unsigned lg_n, u64* pa, u64* pb) {
+    size_t k = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if (k >= (size_t(1) << lg_n)) return;
+    ext2 r = e_pow(z, k);
+    pa[k] = r.a;
+    pb[k] = r.b;
+}
+void launch_ext_powers(ext2 z, unsigned lg_n, u64* pa, u64* pb, cudaStream_t st) {
+    size_t n = size_t(1) << lg_n;
+    ext_powers_kernel<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(z, lg_n, pa, pb);
+}
+
+__global__ void __launch_bounds__(256) eval_polys_kernel(const u64* __restrict__ coeffs, size_t stride, unsigned lg_n,
+                                                         const u64* __restrict__ za, const u64* __restrict__ zb, u64* __restrict__ out) {
+    __shared__ u64 sa[8], sb[8];
+    const u64* c = coeffs + (size_t)blockIdx.x * stride;
+    size_t n = size_t(1) << lg_n;
+    u64 a = 0, b = 0;
+    for (size_t k = threadIdx.x; k < n; k += blockDim.x) {
+        u64 v = c[k];
+        a = gl_add(a, gl_mul(v, za[k]));
+        b = gl_add(b, gl_mul(v, zb[k]));
+    }
+    for (int off = 16; off > 0; off >>= 1) {
+        a = gl_add(a, __shfl_down_sync(0xffffffffu, a, off));
+        b = gl_add(b, __shfl_down_sync(0xffffffffu, b, off));
+    }
+    int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (lane == 0) { sa[warp] = a; sb[warp] = b; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int wv = 1; wv < (int)(blockDim.x >> 5); ++wv) { a = gl_add(a, sa[wv]); b = gl_add(b, sb[wv]); }
+        out[2 * blockIdx.x] = a;
+        out[2 * blockIdx.x + 1] = b;
+    }
+}
+void launch_eval_polys(const u64* coeffs, size_t stride, int ncols, unsigned lg_n, const u64* za, const u64* zb, u64* out, cudaStream_t st) {
+    if (ncols <= 0) return;
+    eval_polys_kernel<<<ncols, 256, 0, st>>>(coeffs, stride, lg_n, za, zb, out);
+}
+
+// ---------------------------------------------------------------------------------------------
+// FRI (a10-a13)
+// ---------------------------------------------------------------------------------------------
+struct FriCombineArgs {
+    FriCombineParams p;
+    const u64* apa; const u64* apb;     // alpha^j, j < total columns
+    ext2 alpha_shift;                   // alpha^(#polys opened at g*zeta)
+    u64* oa; u64* ob;
+};
+__global__ void __launch_bounds__(128) fri_combine_kernel(FriCombineArgs a) {
+    const FriCombineParams& P = a.p;
+    size_t n = size_t(1) << P.lg_n;
+    size_t l = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if (l >= n) return;
+    u64 s0a = 0, s0b = 0, s1a = 0, s1b = 0;
+    int j = 0;
+    for (int t = 0; t < 4; ++t) {
+        const u64* col = P.lde[t] + l;
+        for (int c = 0; c < P.ncols[t]; ++c, ++j) {
+            u64 v = col[(size_t)c * P.stride[t]];
+            s0a = gl_add(s0a, gl_mul(v, a.apa[j]));
+            s0b = gl_add(s0b, gl_mul(v, a.apb[j]));
+        }
+    }
+    for (int c = 0; c < P.num_zs; ++c) {
+        u64 v = P.lde[2][(size_t)c * P.stride[2] + l];
+        s1a = gl_add(s1a, gl_mul(v, a.apa[c]));
+        s1b = gl_add(s1b, gl_mul(v, a.apb[c]));
+    }
+    u64 x = gl_mul(GL_GEN, root_pow_lg(P.lg_n, bitrev32((u32)l, P.lg_n), false));
+    ext2 X = e_from(x);
+    ext2 q0 = e_mul(e_sub(e_make(s0a, s0b), P.reduced0), e_inv(e_sub(X, P.zeta)));
+    ext2 q1 = e_mul(e_sub(e_make(s1a, s1b), P.reduced1), e_inv(e_sub(X, P.zeta_next)));
+    ext2 q = e_add(e_mul(q0, a.alpha_shift), q1);
+    a.oa[l] = q.a;
+    a.ob[l] = q.b;
+}
+void launch_fri_combine(const FriCombineParams& p, const u64* apa, const u64* apb, u64* oa, u64* ob, cudaStream_t st) {
+    FriCombineArgs a{p, apa, apb, e_pow(p.alpha, (u64)p.num_zs), oa, ob};
+    size_t n = size_t(1) << p.lg_n;
+    fri_combine_kernel<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(a);
+}
+
+__global__ void fri_fold_kernel(const u64* __restrict__ ca, const u64* __restrict__ cb, u64* __restrict__ oa, u64* __restrict__ ob,
+                                size_t m_out, int arity, ext2 beta) {
+    size_t k = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if (k >= m_out) return;
+    ext2 acc = e_make(0, 0);
+    for (int i = arity; i-- > 0;) acc = e_add(e_mul(acc, beta), e_make(ca[k * arity + i], cb[k * arity + i]));
+    oa[k] = acc.a;
+    ob[k] = acc.b;
+}
+void launch_fri_fold(const u64* ca, const u64* cb, u64* oa, u64* ob, size_t m_out, int arity, ext2 beta, cudaStream_t st) {
+    if (!m_out) return;
+    fri_fold_kernel<<<(unsigned)((m_out + 127) / 128), 128, 0, st>>>(ca, cb, oa, ob, m_out, arity, beta);
+}
+
+__global__ void __launch_bounds__(128) pow_search_kernel(const u64* __restrict__ state12, int pos, u64 base, u64 count, unsigned bits,
+                                                         unsigned long long* result) {
+    u64 k = blockIdx.x * (u64)blockDim.x + threadIdx.x;
+    if (k >= count) return;
+    u64 cand = base + k;
+    u64 s[12];
+#pragma unroll
+    for (int i = 0; i < 12; ++i) s[i] = (i == pos) ? cand : state12[i];
+    poseidon_permute(s);
+    u64 resp = gl_canon(s[7]);
+    if (__clzll((long long)resp) >= (int)bits) atomicMin(result, (unsigned long long)cand);
+}
+void launch_pow_search(const u64* state12_dev, int pos, u64 base, u64 count, unsigned bits, unsigned long long* result, cudaStream_t st) {
+    pow_search_kernel<<<(unsigned)((count + 127) / 128), 128, 0, st>>>(state12_dev, pos, base, count, bits, result);
+}
+
+__global__ void gather_rows_kernel(const u64* __restrict__ lde, size_t stride, int width, const u32* __restrict__ idx, u64* __restrict__ out) {
+    int q = blockIdx.x;
+    for (int c = threadIdx.x; c < width; c += blockDim.x) out[(size_t)q * width + c] = lde[(size_t)c * stride + idx[q]];
+}
+void launch_gather_rows(const u64* lde, size_t stride, int width, const u32* idx_dev, int nq, u64* out, cudaStream_t st) {
+    if (nq <= 0 || width <= 0) return;
+    gather_rows_kernel<<<nq, 128, 0, st>>>(lde, stride, width, idx_dev, out);
+}
+__global__ void gather_paths_kernel(const u64* __restrict__ digests, size_t num_leaves, int path_len, const u32* __restrict__ idx,
+                                    u64* __restrict__ out) {
+    int q = blockIdx.x;
+    for (int t = threadIdx.x; t < path_len * 4; t += blockDim.x) {
+        int k = t >> 2, e = t & 3;
+        size_t off = 0;
+        for (int j = 0; j < k; ++j) off += num_leaves >> j;
+        size_t node = ((size_t)idx[q] >> k) ^ 1;
+        out[((size_t)q * path_len + k) * 4 + e] = digests[(off + node) * 4 + e];
+    }
+}
+void launch_gather_paths(const u64* digests, size_t num_leaves, int path_len, const u32* idx_dev, int nq, u64* out, cudaStream_t st) {
+    if (nq <= 0 || path_len <= 0) return;
+    gather_paths_kernel<<<nq, 64, 0, st>>>(digests, num_leaves, path_len, idx_dev, out);
+}
+__global__ void gather_ext_leaves_kernel(const u64* __restrict__ a, const u64* __restrict__ b, int arity, const u32* __restrict__ idx,
+                                         u64* __restrict__ out) {
+    int q = blockIdx.x;
+    for (int k = threadIdx.x; k < arity; k += blockDim.x) {
+        size_t src = (size_t)idx[q] * arity + k;
+        out[((size_t)q * arity + k) * 2] = a[src];
+        out[((size_t)q * arity + k) * 2 + 1] = b[src];
+    }
+}
+void launch_gather_ext_leaves(const u64* a, const u64* b, int arity, const u32* idx_dev, int nq, u64* out, cudaStream_t st) {
+    if (nq <= 0) return;
+    gather_ext_leaves_kernel<<<nq, 32, 0, st>>>(a, b, arity, idx_dev, out);
+}
+
+}  // namespace zkb

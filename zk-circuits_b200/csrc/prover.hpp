@@ -1,0 +1,111 @@
+// Host pipeline of the B200 prover: owns all device memory of one circuit context and drives the
+// kernels in the order of qp-plonky2 1.1.1 `plonk::prover::prove_with_partition_witness`
+// (reached from /root/reference/wormhole/prover/src/lib.rs:234-236 and
+// /root/reference/wormhole/aggregator/src/circuits/tree.rs:136; stage list SURVEY.md §3.3 (d)-(l)).
+#pragma once
+#include <cuda_runtime.h>
+#include <memory>
+#include <string>
+#include <vector>
+#include "common_data.hpp"
+#include "kernels.h"
+
+namespace zkb {
+
+struct CudaError : std::runtime_error { using std::runtime_error::runtime_error; };
+struct ArgError : std::runtime_error { using std::runtime_error::runtime_error; };
+struct DigestError : std::runtime_error { using std::runtime_error::runtime_error; };
+struct ZetaError : std::runtime_error { using std::runtime_error::runtime_error; };
+struct BufferError : std::runtime_error {
+    size_t required;
+    BufferError(size_t r) : std::runtime_error("output buffer too small"), required(r) {}
+};
+
+void cuda_check(cudaError_t e, const char* what);
+
+class DevBuf {
+public:
+    DevBuf() = default;
+    explicit DevBuf(size_t words) { alloc(words); }
+    ~DevBuf() { release(); }
+    DevBuf(const DevBuf&) = delete;
+    DevBuf& operator=(const DevBuf&) = delete;
+    DevBuf(DevBuf&& o) noexcept : p_(o.p_), words_(o.words_) { o.p_ = nullptr; o.words_ = 0; }
+    void alloc(size_t words);
+    void release();
+    u64* get() const { return p_; }
+    size_t words() const { return words_; }
+private:
+    u64* p_ = nullptr;
+    size_t words_ = 0;
+};
+
+// one committed polynomial batch on the device (PolynomialBatch): coefficients + LDE (leaf order) + tree
+struct BatchDev {
+    int ncols = 0, salt = 0;
+    DevBuf coeffs;     // [ncols][n]        (may alias an external buffer: see coeff_ptr)
+    u64* coeff_ptr = nullptr; size_t coeff_stride = 0;
+    DevBuf lde;        // [ncols + salt][N]
+    DevBuf digests;    // all levels
+    size_t cap_offset = 0;   // digest index of the cap level
+};
+
+enum Stage { T_H2D = 0, T_WIRES_LDE, T_WIRES_MERKLE, T_PP, T_ZS_COMMIT, T_QUOTIENT, T_QUOTIENT_COMMIT, T_OPENINGS,
+             T_FRI_COMBINE, T_FRI_COMMIT, T_POW, T_QUERIES, T_TOTAL, T_COUNT };
+
+class Circuit {
+public:
+    Circuit(const uint8_t* common, size_t len, const u64* const_sigma, bool is_values, const u64* digest, int device);
+    ~Circuit();
+
+    const CommonData& common() const { return cd_; }
+    void verifier_only(u64* cap_out, u64 digest_out[4]) const;
+    void upload_witness(const u64* wires_host);
+    size_t prove_resident(const u64* public_inputs, size_t n_pi, const u64* salts, u64 salt_seed, u32 pow_rule,
+                          uint8_t* out, size_t cap);
+    void partial_products(const u64* wires_host, const u64* betas, const u64* gammas, u64* out_host);
+    void quotient(const u64* wires_host, const u64* zs_pp_host, const u64* pis, size_t n_pi, const u64* betas,
+                  const u64* gammas, const u64* alphas, u64* out_host);
+    float timings[T_COUNT] = {0};
+    int device() const { return device_; }
+
+private:
+    void commit_batch(BatchDev& b, unsigned batch_id, const u64* salts_host, u64 salt_seed, u64* cap_host);
+    void run_partial_products(const u64* betas, const u64* gammas);
+    void run_quotient(const u64* pi_hash, const u64* betas, const u64* gammas, const u64* alphas);
+    void sync();
+
+    CommonData cd_;
+    int device_ = 0;
+    cudaStream_t st_ = nullptr;
+    size_t n_ = 0, N_ = 0;
+    unsigned lg_n_ = 0, lg_N_ = 0;
+
+    BatchDev cs_, wires_, zs_, quot_;
+    DevBuf sigma_vals_;          // [num_routed][n] values over H, natural order
+    DevBuf wires_vals_;          // [num_wires][n]
+    DevBuf zs_vals_;             // [num_zs_pp][n] values, then coefficients in place (aliased by zs_.coeff_ptr)
+    DevBuf q_;                   // [nch][N] quotient values -> coefficients (aliased by quot_.coeff_ptr)
+    DevBuf pp_scratch_, k_is_dev_;
+    DevBuf zpow_;                // 2 * n
+    DevBuf openings_dev_;        // 2 * (all polys + nch)
+    DevBuf apow_dev_;            // quotient alpha powers [nch][nterms]
+    DevBuf fri_apow_;            // 2 * total columns (SoA)
+    DevBuf qparams_dev_;         // QuotientParams
+    // FRI
+    std::vector<DevBuf> fri_coeffs_;   // per layer (+ final): 2 * m_i (SoA a then b)
+    std::vector<DevBuf> fri_values_;   // per layer: 2 * 8 * m_i
+    std::vector<DevBuf> fri_digests_;
+    std::vector<size_t> fri_cap_off_;
+    DevBuf pow_dev_;             // 12 state words + 1 result
+    DevBuf query_idx_dev_;       // u32 indices: (1 + layers) * nq, packed in u64 words
+    DevBuf query_out_dev_;
+    // pinned host staging
+    u64* h_stage_ = nullptr;
+    size_t h_stage_words_ = 0, h_qp_off_ = 0;
+    u64 circuit_digest_[4] = {0};
+    std::vector<u64> cs_cap_;
+    cudaEvent_t ev_[T_COUNT + 1] = {nullptr};
+};
+
+}  // namespace zkb

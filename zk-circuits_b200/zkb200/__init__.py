@@ -1,0 +1,224 @@
+"""zkb200 — ctypes binding over libzkb200.so, the B200-native Plonky2 proving backend.
+
+Host-side mirror of the reference's prove boundary for tests and benchmarks:
+`ProverCircuit(common_bin, const_sigma, ...)` plays `ProverCircuitData` (prover_only + common,
+/root/reference/wormhole/prover/src/lib.rs:114-130) and `ProverCircuit.prove(wires, public_inputs)` plays
+`circuit_data.prove(partial_witness)` (/root/reference/wormhole/prover/src/lib.rs:233-237) after witness
+generation, returning `ProofWithPublicInputs::to_bytes()`.
+
+There is no CPU fallback: loading fails loudly if the CUDA library has not been built, and every call
+fails with ZkbError(ZKB_E_CUDA) when no sm_100 device is present.
+"""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_ROOT = os.path.dirname(_HERE)
+LIB_PATH = os.path.join(_ROOT, "libzkb200.so")
+
+u64p = ctypes.POINTER(ctypes.c_uint64)
+u8p = ctypes.POINTER(ctypes.c_uint8)
+f32p = ctypes.POINTER(ctypes.c_float)
+
+STATUS = {0: "ZKB_OK", -1: "ZKB_E_ARG", -2: "ZKB_E_PARSE", -3: "ZKB_E_UNSUPPORTED_GATE", -4: "ZKB_E_UNSAT",
+          -5: "ZKB_E_ZETA_IN_SUBGROUP", -6: "ZKB_E_CUDA", -7: "ZKB_E_NCCL", -8: "ZKB_E_BUFFER", -9: "ZKB_E_DIGEST"}
+TIMING_KEYS = ["h2d", "wires_lde", "wires_merkle", "partial_products", "zs_commit", "quotient", "quotient_commit",
+               "openings", "fri_combine", "fri_commit", "pow", "queries", "total"]
+
+EXPORTS = ["zkb_version", "zkb_last_error", "zkb_device_count", "zkb_circuit_create", "zkb_circuit_destroy",
+           "zkb_circuit_verifier_only", "zkb_proof_size", "zkb_prove", "zkb_witness_upload", "zkb_prove_resident",
+           "zkb_last_timings", "zkb_poseidon_permute_batch", "zkb_lde_batch", "zkb_merkle_commit", "zkb_commit_batch",
+           "zkb_partial_products", "zkb_quotient"]
+
+
+class ZkbError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"{STATUS.get(code, code)}: {msg}")
+        self.code = code
+        self.status = STATUS.get(code, str(code))
+
+
+def build(force=False):
+    """Compile libzkb200.so for sm_100a (nvcc cross-compiles without a GPU)."""
+    if force or not os.path.exists(LIB_PATH):
+        subprocess.check_call(["make", "-s", "-j4", "-C", _ROOT])
+    return LIB_PATH
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise ImportError(f"{LIB_PATH} is missing: build it with `make -C {_ROOT}` (there is no CPU fallback)")
+        L = ctypes.CDLL(LIB_PATH)
+        L.zkb_version.restype = ctypes.c_char_p
+        L.zkb_last_error.restype = ctypes.c_char_p
+        L.zkb_proof_size.restype = ctypes.c_size_t
+        L.zkb_proof_size.argtypes = [ctypes.c_void_p]
+        L.zkb_circuit_create.argtypes = [u8p, ctypes.c_size_t, u64p, ctypes.c_int, u64p, ctypes.c_int, ctypes.POINTER(ctypes.c_void_p)]
+        L.zkb_circuit_destroy.argtypes = [ctypes.c_void_p]
+        L.zkb_circuit_verifier_only.argtypes = [ctypes.c_void_p, u64p, ctypes.c_size_t, u64p]
+        L.zkb_prove.argtypes = [ctypes.c_void_p, u64p, u64p, ctypes.c_size_t, u64p, ctypes.c_uint64, ctypes.c_uint32, u8p,
+                                ctypes.c_size_t, ctypes.POINTER(ctypes.c_size_t)]
+        L.zkb_witness_upload.argtypes = [ctypes.c_void_p, u64p]
+        L.zkb_prove_resident.argtypes = [ctypes.c_void_p, u64p, ctypes.c_size_t, u64p, ctypes.c_uint64, ctypes.c_uint32, u8p,
+                                         ctypes.c_size_t, ctypes.POINTER(ctypes.c_size_t)]
+        L.zkb_last_timings.argtypes = [ctypes.c_void_p, f32p, ctypes.c_int]
+        L.zkb_poseidon_permute_batch.argtypes = [u64p, ctypes.c_size_t, ctypes.c_int]
+        L.zkb_lde_batch.argtypes = [u64p, ctypes.c_size_t, ctypes.c_size_t, ctypes.c_uint, ctypes.c_int, u64p, u64p, ctypes.c_int]
+        L.zkb_merkle_commit.argtypes = [u64p, ctypes.c_size_t, ctypes.c_size_t, ctypes.c_uint, u64p, u64p, ctypes.c_int]
+        L.zkb_commit_batch.argtypes = [u64p, ctypes.c_size_t, ctypes.c_size_t, ctypes.c_uint, ctypes.c_uint, ctypes.c_int, u64p, f32p, ctypes.c_int]
+        L.zkb_partial_products.argtypes = [ctypes.c_void_p, u64p, u64p, u64p, u64p]
+        L.zkb_quotient.argtypes = [ctypes.c_void_p, u64p, u64p, u64p, ctypes.c_size_t, u64p, u64p, u64p, u64p]
+        _lib = L
+    return _lib
+
+
+def _check(rc):
+    if rc != 0:
+        raise ZkbError(rc, lib().zkb_last_error().decode())
+
+
+def _u64(a):
+    a = np.ascontiguousarray(a, dtype=np.uint64)
+    return a, a.ctypes.data_as(u64p)
+
+
+def _ptr(addr_or_array):
+    """Accept a numpy array or a raw host address (e.g. a pinned torch tensor's data_ptr())."""
+    if isinstance(addr_or_array, int):
+        return None, ctypes.cast(addr_or_array, u64p)
+    return _u64(addr_or_array)
+
+
+def version():
+    return lib().zkb_version().decode()
+
+
+def device_count():
+    return lib().zkb_device_count()
+
+
+def poseidon_permute_batch(states, device=0):
+    a = np.array(states, dtype=np.uint64, order="C").reshape(-1, 12).copy()
+    _check(lib().zkb_poseidon_permute_batch(a.ctypes.data_as(u64p), a.shape[0], device))
+    return a
+
+
+def lde_batch(values, rate_bits=3, from_coeffs=False, want_lde=True, device=0):
+    a, p = _u64(values)
+    if a.ndim != 2:
+        raise ValueError("values must be (ncols, n)")
+    ncols, n = a.shape
+    coeffs = np.zeros((ncols, n), dtype=np.uint64)
+    lde = np.zeros((ncols, n << rate_bits), dtype=np.uint64) if want_lde else None
+    _check(lib().zkb_lde_batch(p, ncols, n, rate_bits, int(from_coeffs), coeffs.ctypes.data_as(u64p),
+                               lde.ctypes.data_as(u64p) if want_lde else None, device))
+    return coeffs, lde
+
+
+def merkle_commit(leaves_colmajor, cap_height, want_digests=True, device=0):
+    a, p = _u64(leaves_colmajor)
+    width, nl = a.shape
+    lg = nl.bit_length() - 1
+    total = sum(nl >> k for k in range(lg - cap_height + 1))
+    digests = np.zeros((total, 4), dtype=np.uint64) if want_digests else None
+    cap = np.zeros((1 << cap_height, 4), dtype=np.uint64)
+    _check(lib().zkb_merkle_commit(p, width, nl, cap_height, digests.ctypes.data_as(u64p) if want_digests else None,
+                                   cap.ctypes.data_as(u64p), device))
+    return digests, cap
+
+
+def commit_batch(values, rate_bits=3, cap_height=4, reps=1, device=0):
+    """Fused from_values (iNTT + LDE + Merkle). Returns (cap, {'lde_ms', 'merkle_ms'})."""
+    a, p = _u64(values)
+    ncols, n = a.shape
+    cap = np.zeros((1 << cap_height, 4), dtype=np.uint64)
+    t = np.zeros(2, dtype=np.float32)
+    _check(lib().zkb_commit_batch(p, ncols, n, rate_bits, cap_height, reps, cap.ctypes.data_as(u64p), t.ctypes.data_as(f32p), device))
+    return cap, {"lde_ms": float(t[0]), "merkle_ms": float(t[1])}
+
+
+class ProverCircuit:
+    """Device-resident circuit context (constants/sigmas commitment, twiddles, work buffers)."""
+
+    def __init__(self, common_bin, const_sigma, is_values=False, circuit_digest=None, device=0):
+        self._h = ctypes.c_void_p()
+        cb = np.frombuffer(bytes(common_bin), dtype=np.uint8).copy()
+        cs, csp = _u64(const_sigma)
+        dg = dgp = None
+        if circuit_digest is not None:
+            dg, dgp = _u64(circuit_digest)
+        _check(lib().zkb_circuit_create(cb.ctypes.data_as(u8p), cb.size, csp, int(is_values), dgp, device, ctypes.byref(self._h)))
+        self.proof_size = lib().zkb_proof_size(self._h)
+        self.device = device
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib().zkb_circuit_destroy(self._h)
+            self._h = None
+
+    __del__ = close
+
+    def verifier_only(self, cap_height=4):
+        cap = np.zeros((1 << cap_height, 4), dtype=np.uint64)
+        digest = np.zeros(4, dtype=np.uint64)
+        _check(lib().zkb_circuit_verifier_only(self._h, cap.ctypes.data_as(u64p), cap.size, digest.ctypes.data_as(u64p)))
+        return cap, digest
+
+    def prove(self, wires, public_inputs, salts=None, salt_seed=0, pow_rule=0):
+        """wires: (num_wires, n) array or pinned host address; returns proof bytes."""
+        _, wp = _ptr(wires)
+        pa, pp = _u64(public_inputs)
+        sa = sp = None
+        if salts is not None:
+            sa, sp = _u64(salts)
+        out = np.zeros(self.proof_size, dtype=np.uint8)
+        n = ctypes.c_size_t(0)
+        _check(lib().zkb_prove(self._h, wp, pp, pa.size, sp, salt_seed, pow_rule, out.ctypes.data_as(u8p), out.size, ctypes.byref(n)))
+        return out[: n.value].tobytes()
+
+    def upload_witness(self, wires):
+        _, wp = _ptr(wires)
+        _check(lib().zkb_witness_upload(self._h, wp))
+
+    def prove_resident(self, public_inputs, salts=None, salt_seed=0, pow_rule=0, out=None):
+        pa, pp = _u64(public_inputs)
+        sa = sp = None
+        if salts is not None:
+            sa, sp = _u64(salts)
+        if out is None:
+            out = np.zeros(self.proof_size, dtype=np.uint8)
+        n = ctypes.c_size_t(0)
+        _check(lib().zkb_prove_resident(self._h, pp, pa.size, sp, salt_seed, pow_rule, out.ctypes.data_as(u8p), out.size, ctypes.byref(n)))
+        return out[: n.value]
+
+    def timings(self):
+        t = np.zeros(len(TIMING_KEYS), dtype=np.float32)
+        k = lib().zkb_last_timings(self._h, t.ctypes.data_as(f32p), t.size)
+        return {key: float(v) for key, v in zip(TIMING_KEYS[:k], t[:k])}
+
+    def partial_products(self, wires, betas, gammas, num_cols, n):
+        wa, wp = _u64(wires)
+        ba, bp = _u64(betas)
+        ga, gp = _u64(gammas)
+        out = np.zeros((num_cols, n), dtype=np.uint64)
+        _check(lib().zkb_partial_products(self._h, wp, bp, gp, out.ctypes.data_as(u64p)))
+        return out
+
+    def quotient(self, wires, zs_pp, public_inputs, betas, gammas, alphas, num_chunks, n):
+        wa, wp = _u64(wires)
+        za, zp = _u64(zs_pp)
+        pa, pp = _u64(public_inputs)
+        ba, bp = _u64(betas)
+        ga, gp = _u64(gammas)
+        aa, ap = _u64(alphas)
+        out = np.zeros((num_chunks, n), dtype=np.uint64)
+        _check(lib().zkb_quotient(self._h, wp, zp, pp, pa.size, bp, gp, ap, out.ctypes.data_as(u64p)))
+        return out

@@ -45,6 +45,8 @@ typedef struct zkb_circuit zkb_circuit;
 const char* zkb_version(void);
 const char* zkb_last_error(void);
 int zkb_device_count(void);
+/* number of CUDA kernels this library has launched so far in this process (bench.py reports the per-step delta) */
+unsigned long long zkb_kernel_launch_count(void);
 
 /* ---- circuit context: replaces the prover-side use of ProverOnlyCircuitData + CommonCircuitData
  * (wormhole/prover/src/lib.rs:114-130; built by circuit/src/circuit.rs:98-108).
@@ -105,6 +107,20 @@ int zkb_partial_products(zkb_circuit* c, const uint64_t* wires, const uint64_t* 
 /* compute_quotient_polys from wire / Z-partial-product VALUES (unsalted): out [num_challenges*qdf][n] coefficients */
 int zkb_quotient(zkb_circuit* c, const uint64_t* wires, const uint64_t* zs_pp, const uint64_t* public_inputs, size_t n_pi,
                  const uint64_t* betas, const uint64_t* gammas, const uint64_t* alphas, uint64_t* out);
+
+/* ---- synthetic workload generator (host code; stands in for the Rust side of the boundary, i.e.
+ * CircuitBuilder::build_prover + witness generation, which need a Rust toolchain). Produces a circuit with the
+ * reference wormhole circuit's configuration, gate set and row mix and a satisfying witness.
+ * Used by bench.py / smoke() / tests to obtain workloads; not part of the proving path. ---- */
+typedef struct zkb_synth zkb_synth;
+int zkb_synth_create(unsigned min_degree_bits, int zk, size_t n_poseidon, size_t n_base_sum, size_t n_arith, size_t n_const,
+                     size_t num_public_inputs, uint64_t seed, zkb_synth** out);
+int zkb_synth_destroy(zkb_synth* s);
+size_t zkb_synth_common_len(const zkb_synth* s);
+size_t zkb_synth_degree(const zkb_synth* s);
+/* any output pointer may be NULL: common [common_len] bytes, const_sigma_values [84][n], wires [135][n],
+ * public_inputs [num_public_inputs] */
+int zkb_synth_get(const zkb_synth* s, uint8_t* common, uint64_t* const_sigma_values, uint64_t* wires, uint64_t* public_inputs);
 
 #ifdef __cplusplus
 }

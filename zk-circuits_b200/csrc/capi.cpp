@@ -1,6 +1,7 @@
 // C ABI of libzkb200.so (include/zkb200.h). No exception crosses this boundary; errors map to zkb_status.
 #include "../../include/zkb200.h"
 #include "prover.hpp"
+#include "synth.hpp"
 #include <cstring>
 #include <new>
 
@@ -8,6 +9,9 @@ using namespace zkb;
 
 struct zkb_circuit {
     std::unique_ptr<Circuit> impl;
+};
+struct zkb_synth {
+    SynthCircuit sc;
 };
 
 namespace {
@@ -52,6 +56,7 @@ extern "C" {
 
 const char* zkb_version(void) { return "zkb200 0.1.0 (sm_100a)"; }
 const char* zkb_last_error(void) { return g_last_error.c_str(); }
+unsigned long long zkb_kernel_launch_count(void) { return kernel_launch_count(); }
 int zkb_device_count(void) {
     int n = 0;
     if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
@@ -227,6 +232,41 @@ int zkb_commit_batch(const uint64_t* values, size_t ncols, size_t n, unsigned ra
         cudaEventDestroy(e0); cudaEventDestroy(e1); cudaEventDestroy(e2);
         if (times_ms) { times_ms[0] = t_lde / reps; times_ms[1] = t_merkle / reps; }
         cuda_check(cudaMemcpy(cap_out, dg.get() + cap_off * 4, (size_t(32)) << cap_height, cudaMemcpyDeviceToHost), "D2H cap");
+        return (int)ZKB_OK;
+    });
+}
+
+// ---- synthetic workloads ----
+int zkb_synth_create(unsigned min_degree_bits, int zk, size_t n_poseidon, size_t n_base_sum, size_t n_arith, size_t n_const,
+                     size_t num_public_inputs, uint64_t seed, zkb_synth** out) {
+    return guarded([&] {
+        if (!out) throw ArgError("out is null");
+        *out = nullptr;
+        if (min_degree_bits > 20 || num_public_inputs > 1024) throw ArgError("bad synthetic circuit shape");
+        SynthSpec sp;
+        sp.min_degree_bits = min_degree_bits; sp.zk = zk != 0;
+        sp.n_poseidon = n_poseidon; sp.n_base_sum = n_base_sum; sp.n_arith = n_arith; sp.n_const = n_const;
+        sp.num_public_inputs = num_public_inputs; sp.seed = seed;
+        auto s = std::make_unique<zkb_synth>();
+        s->sc = make_synth_circuit(sp);
+        *out = s.release();
+        return (int)ZKB_OK;
+    });
+}
+int zkb_synth_destroy(zkb_synth* s) { delete s; return ZKB_OK; }
+size_t zkb_synth_common_len(const zkb_synth* s) { return s ? s->sc.common.size() : 0; }
+size_t zkb_synth_degree(const zkb_synth* s) { return s ? (size_t(1) << s->sc.degree_bits) : 0; }
+int zkb_synth_get(const zkb_synth* s, uint8_t* common, uint64_t* const_sigma_values, uint64_t* wires, uint64_t* public_inputs) {
+    return guarded([&] {
+        if (!s) throw ArgError("synth is null");
+        const SynthCircuit& sc = s->sc;
+        size_t n = size_t(1) << sc.degree_bits;
+        if (common) std::memcpy(common, sc.common.data(), sc.common.size());
+        if (const_sigma_values)
+            for (size_t c = 0; c < sc.const_sigma_values.size(); ++c) std::memcpy(const_sigma_values + c * n, sc.const_sigma_values[c].data(), n * 8);
+        if (wires)
+            for (size_t c = 0; c < sc.wires.size(); ++c) std::memcpy(wires + c * n, sc.wires[c].data(), n * 8);
+        if (public_inputs) std::memcpy(public_inputs, sc.public_inputs.data(), sc.public_inputs.size() * 8);
         return (int)ZKB_OK;
     });
 }

@@ -72,8 +72,53 @@ ZKB_HD void mul128(u64 a, u64 b, u64& lo, u64& hi) {
 #endif
 }
 
+#if defined(__CUDA_ARCH__)
+// ---- device fast paths: 32-bit limbs, carry flags through add.cc/addc (IADD3/IADD3.X/IMAD.X in SASS), no
+// compare+select sequences. The limb algorithms were checked exhaustively on edge values on the host. ----
+
+// (a1:a0) * (b1:b0) -> 128-bit product limbs r0..r3: 4 x IMAD.WIDE.U32 + two 3-limb carry chains
+__device__ __forceinline__ void gl_mul128_limbs(u32 a0, u32 a1, u32 b0, u32 b1, u32& r0, u32& r1, u32& r2, u32& r3) {
+    u64 p00 = (u64)a0 * b0, p01 = (u64)a0 * b1, p10 = (u64)a1 * b0, p11 = (u64)a1 * b1;
+    asm("{\n\t"
+        "add.cc.u32 %0, %3, %4;\n\t"        // r1 = p00.hi + p01.lo
+        "addc.cc.u32 %1, %5, %7;\n\t"       // r2 = p01.hi + p10.hi + c
+        "addc.u32 %2, %9, 0;\n\t"           // r3 = p11.hi + c
+        "add.cc.u32 %0, %0, %6;\n\t"        // r1 += p10.lo
+        "addc.cc.u32 %1, %1, %8;\n\t"       // r2 += p11.lo + c
+        "addc.u32 %2, %2, 0;\n\t"
+        "}" : "=&r"(r1), "=&r"(r2), "=&r"(r3)
+            : "r"((u32)(p00 >> 32)), "r"((u32)p01), "r"((u32)(p01 >> 32)), "r"((u32)p10), "r"((u32)(p10 >> 32)),
+              "r"((u32)p11), "r"((u32)(p11 >> 32)));
+    r0 = (u32)p00;
+}
+// T = (r1:r0) + r2*(2^32-1) - r3 lies in (-2^32, 2^65): result = (T mod 2^64) + EPS*[T >= 2^64] - EPS*[T < 0],
+// which needs exactly one correction and cannot wrap again. r2*EPS + r0 is one IMAD.WIDE
+// (cannot overflow), so the fold costs 1 FMA-pipe + 10 ALU-pipe instructions.
+__device__ __forceinline__ u64 gl_reduce_limbs(u32 r0, u32 r1, u32 r2, u32 r3) {
+    u64 A = (u64)r2 * 0xFFFFFFFFu + r0;
+    u32 o0, o1;
+    asm("{\n\t"
+        ".reg .u32 mb, mc;\n\t"
+        "add.cc.u32 %1, %3, %4;\n\t"        // high limb + r1 -> carry
+        "addc.u32 mc, 0, 0;\n\t"
+        "sub.cc.u32 %0, %2, %5;\n\t"        // - r3 -> borrow
+        "subc.cc.u32 %1, %1, 0;\n\t"
+        "subc.u32 mb, 0, 0;\n\t"            // borrow ? 0xffffffff : 0
+        "neg.s32 mc, mc;\n\t"               // carry  ? 0xffffffff : 0
+        "add.cc.u32 %0, %0, mc;\n\t"        // + EPS on carry
+        "addc.u32 %1, %1, 0;\n\t"
+        "sub.cc.u32 %0, %0, mb;\n\t"        // - EPS on borrow
+        "subc.u32 %1, %1, 0;\n\t"
+        "}" : "=&r"(o0), "=&r"(o1) : "r"((u32)A), "r"((u32)(A >> 32)), "r"(r1), "r"(r3));
+    return ((u64)o1 << 32) | o0;
+}
+#endif
+
 // (hi:lo) mod p into [0, 2^64) — not necessarily canonical
 ZKB_HD u64 gl_reduce128_lazy(u64 lo, u64 hi) {
+#if defined(__CUDA_ARCH__)
+    return gl_reduce_limbs((u32)lo, (u32)(lo >> 32), (u32)hi, (u32)(hi >> 32));
+#else
     u64 hi_hi = hi >> 32, hi_lo = hi & GL_EPS;
     u64 t0 = lo - hi_hi;
     if (lo < hi_hi) t0 -= GL_EPS;
@@ -81,12 +126,54 @@ ZKB_HD u64 gl_reduce128_lazy(u64 lo, u64 hi) {
     u64 r = t0 + t1;
     if (r < t1) r += GL_EPS;
     return r;
+#endif
 }
 // inputs: any u64; output lazy
 ZKB_HD u64 gl_mul_lazy(u64 a, u64 b) {
+#if defined(__CUDA_ARCH__)
+    u32 r0, r1, r2, r3;
+    gl_mul128_limbs((u32)a, (u32)(a >> 32), (u32)b, (u32)(b >> 32), r0, r1, r2, r3);
+    return gl_reduce_limbs(r0, r1, r2, r3);
+#else
     u64 lo, hi;
     mul128(a, b, lo, hi);
     return gl_reduce128_lazy(lo, hi);
+#endif
+}
+// a any u64, c <= p - 1 (canonical): a + c cannot wrap twice
+ZKB_HD u64 gl_add_lazy_c(u64 a, u64 c) {
+#if defined(__CUDA_ARCH__)
+    u32 o0, o1;
+    asm("{\n\t.reg .u32 m;\n\t"
+        "add.cc.u32 %0, %2, %4;\n\t"
+        "addc.cc.u32 %1, %3, %5;\n\t"
+        "addc.u32 m, 0, 0;\n\t"
+        "neg.s32 m, m;\n\t"
+        "add.cc.u32 %0, %0, m;\n\t"
+        "addc.u32 %1, %1, 0;\n\t}" : "=&r"(o0), "=&r"(o1) : "r"((u32)a), "r"((u32)(a >> 32)), "r"((u32)c), "r"((u32)(c >> 32)));
+    return ((u64)o1 << 32) | o0;
+#else
+    u64 s = a + c;
+    if (s < a) s += GL_EPS;
+    return s;
+#endif
+}
+// a any u64, c <= p - 1 (canonical): a - c cannot borrow twice
+ZKB_HD u64 gl_sub_lazy_c(u64 a, u64 c) {
+#if defined(__CUDA_ARCH__)
+    u32 o0, o1;
+    asm("{\n\t.reg .u32 m;\n\t"
+        "sub.cc.u32 %0, %2, %4;\n\t"
+        "subc.cc.u32 %1, %3, %5;\n\t"
+        "subc.u32 m, 0, 0;\n\t"
+        "sub.cc.u32 %0, %0, m;\n\t"
+        "subc.u32 %1, %1, 0;\n\t}" : "=&r"(o0), "=&r"(o1) : "r"((u32)a), "r"((u32)(a >> 32)), "r"((u32)c), "r"((u32)(c >> 32)));
+    return ((u64)o1 << 32) | o0;
+#else
+    u64 d = a - c;
+    if (a < c) d -= GL_EPS;
+    return d;
+#endif
 }
 ZKB_HD u64 gl_mul(u64 a, u64 b) { return gl_canon(gl_mul_lazy(a, b)); }
 ZKB_HD u64 gl_sqr(u64 a) { return gl_mul(a, a); }

@@ -3,6 +3,7 @@
 // Integer-only; no tensor cores (nothing here is a dense contraction). Launchers are in kernels.h.
 #include "kernels.h"
 #include "poseidon.cuh"
+#include <atomic>
 #include <mutex>
 #include <stdexcept>
 #include <string>
@@ -16,6 +17,10 @@ namespace zkb {
         if (e_ != cudaSuccess)                                                                              \
             throw std::runtime_error(std::string("CUDA error: ") + cudaGetErrorString(e_) + " at " #x);     \
     } while (0)
+
+static std::atomic<unsigned long long> g_kernel_launches{0};
+unsigned long long kernel_launch_count() { return g_kernel_launches.load(); }
+#define ZKB_COUNT_LAUNCH() (g_kernel_launches.fetch_add(1, std::memory_order_relaxed))
 
 // ---------------------------------------------------------------------------------------------
 // device tables
@@ -94,6 +99,14 @@ void device_tables_init(int device) {
     ZKB_CUDA_CHECK(cudaGetDevice(&prev));
     ZKB_CUDA_CHECK(cudaSetDevice(device));
     ZKB_CUDA_CHECK(cudaMemcpyToSymbol(c_rc, host_round_constants(), sizeof(u64) * P_WIDTH * P_ROUNDS));
+    {
+        std::vector<u64> rc2(2 * P_WIDTH * (P_ROUNDS + 1), 0);
+        for (int i = 0; i < P_WIDTH * P_ROUNDS; ++i) {
+            rc2[2 * i] = host_round_constants()[i] & 0xFFFFFFFFu;
+            rc2[2 * i + 1] = host_round_constants()[i] >> 32;
+        }
+        ZKB_CUDA_CHECK(cudaMemcpyToSymbol(c_rc2, rc2.data(), sizeof(u64) * rc2.size()));
+    }
     std::vector<u64> A(2048), B(2048), C(1024);
     u64 T = GL_TWO_ADIC_ROOT, T11 = gl_pow(T, 1u << 11), T22 = gl_pow(T, 1u << 22);
     A[0] = B[0] = C[0] = 1;
@@ -129,6 +142,7 @@ __global__ void __launch_bounds__(128) poseidon_permute_kernel(u64* states, size
 }
 void launch_poseidon_permute(u64* states, size_t count, cudaStream_t st) {
     if (!count) return;
+    ZKB_COUNT_LAUNCH();
     poseidon_permute_kernel<<<(unsigned)((count + 127) / 128), 128, 0, st>>>(states, count);
 }
 
@@ -154,13 +168,9 @@ __global__ void __launch_bounds__(128) merkle_leaves_kernel(const u64* __restric
         return;
     }
     const u64* p = leaves + l;
-    int c = 0;
-    for (; c + 8 <= width; c += 8) {
-#pragma unroll
-        for (int k = 0; k < 8; ++k) s[k] = __ldg(p + (size_t)(c + k) * col_stride);
-        poseidon_permute(s);
-    }
-    if (c < width) {
+    // one call site of the (large) permutation: a second inlined copy would not fit the instruction cache
+#pragma unroll 1
+    for (int c = 0; c < width; c += 8) {
 #pragma unroll
         for (int k = 0; k < 8; ++k)
             if (c + k < width) s[k] = __ldg(p + (size_t)(c + k) * col_stride);
@@ -170,6 +180,7 @@ __global__ void __launch_bounds__(128) merkle_leaves_kernel(const u64* __restric
 }
 void launch_merkle_leaves(const u64* leaves, size_t col_stride, int width, size_t num_leaves, u64* digests, cudaStream_t st) {
     if (!num_leaves) return;
+    ZKB_COUNT_LAUNCH();
     merkle_leaves_kernel<<<(unsigned)((num_leaves + 127) / 128), 128, 0, st>>>(leaves, col_stride, width, num_leaves, digests);
 }
 
@@ -200,6 +211,7 @@ __global__ void __launch_bounds__(128) merkle_leaves_ext_kernel(const u64* __res
 }
 void launch_merkle_leaves_ext(const u64* a, const u64* b, int arity, size_t num_leaves, u64* digests, cudaStream_t st) {
     if (!num_leaves) return;
+    ZKB_COUNT_LAUNCH();
     merkle_leaves_ext_kernel<<<(unsigned)((num_leaves + 127) / 128), 128, 0, st>>>(a, b, arity, num_leaves, digests);
 }
 
@@ -230,6 +242,7 @@ size_t launch_merkle_levels(u64* digests, size_t num_leaves, unsigned cap_height
     size_t off = 0;
     for (unsigned k = 0; k + cap_height < lg; ++k) {
         size_t n_in = num_leaves >> k, n_out = n_in >> 1;
+        ZKB_COUNT_LAUNCH();
         merkle_level_kernel<<<(unsigned)((n_out + 127) / 128), 128, 0, st>>>(digests + off * 4, digests + (off + n_in) * 4, n_out);
         off += n_in;
     }
@@ -253,6 +266,7 @@ __global__ void salt_fill_kernel(u64* out, size_t stride, size_t num_leaves, u64
 }
 void launch_salt_fill(u64* out, size_t stride, size_t num_leaves, u64 seed, unsigned batch, cudaStream_t st) {
     dim3 grid((unsigned)((num_leaves + 255) / 256), 4);
+    ZKB_COUNT_LAUNCH();
     salt_fill_kernel<<<grid, 256, 0, st>>>(out, stride, num_leaves, seed, batch);
 }
 
@@ -371,6 +385,7 @@ static void run_block_pass(const BlockNttArgs& a, int ncols, cudaStream_t st) {
     unsigned mb = 1u << a.lb;
     unsigned threads = mb / 2 < 1024 ? (mb / 2 < 32 ? 32 : mb / 2) : 1024;
     dim3 grid(a.blocks_per_col, (unsigned)ncols);
+    ZKB_COUNT_LAUNCH();
     ntt_block_kernel<<<grid, threads, sizeof(u64) * mb, st>>>(a);
 }
 static void run_strided_pass(u64* data, size_t stride, int ncols, unsigned lg_m, unsigned lb, bool dit, bool inverse, cudaStream_t st) {
@@ -382,6 +397,7 @@ static void run_strided_pass(u64* data, size_t stride, int ncols, unsigned lg_m,
     StridedNttArgs a{data, stride, lg_m, lb, ltb, dit ? 1 : 0, inverse ? 1 : 0};
     size_t smem = sizeof(u64) << (lT + ltb);
     dim3 grid(1u << (lb - ltb), (unsigned)ncols);
+    ZKB_COUNT_LAUNCH();
     ntt_strided_kernel<<<grid, 1024, smem, st>>>(a);
 }
 
@@ -403,6 +419,7 @@ __global__ void bitrev_scale_kernel(u64* data, size_t stride, unsigned lg_n, u64
 void launch_bitrev_permute(u64* data, size_t stride, int ncols, unsigned lg_n, cudaStream_t st) {
     if (ncols <= 0) return;
     dim3 grid((unsigned)(((size_t(1) << lg_n) + 255) / 256), (unsigned)ncols);
+    ZKB_COUNT_LAUNCH();
     bitrev_scale_kernel<<<grid, 256, 0, st>>>(data, stride, lg_n, 1);
 }
 
@@ -423,6 +440,7 @@ void launch_intt_natural(const u64* src, size_t src_stride, u64* dst, size_t dst
     BlockNttArgs a{dst, dst_stride, dst, dst_stride, lb, 1u << (lg_n - lb), 0, 1, 0, 1};
     run_block_pass(a, ncols, st);
     dim3 grid((unsigned)(((size_t(1) << lg_n) + 255) / 256), (unsigned)ncols);
+    ZKB_COUNT_LAUNCH();
     bitrev_scale_kernel<<<grid, 256, 0, st>>>(dst, dst_stride, lg_n, ninv);
 }
 
@@ -450,6 +468,7 @@ void launch_lde(const u64* coeffs, size_t coeff_stride, u64* out, size_t out_str
     int groups = ncols < 8 ? ncols : 8;
     int cpg = (ncols + groups - 1) / groups;
     dim3 grid((unsigned)((n + 127) / 128), (unsigned)((ncols + cpg - 1) / cpg));
+    ZKB_COUNT_LAUNCH();
     lde_prescale_kernel<<<grid, 128, 0, st>>>(coeffs, coeff_stride, out, out_stride, ncols, lg_n, rate_bits, shift, cpg);
     unsigned nblk = 1u << rate_bits;
     if (lg_n <= NTT_MAX_LB) {
@@ -480,6 +499,7 @@ void launch_coset_intt_bitrev(u64* data, size_t stride, int ncols, unsigned lg_m
     run_block_pass(a, ncols, st);
     if (lg_m > lb) run_strided_pass(data, stride, ncols, lg_m, lb, true, true, st);
     size_t m = size_t(1) << lg_m;
+    ZKB_COUNT_LAUNCH();
     scale_pows_kernel<<<(unsigned)((m + 255) / 256), 256, 0, st>>>(data, stride, ncols, m, gl_inv(u64(1) << lg_m), gl_inv(shift));
 }
 
@@ -585,9 +605,12 @@ void launch_partial_products(const u64* wires, size_t wire_stride, const u64* si
     a.prefix = a.rowtot + (size_t)num_challenges * n;
     a.out = out; a.out_stride = out_stride;
     dim3 grid((unsigned)((n + 127) / 128), (unsigned)num_challenges);
+    ZKB_COUNT_LAUNCH();
     pp_chunk_kernel<<<grid, 128, 0, st>>>(a);
     unsigned nt = n < 1024 ? (unsigned)n : 1024;
+    ZKB_COUNT_LAUNCH();
     pp_scan_kernel<<<num_challenges, nt, 0, st>>>(a);
+    ZKB_COUNT_LAUNCH();
     pp_finalize_kernel<<<grid, 128, 0, st>>>(a);
 }
 
@@ -710,12 +733,12 @@ __global__ void __launch_bounds__(128) quotient_kernel(QuotientArgs a) {
 #pragma unroll 1
                 for (int r = 0; r < P_HALF_FULL; ++r) {
 #pragma unroll
-                    for (int j = 0; j < 12; ++j) st[j] = gl_add_lazy(st[j], c_rc[rc + j]);
+                    for (int j = 0; j < 12; ++j) st[j] = gl_add_lazy_c(st[j], c_rc[rc + j]);
                     if (r != 0) {
 #pragma unroll
                         for (int j = 0; j < 12; ++j) {
                             u64 sin = W(29 + 12 * (r - 1) + j);
-                            add_c(gl_sub_lazy(st[j], sin));
+                            add_c(gl_sub_lazy_c(st[j], sin));
                             st[j] = sin;
                         }
                     }
@@ -727,9 +750,9 @@ __global__ void __launch_bounds__(128) quotient_kernel(QuotientArgs a) {
 #pragma unroll 1
                 for (int r = 0; r < P_PARTIAL; ++r) {
 #pragma unroll
-                    for (int j = 0; j < 12; ++j) st[j] = gl_add_lazy(st[j], c_rc[rc + j]);
+                    for (int j = 0; j < 12; ++j) st[j] = gl_add_lazy_c(st[j], c_rc[rc + j]);
                     u64 sin = W(65 + r);
-                    add_c(gl_sub_lazy(st[0], sin));
+                    add_c(gl_sub_lazy_c(st[0], sin));
                     st[0] = gl_sbox7(sin);
                     mds_layer(st);
                     rc += 12;
@@ -737,11 +760,11 @@ __global__ void __launch_bounds__(128) quotient_kernel(QuotientArgs a) {
 #pragma unroll 1
                 for (int r = 0; r < P_HALF_FULL; ++r) {
 #pragma unroll
-                    for (int j = 0; j < 12; ++j) st[j] = gl_add_lazy(st[j], c_rc[rc + j]);
+                    for (int j = 0; j < 12; ++j) st[j] = gl_add_lazy_c(st[j], c_rc[rc + j]);
 #pragma unroll
                     for (int j = 0; j < 12; ++j) {
                         u64 sin = W(87 + 12 * r + j);
-                        add_c(gl_sub_lazy(st[j], sin));
+                        add_c(gl_sub_lazy_c(st[j], sin));
                         st[j] = sin;
                     }
 #pragma unroll
@@ -750,7 +773,7 @@ __global__ void __launch_bounds__(128) quotient_kernel(QuotientArgs a) {
                     rc += 12;
                 }
 #pragma unroll
-                for (int j = 0; j < 12; ++j) add_c(gl_sub_lazy(st[j], W(12 + j)));
+                for (int j = 0; j < 12; ++j) add_c(gl_sub_lazy_c(st[j], W(12 + j)));
                 break;
             }
             default: break;   // rejected on the host (ZKB_E_UNSUPPORTED_GATE)
@@ -768,6 +791,7 @@ void launch_quotient(const QuotientParams* params_dev, const QuotientParams& ph,
                      size_t z_stride, u64* out, size_t out_stride, cudaStream_t st) {
     QuotientArgs a{params_dev, apow_dev, nterms, cs_lde, cs_stride, wires_lde, w_stride, zs_lde, z_stride, out, out_stride};
     size_t N = size_t(1) << (ph.lg_n + ph.rate_bits);
+    ZKB_COUNT_LAUNCH();
     quotient_kernel<<<(unsigned)((N + 127) / 128), 128, 0, st>>>(a);
 }
 
@@ -783,6 +807,7 @@ __global__ void ext_powers_kernel(ext2 z, unsigned lg_n, u64* pa, u64* pb) {
 }
 void launch_ext_powers(ext2 z, unsigned lg_n, u64* pa, u64* pb, cudaStream_t st) {
     size_t n = size_t(1) << lg_n;
+    ZKB_COUNT_LAUNCH();
     ext_powers_kernel<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(z, lg_n, pa, pb);
 }
 
@@ -812,6 +837,7 @@ __global__ void __launch_bounds__(256) eval_polys_kernel(const u64* __restrict__
 }
 void launch_eval_polys(const u64* coeffs, size_t stride, int ncols, unsigned lg_n, const u64* za, const u64* zb, u64* out, cudaStream_t st) {
     if (ncols <= 0) return;
+    ZKB_COUNT_LAUNCH();
     eval_polys_kernel<<<ncols, 256, 0, st>>>(coeffs, stride, lg_n, za, zb, out);
 }
 
@@ -855,6 +881,7 @@ __global__ void __launch_bounds__(128) fri_combine_kernel(FriCombineArgs a) {
 void launch_fri_combine(const FriCombineParams& p, const u64* apa, const u64* apb, u64* oa, u64* ob, cudaStream_t st) {
     FriCombineArgs a{p, apa, apb, e_pow(p.alpha, (u64)p.num_zs), oa, ob};
     size_t n = size_t(1) << p.lg_n;
+    ZKB_COUNT_LAUNCH();
     fri_combine_kernel<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(a);
 }
 
@@ -869,6 +896,7 @@ __global__ void fri_fold_kernel(const u64* __restrict__ ca, const u64* __restric
 }
 void launch_fri_fold(const u64* ca, const u64* cb, u64* oa, u64* ob, size_t m_out, int arity, ext2 beta, cudaStream_t st) {
     if (!m_out) return;
+    ZKB_COUNT_LAUNCH();
     fri_fold_kernel<<<(unsigned)((m_out + 127) / 128), 128, 0, st>>>(ca, cb, oa, ob, m_out, arity, beta);
 }
 
@@ -885,6 +913,7 @@ __global__ void __launch_bounds__(128) pow_search_kernel(const u64* __restrict__
     if (__clzll((long long)resp) >= (int)bits) atomicMin(result, (unsigned long long)cand);
 }
 void launch_pow_search(const u64* state12_dev, int pos, u64 base, u64 count, unsigned bits, unsigned long long* result, cudaStream_t st) {
+    ZKB_COUNT_LAUNCH();
     pow_search_kernel<<<(unsigned)((count + 127) / 128), 128, 0, st>>>(state12_dev, pos, base, count, bits, result);
 }
 
@@ -894,6 +923,7 @@ __global__ void gather_rows_kernel(const u64* __restrict__ lde, size_t stride, i
 }
 void launch_gather_rows(const u64* lde, size_t stride, int width, const u32* idx_dev, int nq, u64* out, cudaStream_t st) {
     if (nq <= 0 || width <= 0) return;
+    ZKB_COUNT_LAUNCH();
     gather_rows_kernel<<<nq, 128, 0, st>>>(lde, stride, width, idx_dev, out);
 }
 __global__ void gather_paths_kernel(const u64* __restrict__ digests, size_t num_leaves, int path_len, const u32* __restrict__ idx,
@@ -909,6 +939,7 @@ __global__ void gather_paths_kernel(const u64* __restrict__ digests, size_t num_
 }
 void launch_gather_paths(const u64* digests, size_t num_leaves, int path_len, const u32* idx_dev, int nq, u64* out, cudaStream_t st) {
     if (nq <= 0 || path_len <= 0) return;
+    ZKB_COUNT_LAUNCH();
     gather_paths_kernel<<<nq, 64, 0, st>>>(digests, num_leaves, path_len, idx_dev, out);
 }
 __global__ void gather_ext_leaves_kernel(const u64* __restrict__ a, const u64* __restrict__ b, int arity, const u32* __restrict__ idx,
@@ -922,6 +953,7 @@ __global__ void gather_ext_leaves_kernel(const u64* __restrict__ a, const u64* _
 }
 void launch_gather_ext_leaves(const u64* a, const u64* b, int arity, const u32* idx_dev, int nq, u64* out, cudaStream_t st) {
     if (nq <= 0) return;
+    ZKB_COUNT_LAUNCH();
     gather_ext_leaves_kernel<<<nq, 32, 0, st>>>(a, b, arity, idx_dev, out);
 }
 

@@ -28,10 +28,11 @@ STATUS = {0: "ZKB_OK", -1: "ZKB_E_ARG", -2: "ZKB_E_PARSE", -3: "ZKB_E_UNSUPPORTE
 TIMING_KEYS = ["h2d", "wires_lde", "wires_merkle", "partial_products", "zs_commit", "quotient", "quotient_commit",
                "openings", "fri_combine", "fri_commit", "pow", "queries", "total"]
 
-EXPORTS = ["zkb_version", "zkb_last_error", "zkb_device_count", "zkb_circuit_create", "zkb_circuit_destroy",
+EXPORTS = ["zkb_version", "zkb_last_error", "zkb_device_count", "zkb_kernel_launch_count", "zkb_circuit_create", "zkb_circuit_destroy",
            "zkb_circuit_verifier_only", "zkb_proof_size", "zkb_prove", "zkb_witness_upload", "zkb_prove_resident",
            "zkb_last_timings", "zkb_poseidon_permute_batch", "zkb_lde_batch", "zkb_merkle_commit", "zkb_commit_batch",
-           "zkb_partial_products", "zkb_quotient"]
+           "zkb_partial_products", "zkb_quotient", "zkb_synth_create", "zkb_synth_destroy", "zkb_synth_common_len",
+           "zkb_synth_degree", "zkb_synth_get"]
 
 
 class ZkbError(RuntimeError):
@@ -59,6 +60,7 @@ def lib():
         L = ctypes.CDLL(LIB_PATH)
         L.zkb_version.restype = ctypes.c_char_p
         L.zkb_last_error.restype = ctypes.c_char_p
+        L.zkb_kernel_launch_count.restype = ctypes.c_ulonglong
         L.zkb_proof_size.restype = ctypes.c_size_t
         L.zkb_proof_size.argtypes = [ctypes.c_void_p]
         L.zkb_circuit_create.argtypes = [u8p, ctypes.c_size_t, u64p, ctypes.c_int, u64p, ctypes.c_int, ctypes.POINTER(ctypes.c_void_p)]
@@ -76,6 +78,13 @@ def lib():
         L.zkb_commit_batch.argtypes = [u64p, ctypes.c_size_t, ctypes.c_size_t, ctypes.c_uint, ctypes.c_uint, ctypes.c_int, u64p, f32p, ctypes.c_int]
         L.zkb_partial_products.argtypes = [ctypes.c_void_p, u64p, u64p, u64p, u64p]
         L.zkb_quotient.argtypes = [ctypes.c_void_p, u64p, u64p, u64p, ctypes.c_size_t, u64p, u64p, u64p, u64p]
+        L.zkb_synth_create.argtypes = [ctypes.c_uint, ctypes.c_int] + [ctypes.c_size_t] * 5 + [ctypes.c_uint64, ctypes.POINTER(ctypes.c_void_p)]
+        L.zkb_synth_destroy.argtypes = [ctypes.c_void_p]
+        L.zkb_synth_common_len.argtypes = [ctypes.c_void_p]
+        L.zkb_synth_common_len.restype = ctypes.c_size_t
+        L.zkb_synth_degree.argtypes = [ctypes.c_void_p]
+        L.zkb_synth_degree.restype = ctypes.c_size_t
+        L.zkb_synth_get.argtypes = [ctypes.c_void_p, u8p, u64p, u64p, u64p]
         _lib = L
     return _lib
 
@@ -103,6 +112,10 @@ def version():
 
 def device_count():
     return lib().zkb_device_count()
+
+
+def kernel_launch_count():
+    return int(lib().zkb_kernel_launch_count())
 
 
 def poseidon_permute_batch(states, device=0):
@@ -222,3 +235,32 @@ class ProverCircuit:
         out = np.zeros((num_chunks, n), dtype=np.uint64)
         _check(lib().zkb_quotient(self._h, wp, zp, pp, pa.size, bp, gp, ap, out.ctypes.data_as(u64p)))
         return out
+
+
+# row mixes of the reference circuits
+WORMHOLE = dict(n_poseidon=488, n_base_sum=3800, n_arith=2520, n_const=100, num_public_inputs=16)
+VOTING = dict(n_poseidon=34, n_base_sum=33, n_arith=120, n_const=12, num_public_inputs=13)
+TINY = dict(n_poseidon=6, n_base_sum=5, n_arith=6, n_const=3, num_public_inputs=5)
+
+
+class SynthCircuit:
+    """Synthetic wormhole-/voting-shaped circuit + satisfying witness (csrc/synth.cpp; host code)."""
+
+    def __init__(self, zk=False, seed=1, min_degree_bits=0, n_poseidon=488, n_base_sum=3800, n_arith=2520, n_const=100,
+                 num_public_inputs=16):
+        h = ctypes.c_void_p()
+        _check(lib().zkb_synth_create(min_degree_bits, int(zk), n_poseidon, n_base_sum, n_arith, n_const, num_public_inputs,
+                                      seed, ctypes.byref(h)))
+        try:
+            n = lib().zkb_synth_degree(h)
+            cb = np.zeros(lib().zkb_synth_common_len(h), dtype=np.uint8)
+            self.n = n
+            self.zk = bool(zk)
+            self.const_sigma_values = np.zeros((84, n), dtype=np.uint64)
+            self.wires = np.zeros((135, n), dtype=np.uint64)
+            self.public_inputs = np.zeros(num_public_inputs, dtype=np.uint64)
+            _check(lib().zkb_synth_get(h, cb.ctypes.data_as(u8p), self.const_sigma_values.ctypes.data_as(u64p),
+                                       self.wires.ctypes.data_as(u64p), self.public_inputs.ctypes.data_as(u64p)))
+            self.common = cb.tobytes()
+        finally:
+            lib().zkb_synth_destroy(h)

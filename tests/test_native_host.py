@@ -1,0 +1,16 @@
+"""Host (g++) build of the device arithmetic headers: the limb-form Poseidon in csrc/poseidon.cuh compiles for the host
+too, so its algebra (FFT-style MDS, limb normalisation, lazy folds) is checked here without a GPU against the plain
+u128 permutation. The GPU parity tests then only have to catch code-generation differences."""
+import os
+import subprocess
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_limb_poseidon_matches_plain_permutation(tmp_path):
+    exe = tmp_path / "test_poseidon_limbs"
+    subprocess.check_call(["/usr/bin/g++", "-O2", "-std=c++17", "-o", str(exe),
+                           os.path.join(ROOT, "tests", "native", "test_poseidon_limbs.cpp")])
+    out = subprocess.run([str(exe), "5000"], capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert out.stdout.strip().endswith("ok")

@@ -42,50 +42,6 @@ ZKB_D u64 root_pow_lg(unsigned lg, u32 e, bool inv) {
     return root_pow(E);
 }
 
-// ---- host: regenerate the Poseidon round constants (ChaCha8, rand seed_from_u64(0)) ----
-static inline u32 rotl32(u32 x, int r) { return (x << r) | (x >> (32 - r)); }
-static void chacha8_block(const u32 key[8], u64 counter, u32 out[16]) {
-    u32 s[16] = {0x61707865, 0x3320646e, 0x79622d32, 0x6b206574};
-    for (int i = 0; i < 8; ++i) s[4 + i] = key[i];
-    s[12] = (u32)counter; s[13] = (u32)(counter >> 32); s[14] = 0; s[15] = 0;
-    u32 x[16];
-    for (int i = 0; i < 16; ++i) x[i] = s[i];
-    auto qr = [&](int a, int b, int c, int d) {
-        x[a] += x[b]; x[d] = rotl32(x[d] ^ x[a], 16);
-        x[c] += x[d]; x[b] = rotl32(x[b] ^ x[c], 12);
-        x[a] += x[b]; x[d] = rotl32(x[d] ^ x[a], 8);
-        x[c] += x[d]; x[b] = rotl32(x[b] ^ x[c], 7);
-    };
-    for (int r = 0; r < 4; ++r) {
-        qr(0, 4, 8, 12); qr(1, 5, 9, 13); qr(2, 6, 10, 14); qr(3, 7, 11, 15);
-        qr(0, 5, 10, 15); qr(1, 6, 11, 12); qr(2, 7, 8, 13); qr(3, 4, 9, 14);
-    }
-    for (int i = 0; i < 16; ++i) out[i] = x[i] + s[i];
-}
-const u64* host_round_constants() {
-    static u64 rc[P_WIDTH * P_ROUNDS];
-    static std::once_flag once;
-    std::call_once(once, [] {
-        u64 state = 0;
-        u32 key[8];
-        for (int i = 0; i < 8; ++i) {   // PCG32 seed expansion
-            state = state * 6364136223846793005ULL + 11634580027462260723ULL;
-            u32 xs = (u32)(((state >> 18) ^ state) >> 27), rot = (u32)(state >> 59);
-            key[i] = (xs >> rot) | (xs << ((32 - rot) & 31));
-        }
-        u32 blk[16];
-        int pos = 16, n = 0;
-        u64 ctr = 0;
-        auto next = [&]() { if (pos == 16) { chacha8_block(key, ctr++, blk); pos = 0; } return blk[pos++]; };
-        while (n < P_WIDTH * P_ROUNDS) {
-            u64 lo = next(), hi = next();
-            unsigned __int128 m = (unsigned __int128)(lo | (hi << 32)) * GL_P;   // uniform sample in [0, p)
-            if ((u64)m <= GL_P - 1) rc[n++] = (u64)(m >> 64);
-        }
-    });
-    return rc;
-}
-
 struct BlockNttArgs;
 struct StridedNttArgs;
 static void ntt_set_func_attributes();   // defined with the NTT kernels below
@@ -99,6 +55,7 @@ void device_tables_init(int device) {
     ZKB_CUDA_CHECK(cudaGetDevice(&prev));
     ZKB_CUDA_CHECK(cudaSetDevice(device));
     ZKB_CUDA_CHECK(cudaMemcpyToSymbol(c_rc, host_round_constants(), sizeof(u64) * P_WIDTH * P_ROUNDS));
+    ZKB_CUDA_CHECK(cudaMemcpyToSymbol(c_rc3, host_round_constant_limbs(), sizeof(u32) * 3 * P_WIDTH * P_ROUNDS));
     {
         std::vector<u64> rc2(2 * P_WIDTH * (P_ROUNDS + 1), 0);
         for (int i = 0; i < P_WIDTH * P_ROUNDS; ++i) {
@@ -146,35 +103,39 @@ void launch_poseidon_permute(u64* states, size_t count, cudaStream_t st) {
     poseidon_permute_kernel<<<(unsigned)((count + 127) / 128), 128, 0, st>>>(states, count);
 }
 
-ZKB_D void store_digest(u64* digests, size_t idx, const u64* s) {
+ZKB_D void store_digest(u64* digests, size_t idx, u64 d0, u64 d1, u64 d2, u64 d3) {
     ulonglong2* p = reinterpret_cast<ulonglong2*>(digests + idx * 4);
-    p[0] = make_ulonglong2(gl_canon(s[0]), gl_canon(s[1]));
-    p[1] = make_ulonglong2(gl_canon(s[2]), gl_canon(s[3]));
+    p[0] = make_ulonglong2(d0, d1);
+    p[1] = make_ulonglong2(d2, d3);
+}
+ZKB_D void store_digest(u64* digests, size_t idx, const PoseidonState& s) {
+    store_digest(digests, idx, s.get(0), s.get(1), s.get(2), s.get(3));
 }
 
-// one leaf per thread; column-major reads are coalesced across the warp
+// one leaf per thread; column-major reads are coalesced across the warp. The sponge state stays in limb form
+// between permutations (overwrite mode: the 8 rate words are replaced, the capacity words carry over).
 __global__ void __launch_bounds__(128) merkle_leaves_kernel(const u64* __restrict__ leaves, size_t col_stride, int width,
                                                             size_t num_leaves, u64* __restrict__ digests) {
     size_t l = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
     if (l >= num_leaves) return;
-    u64 s[12];
-#pragma unroll
-    for (int k = 0; k < 12; ++k) s[k] = 0;
     if (width <= 4) {   // hash_or_noop: short leaves are copied, not hashed
+        u64 d[4] = {0, 0, 0, 0};
 #pragma unroll
         for (int c = 0; c < 4; ++c)
-            if (c < width) s[c] = leaves[(size_t)c * col_stride + l];
-        store_digest(digests, l, s);
+            if (c < width) d[c] = leaves[(size_t)c * col_stride + l];
+        store_digest(digests, l, d[0], d[1], d[2], d[3]);
         return;
     }
+    PoseidonState s;
+    s.zero();
     const u64* p = leaves + l;
     // one call site of the (large) permutation: a second inlined copy would not fit the instruction cache
 #pragma unroll 1
     for (int c = 0; c < width; c += 8) {
 #pragma unroll
         for (int k = 0; k < 8; ++k)
-            if (c + k < width) s[k] = __ldg(p + (size_t)(c + k) * col_stride);
-        poseidon_permute(s);
+            if (c + k < width) s.set(k, __ldg(p + (size_t)(c + k) * col_stride));
+        s.permute();
     }
     store_digest(digests, l, s);
 }
@@ -188,24 +149,25 @@ __global__ void __launch_bounds__(128) merkle_leaves_ext_kernel(const u64* __res
                                                                 size_t num_leaves, u64* __restrict__ digests) {
     size_t l = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
     if (l >= num_leaves) return;
-    u64 s[12];
-#pragma unroll
-    for (int k = 0; k < 12; ++k) s[k] = 0;
     const u64* pa = a + l * arity;
     const u64* pb = b + l * arity;
     int width = 2 * arity;
     if (width <= 4) {
+        u64 d[4] = {0, 0, 0, 0};
 #pragma unroll
         for (int c = 0; c < 4; ++c)
-            if (c < width) s[c] = (c & 1) ? pb[c >> 1] : pa[c >> 1];
-        store_digest(digests, l, s);
+            if (c < width) d[c] = (c & 1) ? pb[c >> 1] : pa[c >> 1];
+        store_digest(digests, l, d[0], d[1], d[2], d[3]);
         return;
     }
+    PoseidonState s;
+    s.zero();
+#pragma unroll 1
     for (int c = 0; c < width; c += 8) {
 #pragma unroll
         for (int k = 0; k < 8; ++k)
-            if (c + k < width) s[k] = (k & 1) ? pb[(c + k) >> 1] : pa[(c + k) >> 1];
-        poseidon_permute(s);
+            if (c + k < width) s.set(k, (k & 1) ? pb[(c + k) >> 1] : pa[(c + k) >> 1]);
+        s.permute();
     }
     store_digest(digests, l, s);
 }
@@ -221,8 +183,11 @@ __global__ void __launch_bounds__(128) merkle_level_kernel(const u64* __restrict
     if (i >= n_out) return;
     const ulonglong2* p = reinterpret_cast<const ulonglong2*>(in + i * 8);
     ulonglong2 v0 = p[0], v1 = p[1], v2 = p[2], v3 = p[3];
-    u64 s[12] = {v0.x, v0.y, v1.x, v1.y, v2.x, v2.y, v3.x, v3.y, 0, 0, 0, 0};
-    poseidon_permute(s);
+    PoseidonState s;
+    s.zero();
+    s.set(0, v0.x); s.set(1, v0.y); s.set(2, v1.x); s.set(3, v1.y);
+    s.set(4, v2.x); s.set(5, v2.y); s.set(6, v3.x); s.set(7, v3.y);
+    s.permute();
     store_digest(out, i, s);
 }
 size_t merkle_level_offset(size_t num_leaves, unsigned level) {

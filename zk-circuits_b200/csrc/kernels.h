@@ -9,12 +9,12 @@
 #include <cstddef>
 #include <cstdint>
 #include "field.cuh"
+#include "poseidon_consts.hpp"   // host_round_constants()
 
 namespace zkb {
 
 // ---- one-time init (per device): Poseidon constants + twiddle tables ----
 void device_tables_init(int device);            // idempotent, thread-safe
-const u64* host_round_constants();              // 360 constants (regenerated from ChaCha8 seed 0)
 unsigned long long kernel_launch_count();       // kernels launched by this library so far (process-wide)
 
 // ---- Poseidon / Merkle ----

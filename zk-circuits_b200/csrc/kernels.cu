@@ -30,6 +30,7 @@ __device__ u64 d_rootA[2048], d_rootB[2048], d_rootC[1024];
 constexpr unsigned W_LG = 14;                       // direct twiddle table for blocks up to 2^14
 __device__ u64 d_W[1 << (W_LG - 1)];                // w_{2^14}^k
 __device__ u64 d_Winv[1 << (W_LG - 1)];             // w_{2^14}^-k
+__device__ u32 d_rc3[3 * P_WIDTH * P_ROUNDS];       // Poseidon round constants as limbs, for per-lane (divergent) indexing
 
 ZKB_D u64 root_pow(u32 E) {
     u64 r = gl_mul(d_rootA[E & 2047], d_rootB[(E >> 11) & 2047]);
@@ -56,6 +57,7 @@ void device_tables_init(int device) {
     ZKB_CUDA_CHECK(cudaSetDevice(device));
     ZKB_CUDA_CHECK(cudaMemcpyToSymbol(c_rc, host_round_constants(), sizeof(u64) * P_WIDTH * P_ROUNDS));
     ZKB_CUDA_CHECK(cudaMemcpyToSymbol(c_rc3, host_round_constant_limbs(), sizeof(u32) * 3 * P_WIDTH * P_ROUNDS));
+    ZKB_CUDA_CHECK(cudaMemcpyToSymbol(d_rc3, host_round_constant_limbs(), sizeof(u32) * 3 * P_WIDTH * P_ROUNDS));
     {
         std::vector<u64> rc2(2 * P_WIDTH * (P_ROUNDS + 1), 0);
         for (int i = 0; i < P_WIDTH * P_ROUNDS; ++i) {
@@ -201,6 +203,44 @@ size_t merkle_digest_count(size_t num_leaves, unsigned cap_height) {
     unsigned levels = lg >= cap_height ? lg - cap_height : 0;
     return merkle_level_offset(num_leaves, levels + 1);
 }
+// Lane-parallel compression for the SMALL levels of a tree, where one permutation per thread leaves the GPU waiting on
+// a single dependency chain (~45 us per level measured): here 12 lanes hold the 12 state words of one node (two nodes
+// per warp, lanes 0-11 and 16-27), every lane runs the same S-box code on its own word, and the circulant MDS is
+// out_j = sum_i C[i] * x_{(j+i) mod 12}, i.e. 11 warp shuffles per limb. ~4x the issue slots per node, ~1/5 the latency.
+__global__ void __launch_bounds__(128) merkle_level_wide_kernel(const u64* __restrict__ in, u64* __restrict__ out, size_t n_out) {
+    __shared__ u32 s_rc[3 * P_WIDTH * P_ROUNDS];
+    for (unsigned i = threadIdx.x; i < 3 * P_WIDTH * P_ROUNDS; i += blockDim.x) s_rc[i] = d_rc3[i];
+    __syncthreads();
+    const unsigned lane = threadIdx.x & 31, j = lane & 15, jj = j < 12 ? j : 11;
+    const size_t node = ((size_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * 2 + (lane >> 4);
+    const bool live = node < n_out;
+    u32 x0, x1, x2;
+    limb_split((live && j < 8) ? in[node * 8 + j] : 0, x0, x1, x2);
+#pragma unroll 1
+    for (int r = 0; r < P_ROUNDS; ++r) {
+        const u32* rc = s_rc + 36 * r + 3 * jj;
+        x0 += rc[0]; x1 += rc[1]; x2 += rc[2];
+        u32 y0, y1, y2;
+        limb_split(gl_sbox7(limb_to_u64(x0, x1, x2)), y0, y1, y2);
+        if (!(r < P_HALF_FULL || r >= P_HALF_FULL + P_PARTIAL) && jj != 0) {
+            limb_normalize(x0, x1, x2);
+            y0 = x0; y1 = x1; y2 = x2;
+        }
+        x0 = x1 = x2 = 0;
+#pragma unroll
+        for (int i = 0; i < 12; ++i) {
+            int src = (int)jj + i;
+            if (src >= 12) src -= 12;
+            x0 += ZKB_MDS_C(i) * __shfl_sync(0xffffffffu, y0, src, 16);
+            x1 += ZKB_MDS_C(i) * __shfl_sync(0xffffffffu, y1, src, 16);
+            x2 += ZKB_MDS_C(i) * __shfl_sync(0xffffffffu, y2, src, 16);
+        }
+        if (jj == 0) { x0 += 8 * y0; x1 += 8 * y1; x2 += 8 * y2; }
+    }
+    if (live && j < 4) out[node * 4 + j] = gl_canon(limb_to_u64(x0, x1, x2));
+}
+
+constexpr size_t MERKLE_WIDE_MAX_NODES = 4096;   // levels this small are latency-bound with one node per thread
 size_t launch_merkle_levels(u64* digests, size_t num_leaves, unsigned cap_height, cudaStream_t st) {
     unsigned lg = 0;
     while ((size_t(1) << lg) < num_leaves) ++lg;
@@ -208,7 +248,10 @@ size_t launch_merkle_levels(u64* digests, size_t num_leaves, unsigned cap_height
     for (unsigned k = 0; k + cap_height < lg; ++k) {
         size_t n_in = num_leaves >> k, n_out = n_in >> 1;
         ZKB_COUNT_LAUNCH();
-        merkle_level_kernel<<<(unsigned)((n_out + 127) / 128), 128, 0, st>>>(digests + off * 4, digests + (off + n_in) * 4, n_out);
+        if (n_out <= MERKLE_WIDE_MAX_NODES)
+            merkle_level_wide_kernel<<<(unsigned)((n_out + 7) / 8), 128, 0, st>>>(digests + off * 4, digests + (off + n_in) * 4, n_out);
+        else
+            merkle_level_kernel<<<(unsigned)((n_out + 127) / 128), 128, 0, st>>>(digests + off * 4, digests + (off + n_in) * 4, n_out);
         off += n_in;
     }
     return off;
@@ -865,21 +908,30 @@ void launch_fri_fold(const u64* ca, const u64* cb, u64* oa, u64* ob, size_t m_ou
     fri_fold_kernel<<<(unsigned)((m_out + 127) / 128), 128, 0, st>>>(ca, cb, oa, ob, m_out, arity, beta);
 }
 
+// Proof-of-work grind, MIN rule, in ONE launch: thread t tries base + t, base + t + T, ... (T = grid size) and stops
+// as soon as its next candidate is not below the smallest witness found so far, so the final *result is the true
+// minimum over [base, base + count) no matter how the blocks are scheduled.
 __global__ void __launch_bounds__(128) pow_search_kernel(const u64* __restrict__ state12, int pos, u64 base, u64 count, unsigned bits,
                                                          unsigned long long* result) {
-    u64 k = blockIdx.x * (u64)blockDim.x + threadIdx.x;
-    if (k >= count) return;
-    u64 cand = base + k;
-    u64 s[12];
+    const u64 stride = (u64)gridDim.x * blockDim.x;
+    u64 init[12];
 #pragma unroll
-    for (int i = 0; i < 12; ++i) s[i] = (i == pos) ? cand : state12[i];
-    poseidon_permute(s);
-    u64 resp = gl_canon(s[7]);
-    if (__clzll((long long)resp) >= (int)bits) atomicMin(result, (unsigned long long)cand);
+    for (int i = 0; i < 12; ++i) init[i] = state12[i];
+    for (u64 k = blockIdx.x * (u64)blockDim.x + threadIdx.x; k < count; k += stride) {
+        const u64 cand = base + k;
+        if (cand >= *reinterpret_cast<volatile unsigned long long*>(result)) break;
+        PoseidonState s;
+#pragma unroll
+        for (int i = 0; i < 12; ++i) s.set(i, i == pos ? cand : init[i]);
+        s.permute();
+        if (__clzll((long long)s.get(7)) >= (int)bits) atomicMin(result, (unsigned long long)cand);
+    }
 }
 void launch_pow_search(const u64* state12_dev, int pos, u64 base, u64 count, unsigned bits, unsigned long long* result, cudaStream_t st) {
     ZKB_COUNT_LAUNCH();
-    pow_search_kernel<<<(unsigned)((count + 127) / 128), 128, 0, st>>>(state12_dev, pos, base, count, bits, result);
+    u64 blocks = (count + 127) / 128;
+    if (blocks > 148 * 8) blocks = 148 * 8;      // one resident wave: 8 CTAs of 128 threads per SM
+    pow_search_kernel<<<(unsigned)blocks, 128, 0, st>>>(state12_dev, pos, base, count, bits, result);
 }
 
 __global__ void gather_rows_kernel(const u64* __restrict__ lde, size_t stride, int width, const u32* __restrict__ idx, u64* __restrict__ out) {

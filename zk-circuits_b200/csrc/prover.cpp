@@ -420,7 +420,7 @@ size_t Circuit::prove_resident(const u64* public_inputs, size_t n_pi, const u64*
         for (int i = 0; i < pos; ++i) h_pow[i] = ch.in_buf[i];
         h_pow[12] = ~u64(0);
         CK(cudaMemcpyAsync(pow_dev_.get(), h_pow, 13 * 8, cudaMemcpyHostToDevice, st_));
-        const u64 batch = u64(1) << 20;
+        const u64 batch = u64(1) << 32;   // one persistent launch scans this range in increasing order and stops at the minimum
         u64 base = 0;
         for (;;) {
             launch_pow_search(pow_dev_.get(), pos, base, batch, cd_.proof_of_work_bits,

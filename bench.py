@@ -5,10 +5,12 @@
     python bench.py --gpus N --steps K --warmup W            # CUDA prover (one process per GPU under torchrun)
     python bench.py --impl reference --gpus N --steps K ...  # CPU arm: the oracle's restated Plonky2 prover
 
-A step = one proof of the synthetic wormhole-shaped zk circuit (config #1: n = 2^14, 135 wires, 6-gate set,
-28 FRI queries, 16 PoW bits; proof = 148 932 bytes) per GPU. `value` is measured with the witness resident in HBM,
-`e2e` through the host-buffer C-ABI call zkb_prove() (H2D of the wire matrix and D2H of the proof inside the timed
-region). Multi-GPU is replica mode (independent proofs, no data-path collective): weak scaling.
+A step = `--streams` (default 8) independent proofs per GPU of the synthetic wormhole-shaped zk circuit (config #1:
+n = 2^14, 135 wires, 6-gate set, 28 FRI queries, 16 PoW bits; proof = 148 932 bytes), each on its own prover context
+and CUDA stream, driven by one host thread each — the way the reference's rayon callers invoke prove(). `value` is
+measured with the witnesses resident in HBM, `e2e` through the host-buffer C-ABI call zkb_prove() (H2D of the wire
+matrix and D2H of the proof inside the timed region); `prove_ms_single_stream` is the latency of one proof alone.
+Multi-GPU is replica mode (independent proofs, no data-path collective): weak scaling.
 """
 import argparse
 import json
@@ -116,6 +118,7 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="zkb200", choices=["zkb200", "reference"])
+    ap.add_argument("--streams", type=int, default=8, help="proofs in flight per GPU (independent prover contexts)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-sweep", action="store_true", help="skip the LDE/Merkle microbench points (config #3)")
     args = ap.parse_args()
@@ -147,49 +150,90 @@ def main():
 
     W = max(3, args.warmup)
     K = max(1, args.steps)
+    B = max(1, args.streams)
     synth = Z.SynthCircuit(zk=True, seed=1, **Z.WORMHOLE)
     n, nw = synth.n, synth.wires.shape[0]
-    circ = Z.ProverCircuit(synth.common, synth.const_sigma_values, is_values=True, device=local_rank)
+    # B independent prover contexts per GPU (one stream each), driven by B host threads: the reference's callers
+    # already prove concurrently from rayon workers (aggregator/src/circuits/tree.rs:93-103), one circuit per call.
+    circs = [Z.ProverCircuit(synth.common, synth.const_sigma_values, is_values=True, device=local_rank) for _ in range(B)]
+    circ = circs[0]
     # pinned host staging for the e2e arm (the reference-side caller would hand over its witness like this)
-    wires_pinned = torch.empty((nw, n), dtype=torch.int64, pin_memory=True)
-    wires_np = wires_pinned.numpy().view(np.uint64)
-    wires_np[:] = synth.wires
-    host_addr = wires_pinned.data_ptr()
+    pinned = [torch.empty((nw, n), dtype=torch.int64, pin_memory=True) for _ in range(B)]
+    for t_ in pinned:
+        t_.numpy().view(np.uint64)[:] = synth.wires
+    host_addr = [t_.data_ptr() for t_ in pinned]
     pis = synth.public_inputs
-    out = np.zeros(circ.proof_size, dtype=np.uint8)
+    outs = [np.zeros(circ.proof_size, dtype=np.uint8) for _ in range(B)]
 
-    # ---- device-resident arm (`value`) ----
-    circ.upload_witness(host_addr)
+    def run_parallel(fn):
+        """fn(b) on B host threads (ctypes drops the GIL inside the C ABI call); returns when all are done."""
+        if B == 1:
+            fn(0)
+            return
+        errs = []
+
+        def wrap(b):
+            try:
+                fn(b)
+            except Exception as e:  # noqa: BLE001
+                errs.append(e)
+
+        th = [threading.Thread(target=wrap, args=(b,)) for b in range(B)]
+        for t_ in th:
+            t_.start()
+        for t_ in th:
+            t_.join()
+        if errs:
+            raise errs[0]
+
+    # ---- single-stream latency + per-stage device times (CUDA events on the circuit's stream) ----
+    for b in range(B):
+        circs[b].upload_witness(host_addr[b])
     for i in range(W):
-        circ.prove_resident(pis, salt_seed=1000 * rank + i, out=out)
+        circ.prove_resident(pis, salt_seed=1000 * rank + i, out=outs[0])
     stage_sum = {}
     barrier()
     launches0 = Z.kernel_launch_count()
+    t0 = time.perf_counter()
+    for i in range(K):
+        circ.prove_resident(pis, salt_seed=2000 * (rank + 1) + i, out=outs[0])
+        for k, v in circ.timings().items():
+            stage_sum[k] = stage_sum.get(k, 0.0) + v
+    torch.cuda.synchronize()
+    t_single = time.perf_counter() - t0
+    launches = (Z.kernel_launch_count() - launches0) // K
+    # ---- device-resident throughput arm (`value`): B proofs in flight per GPU ----
+    for i in range(W):
+        run_parallel(lambda b: circs[b].prove_resident(pis, salt_seed=5000 + 100 * b + i, out=outs[b]))
+    barrier()
     with ClockSampler(local_rank) as clk:
         t0 = time.perf_counter()
         for i in range(K):
-            circ.prove_resident(pis, salt_seed=2000 * (rank + 1) + i, out=out)
-            for k, v in circ.timings().items():
-                stage_sum[k] = stage_sum.get(k, 0.0) + v
+            run_parallel(lambda b: circs[b].prove_resident(pis, salt_seed=2000 * (rank + 1) + 100 * b + i, out=outs[b]))
         torch.cuda.synchronize()
         t_res = time.perf_counter() - t0
-    launches = (Z.kernel_launch_count() - launches0) // K
-    barrier()
-    # ---- end-to-end arm through zkb_prove() with host buffers ----
-    for i in range(2):
-        circ.prove(host_addr, pis, salt_seed=i)
-    barrier()
-    t0 = time.perf_counter()
-    for i in range(K):
-        proof = circ.prove(host_addr, pis, salt_seed=3000 * (rank + 1) + i)
-    torch.cuda.synchronize()
-    t_e2e = time.perf_counter() - t0
+        barrier()
+        # ---- end-to-end arm through zkb_prove() with host buffers ----
+        proofs = [None] * B
+
+        def e2e_step(b, seed):
+            proofs[b] = circs[b].prove(host_addr[b], pis, salt_seed=seed + 100 * b)
+
+        for i in range(2):
+            run_parallel(lambda b: e2e_step(b, i))
+        barrier()
+        t0 = time.perf_counter()
+        for i in range(K):
+            run_parallel(lambda b: e2e_step(b, 3000 * (rank + 1) + i))
+        torch.cuda.synchronize()
+        t_e2e = time.perf_counter() - t0
+    proof = proofs[0]
     barrier()
 
-    t = torch.tensor([t_res, t_e2e], dtype=torch.float64, device="cuda")
+    t = torch.tensor([t_res, t_e2e, t_single], dtype=torch.float64, device="cuda")
     if dist is not None:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    t_res, t_e2e = float(t[0]), float(t[1])
+    t_res, t_e2e, t_single = float(t[0]), float(t[1]), float(t[2])
     stages = {k: v / K for k, v in stage_sum.items()}
 
     if rank != 0:
@@ -207,16 +251,16 @@ def main():
     perms = leaves * ((nw + salt + 7) // 8) + leaves - 16
     pos_ms = stages["wires_merkle"]
     line = {
-        "metric": METRIC, "value": world * K / t_res, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+        "metric": METRIC, "value": world * K * B / t_res, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
         "ms_per_step": 1000 * t_res / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "u64 (Goldilocks field, F_p^2 extension)", "data": "synthetic",
         "config": {"workload": WORKLOAD, "degree_bits": 14, "zero_knowledge": True, "num_wires": nw, "proof_bytes": len(proof),
-                   "proofs_per_step_per_gpu": 1, "parallelism": f"replica x{world} (no collective)",
+                   "proofs_per_step_per_gpu": B, "parallelism": f"replica x{world} (no collective), {B} proof streams per GPU",
                    "l2": "no flush: one proof streams ~0.5 GB of LDE/leaf data, far above the 126 MB L2"},
-        "device_ms_per_proof": stages["total"], "stage_ms": stages,
-        "e2e": {"value": world * K / t_e2e, "unit": UNIT, "ms_per_step": 1000 * t_e2e / K,
-                "h2d_bytes_per_step": int(nw * n * 8 + pis.size * 8), "d2h_bytes_per_step": int(len(proof))},
-        "gpu_launches": int(launches),
+        "prove_ms_single_stream": 1000 * t_single / K, "device_ms_per_proof": stages["total"], "stage_ms": stages,
+        "e2e": {"value": world * K * B / t_e2e, "unit": UNIT, "ms_per_step": 1000 * t_e2e / K,
+                "h2d_bytes_per_step": int(B * (nw * n * 8 + pis.size * 8)), "d2h_bytes_per_step": int(B * len(proof))},
+        "gpu_launches": int(launches) * B,
         "roofline": {"kernel": "wires LDE-NTT (intt + coset prescale + 8x NTT, 135 columns, n=2^14)", "bound": "hbm",
                      "achieved": lde_gbs, "peak": peak, "unit": "GB/s", "frac": lde_gbs / peak, "traffic": None,
                      "peak_source": peak_src, "algorithmic_bytes_per_launch": lde_bytes, "avg_ms": lde_ms},
@@ -250,7 +294,7 @@ def main():
         os_ = O.Synth(zk=True, seed=1, **O.Synth.WORMHOLE)
         oc = O.Circuit(os_.common, os_.const_sigma_values)
         t0 = time.perf_counter()
-        ref = oc.prove(os_.wires, os_.public_inputs, salt_seed=3000 + K - 1)
+        ref = oc.prove(os_.wires, os_.public_inputs, salt_seed=3000 + K - 1)   # same seed as stream 0's last e2e proof
         dt = time.perf_counter() - t0
         line["cpu_baseline"] = {"value": 1.0 / dt, "unit": UNIT, "cores": O.num_threads(), "kind": "port",
                                 "sample": "1 full proof of the bench circuit, oracle's restated Plonky2 prover (OpenMP)",

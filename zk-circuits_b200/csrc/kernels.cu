@@ -3,6 +3,9 @@
 // Integer-only; no tensor cores (nothing here is a dense contraction). Launchers are in kernels.h.
 #include "kernels.h"
 #include "poseidon.cuh"
+#include "ntt.cuh"
+#include <map>
+#include <tuple>
 #include <atomic>
 #include <mutex>
 #include <stdexcept>
@@ -81,6 +84,16 @@ void device_tables_init(int device) {
     for (size_t i = 1; i < half; ++i) { W[i] = gl_mul(W[i - 1], w); Wi[i] = gl_mul(Wi[i - 1], wi); }
     ZKB_CUDA_CHECK(cudaMemcpyToSymbol(d_W, W.data(), half * 8));
     ZKB_CUDA_CHECK(cudaMemcpyToSymbol(d_Winv, Wi.data(), half * 8));
+    {
+        const size_t full = size_t(1) << NTT_SM_LG;
+        std::vector<u64> W14(full);
+        W14[0] = 1;
+        for (size_t i = 1; i < full; ++i) W14[i] = gl_mul(W14[i - 1], w);
+        ZKB_CUDA_CHECK(cudaMemcpyToSymbol(d_W14, W14.data(), full * 8));
+        u64 w16[8];
+        for (int k = 0; k < 8; ++k) w16[k] = W14[(size_t)k << (NTT_SM_LG - 4)];
+        ZKB_CUDA_CHECK(cudaMemcpyToSymbol(c_w16, w16, sizeof(w16)));
+    }
     ntt_set_func_attributes();
     ZKB_CUDA_CHECK(cudaSetDevice(prev));
     done.push_back(device);
@@ -388,6 +401,33 @@ __global__ void __launch_bounds__(1024) ntt_strided_kernel(StridedNttArgs a) {
 static void ntt_set_func_attributes() {   // per device: opt in to > 48 KB dynamic shared memory
     ZKB_CUDA_CHECK(cudaFuncSetAttribute(ntt_block_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(u64) << NTT_MAX_LB)));
     ZKB_CUDA_CHECK(cudaFuncSetAttribute(ntt_strided_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+    ZKB_CUDA_CHECK(cudaFuncSetAttribute(lde_block_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ntt_smem_bytes(NTT_SM_LG)));
+    ZKB_CUDA_CHECK(cudaFuncSetAttribute(intt_block_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ntt_smem_bytes(NTT_SM_LG)));
+}
+static unsigned ntt_block_threads(unsigned lg_n) {
+    unsigned t = lg_n >= 4 ? (1u << (lg_n - 4)) : 1u;
+    return t < 32 ? 32 : (t > 512 ? 512 : t);
+}
+// (shift * w_N^j)^k tables for the fused coset pre-scale, cached per device for the lifetime of the process
+// (1 MB for the wormhole circuit's n = 2^14, rate 8; the FRI layers add a few smaller ones).
+static const u64* coset_table(unsigned lg_n, unsigned rate_bits, u64 shift, cudaStream_t st) {
+    static std::mutex mu;
+    static std::map<std::tuple<int, unsigned, unsigned, u64>, u64*> cache;
+    int dev = 0;
+    ZKB_CUDA_CHECK(cudaGetDevice(&dev));
+    std::lock_guard<std::mutex> lk(mu);
+    auto key = std::make_tuple(dev, lg_n, rate_bits, shift);
+    auto it = cache.find(key);
+    if (it != cache.end()) return it->second;
+    u64* tab = nullptr;
+    const size_t n = size_t(1) << lg_n;
+    ZKB_CUDA_CHECK(cudaMalloc(&tab, (n << rate_bits) * sizeof(u64)));
+    dim3 grid((unsigned)((n + 127) / 128), 1u << rate_bits);
+    ZKB_COUNT_LAUNCH();
+    coset_table_kernel<<<grid, 128, 0, st>>>(tab, lg_n, rate_bits, shift, gl_root_of_unity(lg_n + rate_bits));
+    ZKB_CUDA_CHECK(cudaStreamSynchronize(st));       // other streams may use the table as soon as it is in the cache
+    cache[key] = tab;
+    return tab;
 }
 static void run_block_pass(const BlockNttArgs& a, int ncols, cudaStream_t st) {
     unsigned mb = 1u << a.lb;
@@ -436,9 +476,9 @@ void launch_intt_natural(const u64* src, size_t src_stride, u64* dst, size_t dst
     (void)scratch;
     if (ncols <= 0) return;
     u64 ninv = gl_inv(u64(1) << lg_n);
-    if (lg_n <= NTT_MAX_LB) {
-        BlockNttArgs a{src, src_stride, dst, dst_stride, lg_n, 1, 0, 1, 1, ninv};
-        run_block_pass(a, ncols, st);
+    if (lg_n <= NTT_SM_LG) {
+        ZKB_COUNT_LAUNCH();
+        intt_block_kernel<<<(unsigned)ncols, ntt_block_threads(lg_n), ntt_smem_bytes(lg_n), st>>>(src, src_stride, dst, dst_stride, lg_n, 0, ninv);
         return;
     }
     if (src != dst)
@@ -473,6 +513,13 @@ void launch_lde(const u64* coeffs, size_t coeff_stride, u64* out, size_t out_str
                 unsigned rate_bits, u64 shift, cudaStream_t st) {
     if (ncols <= 0) return;
     size_t n = size_t(1) << lg_n;
+    if (lg_n <= NTT_SM_LG) {
+        const u64* tab = (rate_bits == 0 && shift == 1) ? nullptr : coset_table(lg_n, rate_bits, shift, st);
+        dim3 grid(1u << rate_bits, (unsigned)ncols);
+        ZKB_COUNT_LAUNCH();
+        lde_block_kernel<<<grid, ntt_block_threads(lg_n), ntt_smem_bytes(lg_n), st>>>(coeffs, coeff_stride, out, out_stride, lg_n, tab);
+        return;
+    }
     int groups = ncols < 8 ? ncols : 8;
     int cpg = (ncols + groups - 1) / groups;
     dim3 grid((unsigned)((n + 127) / 128), (unsigned)((ncols + cpg - 1) / cpg));
@@ -502,11 +549,16 @@ __global__ void scale_pows_kernel(u64* data, size_t stride, int ncols, size_t m,
 
 void launch_coset_intt_bitrev(u64* data, size_t stride, int ncols, unsigned lg_m, u64 shift, cudaStream_t st) {
     if (ncols <= 0) return;
-    unsigned lb = lg_m <= NTT_MAX_LB ? lg_m : 13;
-    BlockNttArgs a{data, stride, data, stride, lb, 1u << (lg_m - lb), 1, 1, 0, 1};
-    run_block_pass(a, ncols, st);
-    if (lg_m > lb) run_strided_pass(data, stride, ncols, lg_m, lb, true, true, st);
     size_t m = size_t(1) << lg_m;
+    if (lg_m <= NTT_SM_LG) {
+        ZKB_COUNT_LAUNCH();
+        intt_block_kernel<<<(unsigned)ncols, ntt_block_threads(lg_m), ntt_smem_bytes(lg_m), st>>>(data, stride, data, stride, lg_m, 1, 1);
+    } else {
+        unsigned lb = 13;
+        BlockNttArgs a{data, stride, data, stride, lb, 1u << (lg_m - lb), 1, 1, 0, 1};
+        run_block_pass(a, ncols, st);
+        run_strided_pass(data, stride, ncols, lg_m, lb, true, true, st);
+    }
     ZKB_COUNT_LAUNCH();
     scale_pows_kernel<<<(unsigned)((m + 255) / 256), 256, 0, st>>>(data, stride, ncols, m, gl_inv(u64(1) << lg_m), gl_inv(shift));
 }

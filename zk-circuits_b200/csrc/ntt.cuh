@@ -1,0 +1,150 @@
+// Shared-memory NTT for transform sizes up to 2^14 (one column = one CTA), the size class of the wormhole / voting
+// circuits: replaces qp-plonky2-field's `ifft` / `coset_fft` / `lde` on the device.
+//
+//  * radix-16 decimation-in-frequency passes: a thread loads 16 elements (stride 2^(s-4)) into registers, runs four
+//    butterfly stages there (internal twiddles are the constants w_16^k) and multiplies by the pass twiddle
+//    w_{2^s}^(b * bitrev4(p)) from one table of w_{2^14}^t — 4 block-wide barriers and 4 shared-memory round trips for
+//    14 stages instead of 14;
+//  * natural order in, bit-reversed order out, which IS the Merkle leaf order of PolynomialBatch, so the LDE is written
+//    with coalesced stores and no transpose; the inverse transform uses the same forward code and reads the result at
+//    bitrev((n - k) mod n);
+//  * the coset pre-scale (shift * w_N^j)^k is one multiply per element at load time from a cached table;
+//  * field add/sub on canonical values with carry flags (5 / 7 instructions; the compiler's compare+select form is 9+).
+#pragma once
+#include "field.cuh"
+
+namespace zkb {
+
+constexpr unsigned NTT_SM_LG = 14;                       // largest transform held in shared memory
+__device__ u64 d_W14[1u << NTT_SM_LG];                   // w_{2^14}^t, 0 <= t < 2^14
+__constant__ u64 c_w16[8];                               // w_16^k, k < 8
+
+// canonical in, canonical out
+ZKB_D u64 f_sub(u64 a, u64 b) {
+    u32 o0, o1;
+    asm("{\n\t.reg .u32 m;\n\t"
+        "sub.cc.u32 %0, %2, %4;\n\t"
+        "subc.cc.u32 %1, %3, %5;\n\t"
+        "subc.u32 m, 0, 0;\n\t"              // borrow ? 0xffffffff : 0
+        "sub.cc.u32 %0, %0, m;\n\t"          // + p  ==  - (2^32 - 1)  (mod 2^64)
+        "subc.u32 %1, %1, 0;\n\t}"
+        : "=&r"(o0), "=&r"(o1) : "r"((u32)a), "r"((u32)(a >> 32)), "r"((u32)b), "r"((u32)(b >> 32)));
+    return ((u64)o1 << 32) | o0;
+}
+ZKB_D u64 f_add(u64 a, u64 b) {               // a - (p - b); p - b in (0, p], and a < p, so one borrow fix is exact
+    u32 o0, o1;
+    asm("{\n\t.reg .u32 m, n0, n1;\n\t"
+        "sub.cc.u32 n0, 1, %4;\n\t"
+        "subc.u32 n1, 0xffffffff, %5;\n\t"
+        "sub.cc.u32 %0, %2, n0;\n\t"
+        "subc.cc.u32 %1, %3, n1;\n\t"
+        "subc.u32 m, 0, 0;\n\t"
+        "sub.cc.u32 %0, %0, m;\n\t"
+        "subc.u32 %1, %1, 0;\n\t}"
+        : "=&r"(o0), "=&r"(o1) : "r"((u32)a), "r"((u32)(a >> 32)), "r"((u32)b), "r"((u32)(b >> 32)));
+    return ((u64)o1 << 32) | o0;
+}
+
+ZKB_D unsigned ntt_pad(unsigned i) { return i + (i >> 4); }          // one spare word per 16: keeps small-stride passes off one bank
+inline size_t ntt_smem_bytes(unsigned lg) { return sizeof(u64) * ((size_t(1) << lg) + (size_t(1) << lg) / 16 + 1); }
+
+// in-register DIF of 2^K elements (K <= 4); r[p] ends up holding output index bitrev_K(p)
+template <int K>
+ZKB_D void radix_dif(u64* r) {
+#pragma unroll
+    for (int t = 0; t < K; ++t) {
+        const int half = 1 << (K - 1 - t);
+#pragma unroll
+        for (int g = 0; g < (1 << K); g += 2 * half) {
+#pragma unroll
+            for (int j = 0; j < half; ++j) {
+                u64 a = r[g + j], b = r[g + j + half];
+                r[g + j] = f_add(a, b);
+                u64 d = f_sub(a, b);
+                r[g + j + half] = j ? gl_mul(d, c_w16[j * (8 / half)]) : d;
+            }
+        }
+    }
+}
+
+// one radix-2^K pass over sm[0 .. 2^L): sub-transforms of size 2^s, tile = elements b + e * 2^(s-K)
+template <int K>
+ZKB_D void ntt_dif_pass(u64* sm, unsigned L, unsigned s) {
+    constexpr int R = 1 << K;
+    const unsigned lgM = s - K, M = 1u << lgM, ntiles = 1u << (L - K);
+    for (unsigned t = threadIdx.x; t < ntiles; t += blockDim.x) {
+        const unsigned b = t & (M - 1), base = ((t >> lgM) << s) + b;
+        u64 r[R];
+#pragma unroll
+        for (int e = 0; e < R; ++e) r[e] = sm[ntt_pad(base + ((unsigned)e << lgM))];
+        radix_dif<K>(r);
+        if (lgM) {
+#pragma unroll
+            for (int p = 1; p < R; ++p) {
+                const unsigned q = __brev((unsigned)p) >> (32 - K);
+                r[p] = gl_mul(r[p], d_W14[(b * q) << (NTT_SM_LG - s)]);
+            }
+        }
+#pragma unroll
+        for (int p = 0; p < R; ++p) sm[ntt_pad(base + ((unsigned)p << lgM))] = r[p];
+    }
+}
+// forward transform in place: natural order in, sm[pad(i)] = X[bitrev_L(i)] out. Ends with a barrier.
+ZKB_D void ntt_dif_smem(u64* sm, unsigned L) {
+    unsigned s = L;
+    while (s >= 4) { ntt_dif_pass<4>(sm, L, s); s -= 4; __syncthreads(); }
+    if (s == 3) ntt_dif_pass<3>(sm, L, s);
+    else if (s == 2) ntt_dif_pass<2>(sm, L, s);
+    else if (s == 1) ntt_dif_pass<1>(sm, L, s);
+    if (s) __syncthreads();
+}
+
+// coset LDE of one column block: out[jb * n + i] = sum_k coeff[k] (shift w_N^j)^k w_n^(k bitrev(i)),  j = bitrev_r(jb)
+// prescale: [2^rate_bits][n] table of (shift w_N^j)^k, or null for the plain transform (shift 1, rate 0)
+__global__ void __launch_bounds__(512) lde_block_kernel(const u64* __restrict__ coeffs, size_t coeff_stride, u64* __restrict__ out,
+                                                        size_t out_stride, unsigned lg_n, const u64* __restrict__ prescale) {
+    extern __shared__ u64 sm[];
+    const unsigned n = 1u << lg_n, jb = blockIdx.x;
+    const u64* src = coeffs + (size_t)blockIdx.y * coeff_stride;
+    const u64* ps = prescale ? prescale + (size_t)jb * n : nullptr;
+    for (unsigned i = threadIdx.x; i < n; i += blockDim.x) {
+        u64 v = src[i];
+        if (ps) v = gl_mul(v, ps[i]);
+        sm[ntt_pad(i)] = v;
+    }
+    __syncthreads();
+    ntt_dif_smem(sm, lg_n);
+    u64* dst = out + (size_t)blockIdx.y * out_stride + (size_t)jb * n;
+    for (unsigned i = threadIdx.x; i < n; i += blockDim.x) dst[i] = sm[ntt_pad(i)];
+}
+
+// inverse transform of one column: values on <w_n> (natural order, or bit-reversed if in_bitrev) -> coefficients
+// (natural order), times `scale` (= 1/n). Uses the forward code: c_k = X[(n - k) mod n] / n.
+__global__ void __launch_bounds__(512) intt_block_kernel(const u64* __restrict__ in, size_t in_stride, u64* __restrict__ out,
+                                                         size_t out_stride, unsigned lg_n, int in_bitrev, u64 scale) {
+    extern __shared__ u64 sm[];
+    const unsigned n = 1u << lg_n;
+    const u64* src = in + (size_t)blockIdx.x * in_stride;
+    for (unsigned i = threadIdx.x; i < n; i += blockDim.x) {
+        const unsigned pos = in_bitrev ? bitrev32(i, lg_n) : i;
+        sm[ntt_pad(pos)] = src[i];
+    }
+    __syncthreads();
+    ntt_dif_smem(sm, lg_n);
+    u64* dst = out + (size_t)blockIdx.x * out_stride;
+    for (unsigned k = threadIdx.x; k < n; k += blockDim.x) {
+        const unsigned q = (n - k) & (n - 1);
+        dst[k] = gl_mul(sm[ntt_pad(bitrev32(q, lg_n))], scale);
+    }
+}
+
+// table[jb * n + k] = (shift * w_N^bitrev_r(jb))^k, N = n << rate_bits; built once per (n, rate, shift)
+__global__ void coset_table_kernel(u64* table, unsigned lg_n, unsigned rate_bits, u64 shift, u64 w_N) {
+    const unsigned n = 1u << lg_n;
+    const unsigned k = blockIdx.x * blockDim.x + threadIdx.x, jb = blockIdx.y;
+    if (k >= n) return;
+    const u64 base = gl_mul(shift, gl_pow(w_N, bitrev32(jb, rate_bits)));
+    table[(size_t)jb * n + k] = gl_pow(base, k);
+}
+
+}  // namespace zkb

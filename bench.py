@@ -104,7 +104,9 @@ def reference_arm(args, rank):
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
         "warmup": min(args.warmup, 1), "ms_per_step": 1000 * dt / steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "u64 (Goldilocks)", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "proof_bytes": len(proof), "note": "CPU prover on host cores; GPUs unused"},
+        "config": {"workload": WORKLOAD, "degree_bits": 14, "zero_knowledge": True, "num_wires": 135, "proof_bytes": len(proof),
+                   "proofs_per_step_per_gpu": 1, "parallelism": "host cores (OpenMP); GPUs unused",
+                   "note": "restated Plonky2 CPU prover (oracle/), plain u128 field arithmetic, no SIMD"},
         "cpu_baseline": {"value": val, "unit": UNIT, "cores": O.num_threads(), "kind": "port",
                          "sample": f"{steps} full proofs of the bench circuit with the oracle's restated Plonky2 prover (OpenMP)"},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -230,10 +232,9 @@ def main():
     proof = proofs[0]
     barrier()
 
-    t = torch.tensor([t_res, t_e2e, t_single], dtype=torch.float64, device="cuda")
-    if dist is not None:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    t_res, t_e2e, t_single = float(t[0]), float(t[1]), float(t[2])
+    from zkb200 import batch as zbatch   # same max-over-ranks helper the CPU gloo test exercises
+
+    t_res, t_e2e, t_single = zbatch.max_over_ranks([t_res, t_e2e, t_single], device="cuda")
     stages = {k: v / K for k, v in stage_sum.items()}
 
     if rank != 0:

@@ -86,3 +86,20 @@ def test_wormhole_shaped_zk_proof_bytes(zkb, oracle):
     """C1: wormhole-shaped circuit, zk, n = 2^14 — same size as wormhole/bench-data/proof.bin."""
     s, oc, gc, proof = run_case(zkb, oracle, oracle.Synth.WORMHOLE, True, seed=1)
     assert s.info["degree_bits"] == 14 and len(proof) == 148932
+
+
+@pytest.mark.gpu
+def test_batch_of_proofs_on_two_streams(zkb, oracle):
+    """zkb200.batch (the aggregator-style fan-out over independent proofs): 5 proofs on 2 prover contexts / streams of one
+    GPU, each byte-identical to the oracle prover's proof for the same salt seed."""
+    from zkb200 import batch
+
+    s = zkb.SynthCircuit(zk=True, seed=21, **zkb.TINY)
+    provers = [zkb.ProverCircuit(s.common, s.const_sigma_values, is_values=True) for _ in range(2)]
+    oc = oracle.Circuit(s.common, s.const_sigma_values)
+    seeds = [7, 8, 9, 10, 11]
+    proofs = batch.prove_batch(seeds, provers, lambda p, w, i: p.prove(s.wires, s.public_inputs, salt_seed=w))
+    assert len(proofs) == len(seeds)
+    for seed, proof in zip(seeds, proofs):
+        assert proof == oc.prove(s.wires, s.public_inputs, salt_seed=seed)
+        assert oc.verify(proof) == ""

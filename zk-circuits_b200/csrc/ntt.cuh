@@ -45,6 +45,14 @@ ZKB_D u64 f_add(u64 a, u64 b) {               // a - (p - b); p - b in (0, p], a
     return ((u64)o1 << 32) | o0;
 }
 
+// r >= p  <=>  high word all ones and low word >= 1; then r - p = low - 1
+ZKB_D u64 f_canon(u64 r) {
+    u32 lo = (u32)r, hi = (u32)(r >> 32);
+    if (hi == 0xFFFFFFFFu && lo != 0) { lo -= 1; hi = 0; }
+    return ((u64)hi << 32) | lo;
+}
+ZKB_D u64 f_mul(u64 a, u64 b) { return f_canon(gl_mul_lazy(a, b)); }
+
 ZKB_D unsigned ntt_pad(unsigned i) { return i + (i >> 4); }          // one spare word per 16: keeps small-stride passes off one bank
 inline size_t ntt_smem_bytes(unsigned lg) { return sizeof(u64) * ((size_t(1) << lg) + (size_t(1) << lg) / 16 + 1); }
 
@@ -61,29 +69,35 @@ ZKB_D void radix_dif(u64* r) {
                 u64 a = r[g + j], b = r[g + j + half];
                 r[g + j] = f_add(a, b);
                 u64 d = f_sub(a, b);
-                r[g + j + half] = j ? gl_mul(d, c_w16[j * (8 / half)]) : d;
+                r[g + j + half] = j ? f_mul(d, c_w16[j * (8 / half)]) : d;
             }
         }
     }
 }
 
-// one radix-2^K pass over sm[0 .. 2^L): sub-transforms of size 2^s, tile = elements b + e * 2^(s-K)
+// one radix-2^K pass over sm[0 .. 2^L): sub-transforms of size 2^s, tile = elements b + e * 2^(s-K).
+// The pass twiddles are fetched BEFORE the butterflies so that their L1/L2 latency hides behind the arithmetic.
 template <int K>
 ZKB_D void ntt_dif_pass(u64* sm, unsigned L, unsigned s) {
     constexpr int R = 1 << K;
     const unsigned lgM = s - K, M = 1u << lgM, ntiles = 1u << (L - K);
     for (unsigned t = threadIdx.x; t < ntiles; t += blockDim.x) {
         const unsigned b = t & (M - 1), base = ((t >> lgM) << s) + b;
+        u64 tw[R];
+        if (lgM) {
+#pragma unroll
+            for (int p = 1; p < R; ++p) {
+                const unsigned q = __brev((unsigned)p) >> (32 - K);
+                tw[p] = __ldg(&d_W14[(b * q) << (NTT_SM_LG - s)]);
+            }
+        }
         u64 r[R];
 #pragma unroll
         for (int e = 0; e < R; ++e) r[e] = sm[ntt_pad(base + ((unsigned)e << lgM))];
         radix_dif<K>(r);
         if (lgM) {
 #pragma unroll
-            for (int p = 1; p < R; ++p) {
-                const unsigned q = __brev((unsigned)p) >> (32 - K);
-                r[p] = gl_mul(r[p], d_W14[(b * q) << (NTT_SM_LG - s)]);
-            }
+            for (int p = 1; p < R; ++p) r[p] = f_mul(r[p], tw[p]);
         }
 #pragma unroll
         for (int p = 0; p < R; ++p) sm[ntt_pad(base + ((unsigned)p << lgM))] = r[p];
@@ -107,14 +121,32 @@ __global__ void __launch_bounds__(512) lde_block_kernel(const u64* __restrict__ 
     const unsigned n = 1u << lg_n, jb = blockIdx.x;
     const u64* src = coeffs + (size_t)blockIdx.y * coeff_stride;
     const u64* ps = prescale ? prescale + (size_t)jb * n : nullptr;
-    for (unsigned i = threadIdx.x; i < n; i += blockDim.x) {
-        u64 v = src[i];
-        if (ps) v = gl_mul(v, ps[i]);
-        sm[ntt_pad(i)] = v;
+    // n is a multiple of 8 * blockDim whenever n >= 4096 (512 threads): 8 independent loads in flight per thread
+    if ((n & (8 * blockDim.x - 1)) == 0) {
+        for (unsigned i0 = threadIdx.x; i0 < n; i0 += 8 * blockDim.x) {
+            u64 v[8], w[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) v[u] = __ldg(src + i0 + u * blockDim.x);
+            if (ps) {
+#pragma unroll
+                for (int u = 0; u < 8; ++u) w[u] = __ldg(ps + i0 + u * blockDim.x);
+#pragma unroll
+                for (int u = 0; u < 8; ++u) v[u] = f_mul(v[u], w[u]);
+            }
+#pragma unroll
+            for (int u = 0; u < 8; ++u) sm[ntt_pad(i0 + u * blockDim.x)] = v[u];
+        }
+    } else {
+        for (unsigned i = threadIdx.x; i < n; i += blockDim.x) {
+            u64 v = src[i];
+            if (ps) v = f_mul(v, ps[i]);
+            sm[ntt_pad(i)] = v;
+        }
     }
     __syncthreads();
     ntt_dif_smem(sm, lg_n);
     u64* dst = out + (size_t)blockIdx.y * out_stride + (size_t)jb * n;
+#pragma unroll 8
     for (unsigned i = threadIdx.x; i < n; i += blockDim.x) dst[i] = sm[ntt_pad(i)];
 }
 

@@ -1,0 +1,85 @@
+"""Batch proving across GPUs — the host-side mirror of the reference aggregator's fan-out over independent leaf proofs
+(/root/reference/wormhole/aggregator/src/circuits/tree.rs:93-103 maps chunks over rayon; each call owns its circuit data and
+witness). Proofs are independent units, so ranks share NO data-path collective: rank r proves its slice on its own GPU with
+`streams` prover contexts in flight, and the 130-150 KB proofs are gathered on the host.
+
+Works with any initialised torch.distributed backend (NCCL on the GPU box, gloo in the CPU tests) or with none (world 1).
+"""
+import threading
+
+try:
+    import torch.distributed as dist
+except Exception:  # torch absent: single-process use only
+    dist = None
+
+
+def world():
+    if dist is not None and dist.is_available() and dist.is_initialized():
+        return dist.get_rank(), dist.get_world_size()
+    return 0, 1
+
+
+def shard_range(total, rank, world_size):
+    """Contiguous slice [lo, hi) of `total` proofs owned by `rank`; sizes differ by at most one, earlier ranks get the extra."""
+    if world_size <= 0 or not (0 <= rank < world_size):
+        raise ValueError("bad rank / world size")
+    base, extra = divmod(total, world_size)
+    lo = rank * base + min(rank, extra)
+    return lo, lo + base + (1 if rank < extra else 0)
+
+
+def run_streams(jobs, provers):
+    """Run jobs (list of zero-argument-free callables taking a prover) on len(provers) host threads, job i on prover
+    i % len(provers) in submission order; returns results in job order. The C ABI call drops the GIL."""
+    results = [None] * len(jobs)
+    errors = []
+
+    def worker(s):
+        try:
+            for i in range(s, len(jobs), len(provers)):
+                results[i] = jobs[i](provers[s])
+        except Exception as e:  # noqa: BLE001
+            errors.append(e)
+
+    threads = [threading.Thread(target=worker, args=(s,)) for s in range(min(len(provers), len(jobs)))]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    if errors:
+        raise errors[0]
+    return results
+
+
+def prove_batch(witnesses, provers, prove_fn, gather=True):
+    """Prove `witnesses` (a list, identical on every rank) as one distributed batch.
+
+    provers   this rank's prover contexts (one per stream), e.g. [ProverCircuit(..., device=local_rank)] * B distinct objects
+    prove_fn  prove_fn(prover, witness, global_index) -> proof bytes
+    Returns the full list of proofs in witness order on rank 0 (None elsewhere) when gather is set, else this rank's slice.
+    """
+    rank, ws = world()
+    lo, hi = shard_range(len(witnesses), rank, ws)
+    jobs = [(lambda p, i=i: prove_fn(p, witnesses[i], i)) for i in range(lo, hi)]
+    mine = run_streams(jobs, provers)
+    if not gather:
+        return mine
+    if ws == 1:
+        return mine
+    parts = [None] * ws if rank == 0 else None
+    dist.gather_object(mine, parts, dst=0)
+    if rank != 0:
+        return None
+    return [p for part in parts for p in part]
+
+
+def max_over_ranks(values, device=None):
+    """Element-wise max of a list of floats over all ranks (timing rule: a multi-GPU number is the slowest rank's)."""
+    rank, ws = world()
+    if ws == 1:
+        return list(values)
+    import torch
+
+    t = torch.tensor(list(values), dtype=torch.float64, device=device or "cpu")
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return [float(x) for x in t]

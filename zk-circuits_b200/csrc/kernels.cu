@@ -3,7 +3,6 @@
 // Integer-only; no tensor cores (nothing here is a dense contraction). Launchers are in kernels.h.
 #include "kernels.h"
 #include "poseidon.cuh"
-#include "ntt.cuh"
 #include <map>
 #include <tuple>
 #include <atomic>
@@ -30,9 +29,6 @@ unsigned long long kernel_launch_count() { return g_kernel_launches.load(); }
 // ---------------------------------------------------------------------------------------------
 // T = 2^32-th root of unity; T^E = rootA[E & 2047] * rootB[(E >> 11) & 2047] * rootC[E >> 22]
 __device__ u64 d_rootA[2048], d_rootB[2048], d_rootC[1024];
-constexpr unsigned W_LG = 14;                       // direct twiddle table for blocks up to 2^14
-__device__ u64 d_W[1 << (W_LG - 1)];                // w_{2^14}^k
-__device__ u64 d_Winv[1 << (W_LG - 1)];             // w_{2^14}^-k
 __device__ u32 d_rc3[3 * P_WIDTH * P_ROUNDS];       // Poseidon round constants as limbs, for per-lane (divergent) indexing
 
 ZKB_D u64 root_pow(u32 E) {
@@ -46,8 +42,10 @@ ZKB_D u64 root_pow_lg(unsigned lg, u32 e, bool inv) {
     return root_pow(E);
 }
 
-struct BlockNttArgs;
-struct StridedNttArgs;
+}  // namespace zkb
+#include "ntt.cuh"   // shared-memory NTT kernels (need root_pow)
+namespace zkb {
+
 static void ntt_set_func_attributes();   // defined with the NTT kernels below
 
 void device_tables_init(int device) {
@@ -77,21 +75,18 @@ void device_tables_init(int device) {
     ZKB_CUDA_CHECK(cudaMemcpyToSymbol(d_rootA, A.data(), 2048 * 8));
     ZKB_CUDA_CHECK(cudaMemcpyToSymbol(d_rootB, B.data(), 2048 * 8));
     ZKB_CUDA_CHECK(cudaMemcpyToSymbol(d_rootC, C.data(), 1024 * 8));
-    size_t half = size_t(1) << (W_LG - 1);
-    std::vector<u64> W(half), Wi(half);
-    u64 w = gl_root_of_unity(W_LG), wi = gl_inv(w);
-    W[0] = Wi[0] = 1;
-    for (size_t i = 1; i < half; ++i) { W[i] = gl_mul(W[i - 1], w); Wi[i] = gl_mul(Wi[i - 1], wi); }
-    ZKB_CUDA_CHECK(cudaMemcpyToSymbol(d_W, W.data(), half * 8));
-    ZKB_CUDA_CHECK(cudaMemcpyToSymbol(d_Winv, Wi.data(), half * 8));
+    const u64 w = gl_root_of_unity(NTT_SM_LG);
     {
         const size_t full = size_t(1) << NTT_SM_LG;
         std::vector<u64> W14(full);
         W14[0] = 1;
         for (size_t i = 1; i < full; ++i) W14[i] = gl_mul(W14[i - 1], w);
         ZKB_CUDA_CHECK(cudaMemcpyToSymbol(d_W14, W14.data(), full * 8));
-        u64 w16[8];
-        for (int k = 0; k < 8; ++k) w16[k] = W14[(size_t)k << (NTT_SM_LG - 4)];
+        u64 w16[16];
+        for (int k = 0; k < 8; ++k) {
+            w16[k] = W14[(size_t)k << (NTT_SM_LG - 4)];
+            w16[8 + k] = W14[(full - ((size_t)k << (NTT_SM_LG - 4))) & (full - 1)];
+        }
         ZKB_CUDA_CHECK(cudaMemcpyToSymbol(c_w16, w16, sizeof(w16)));
     }
     ntt_set_func_attributes();
@@ -292,161 +287,79 @@ void launch_salt_fill(u64* out, size_t stride, size_t num_leaves, u64 seed, unsi
 }
 
 // ---------------------------------------------------------------------------------------------
-// NTT family (v0: radix-2 stages in shared memory; blocks up to 2^14, strided pass above that)
+// NTT family: host side. Kernels are in ntt.cuh. n <= 2^14: one shared-memory kernel per transform; larger n: two steps
+// (n = n1 * n2: n1-point transforms down TB-wide column tiles + twiddle, then contiguous n2-point transforms).
 // ---------------------------------------------------------------------------------------------
-constexpr unsigned NTT_MAX_LB = 14;
-
-struct BlockNttArgs {
-    const u64* src; size_t src_stride;
-    u64* dst; size_t dst_stride;
-    unsigned lb;           // log2 block size (block = contiguous run of 2^lb elements)
-    unsigned blocks_per_col;
-    int dit;               // 0: DIF (natural in -> bit-reversed out), 1: DIT (bit-reversed in -> natural out)
-    int inverse;           // use inverse twiddles
-    int store_bitrev;      // dst[k] = result[bitrev(k)] within the block
-    u64 scale;             // multiply every output by this (1 = skip)
-};
-
-__global__ void __launch_bounds__(1024) ntt_block_kernel(BlockNttArgs a) {
-    extern __shared__ u64 sm[];
-    const unsigned mb = 1u << a.lb;
-    const u64* src = a.src + (size_t)blockIdx.y * a.src_stride + (size_t)blockIdx.x * mb;
-    u64* dst = a.dst + (size_t)blockIdx.y * a.dst_stride + (size_t)blockIdx.x * mb;
-    for (unsigned i = threadIdx.x; i < mb; i += blockDim.x) sm[i] = src[i];
-    __syncthreads();
-    const u64* W = a.inverse ? d_Winv : d_W;
-    const unsigned half = mb >> 1;
-    if (!a.dit) {
-        for (unsigned lh = a.lb; lh-- > 0;) {
-            unsigned h = 1u << lh;
-            for (unsigned p = threadIdx.x; p < half; p += blockDim.x) {
-                unsigned j = p & (h - 1);
-                unsigned i = ((p >> lh) << (lh + 1)) + j;
-                u64 x = sm[i], y = sm[i + h];
-                u64 tw = W[j << (W_LG - 1 - lh)];
-                sm[i] = gl_add(x, y);
-                sm[i + h] = gl_mul(gl_sub(x, y), tw);
-            }
-            __syncthreads();
-        }
-    } else {
-        for (unsigned lh = 0; lh < a.lb; ++lh) {
-            unsigned h = 1u << lh;
-            for (unsigned p = threadIdx.x; p < half; p += blockDim.x) {
-                unsigned j = p & (h - 1);
-                unsigned i = ((p >> lh) << (lh + 1)) + j;
-                u64 tw = W[j << (W_LG - 1 - lh)];
-                u64 x = sm[i], y = gl_mul(sm[i + h], tw);
-                sm[i] = gl_add(x, y);
-                sm[i + h] = gl_sub(x, y);
-            }
-            __syncthreads();
-        }
-    }
-    for (unsigned i = threadIdx.x; i < mb; i += blockDim.x) {
-        u64 v = a.store_bitrev ? sm[bitrev32(i, a.lb)] : sm[i];
-        if (a.scale != 1) v = gl_mul(v, a.scale);
-        dst[i] = v;
-    }
+struct LargePlan { unsigned lb, lg_n1, lg_tb; };
+static LargePlan large_plan(unsigned lg_n) {
+    if (lg_n > NTT_SM_LG + 10) throw std::runtime_error("NTT size too large (max 2^24)");
+    LargePlan p;
+    p.lb = lg_n >= 20 ? (lg_n - 8 > NTT_SM_LG ? NTT_SM_LG : (lg_n - 8 < 12 ? 12 : lg_n - 8)) : 12;
+    if (lg_n - p.lb > 10) p.lb = lg_n - 10;
+    p.lg_n1 = lg_n - p.lb;
+    p.lg_tb = p.lg_n1 >= 8 ? 4 : 12 - p.lg_n1;          // tile = n1 x TB >= 4096 elements, >= 128 B per row segment
+    return p;
 }
-
-struct StridedNttArgs {
-    u64* data; size_t stride;
-    unsigned lg_m;      // log2 transform size
-    unsigned lb;        // log2 of the contiguous block handled by the block kernel; this pass does h >= 2^lb
-    unsigned ltb;       // log2 tile width (consecutive elements per row)
-    int dit, inverse;
-};
-__global__ void __launch_bounds__(1024) ntt_strided_kernel(StridedNttArgs a) {
-    extern __shared__ u64 sm[];
-    const unsigned lT = a.lg_m - a.lb, T = 1u << lT, TB = 1u << a.ltb, mb = 1u << a.lb;
-    u64* col = a.data + (size_t)blockIdx.y * a.stride;
-    const unsigned b0 = blockIdx.x << a.ltb;
-    const unsigned tot = T << a.ltb;
-    for (unsigned idx = threadIdx.x; idx < tot; idx += blockDim.x) {
-        unsigned t = idx >> a.ltb, bb = idx & (TB - 1);
-        sm[idx] = col[(size_t)t * mb + b0 + bb];
-    }
-    __syncthreads();
-    const unsigned npairs = tot >> 1;
-    for (unsigned s = 0; s < lT; ++s) {
-        unsigned lg = a.dit ? s : (lT - 1 - s);          // g = 2^lg rows apart
-        unsigned g = 1u << lg;
-        unsigned lh = lg + a.lb;                         // h = g * mb
-        for (unsigned pidx = threadIdx.x; pidx < npairs; pidx += blockDim.x) {
-            unsigned bb = pidx & (TB - 1), pp = pidx >> a.ltb;
-            unsigned tj = pp & (g - 1);
-            unsigned t = ((pp >> lg) << (lg + 1)) + tj;
-            unsigned i0 = (t << a.ltb) + bb, i1 = i0 + (g << a.ltb);
-            u32 e = tj * mb + b0 + bb;                   // exponent of w_{2h}
-            u64 tw = root_pow_lg(lh + 1, e, a.inverse);
-            u64 x = sm[i0], y = sm[i1];
-            if (!a.dit) {
-                sm[i0] = gl_add(x, y);
-                sm[i1] = gl_mul(gl_sub(x, y), tw);
-            } else {
-                y = gl_mul(y, tw);
-                sm[i0] = gl_add(x, y);
-                sm[i1] = gl_sub(x, y);
-            }
-        }
-        __syncthreads();
-    }
-    for (unsigned idx = threadIdx.x; idx < tot; idx += blockDim.x) {
-        unsigned t = idx >> a.ltb, bb = idx & (TB - 1);
-        col[(size_t)t * mb + b0 + bb] = sm[idx];
-    }
-}
-
 static void ntt_set_func_attributes() {   // per device: opt in to > 48 KB dynamic shared memory
-    ZKB_CUDA_CHECK(cudaFuncSetAttribute(ntt_block_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(u64) << NTT_MAX_LB)));
-    ZKB_CUDA_CHECK(cudaFuncSetAttribute(ntt_strided_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
     ZKB_CUDA_CHECK(cudaFuncSetAttribute(lde_block_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ntt_smem_bytes(NTT_SM_LG)));
     ZKB_CUDA_CHECK(cudaFuncSetAttribute(intt_block_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ntt_smem_bytes(NTT_SM_LG)));
+    ZKB_CUDA_CHECK(cudaFuncSetAttribute(ntt_cols_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ntt_smem_bytes(NTT_SM_LG)));
 }
 static unsigned ntt_block_threads(unsigned lg_n) {
     unsigned t = lg_n >= 4 ? (1u << (lg_n - 4)) : 1u;
     return t < 32 ? 32 : (t > 512 ? 512 : t);
 }
-// (shift * w_N^j)^k tables for the fused coset pre-scale, cached per device for the lifetime of the process
-// (1 MB for the wormhole circuit's n = 2^14, rate 8; the FRI layers add a few smaller ones).
-static const u64* coset_table(unsigned lg_n, unsigned rate_bits, u64 shift, cudaStream_t st) {
+// Coset pre-scale tables (shift * w_N^j)^k, cached per device for the lifetime of the process. n <= 2^14: one table
+// [2^rate][n] (1 MB for the wormhole circuit). Larger n: the exponent is split k = r * n2 + b, tables [2^rate][n1], [2^rate][n2].
+struct CosetTables { u64* full = nullptr; u64* pre1 = nullptr; u64* pre2 = nullptr; };
+__global__ void coset_table2_kernel(u64* pre1, u64* pre2, unsigned lg_n1, unsigned lg_n2, unsigned rate_bits, u64 shift, u64 w_N) {
+    const unsigned k = blockIdx.x * blockDim.x + threadIdx.x, jb = blockIdx.y;
+    const u64 base = gl_mul(shift, gl_pow(w_N, bitrev32(jb, rate_bits)));
+    if (k < (1u << lg_n2)) pre2[((size_t)jb << lg_n2) + k] = gl_pow(base, k);
+    if (k < (1u << lg_n1)) pre1[((size_t)jb << lg_n1) + k] = gl_pow(gl_pow(base, u64(1) << lg_n2), k);
+}
+static CosetTables coset_tables(unsigned lg_n, unsigned rate_bits, u64 shift, cudaStream_t st) {
     static std::mutex mu;
-    static std::map<std::tuple<int, unsigned, unsigned, u64>, u64*> cache;
+    static std::map<std::tuple<int, unsigned, unsigned, u64>, CosetTables> cache;
     int dev = 0;
     ZKB_CUDA_CHECK(cudaGetDevice(&dev));
     std::lock_guard<std::mutex> lk(mu);
     auto key = std::make_tuple(dev, lg_n, rate_bits, shift);
     auto it = cache.find(key);
     if (it != cache.end()) return it->second;
-    u64* tab = nullptr;
-    const size_t n = size_t(1) << lg_n;
-    ZKB_CUDA_CHECK(cudaMalloc(&tab, (n << rate_bits) * sizeof(u64)));
-    dim3 grid((unsigned)((n + 127) / 128), 1u << rate_bits);
-    ZKB_COUNT_LAUNCH();
-    coset_table_kernel<<<grid, 128, 0, st>>>(tab, lg_n, rate_bits, shift, gl_root_of_unity(lg_n + rate_bits));
-    ZKB_CUDA_CHECK(cudaStreamSynchronize(st));       // other streams may use the table as soon as it is in the cache
-    cache[key] = tab;
-    return tab;
+    CosetTables t;
+    const u64 w_N = gl_root_of_unity(lg_n + rate_bits);
+    if (lg_n <= NTT_SM_LG) {
+        const size_t n = size_t(1) << lg_n;
+        ZKB_CUDA_CHECK(cudaMalloc(&t.full, (n << rate_bits) * sizeof(u64)));
+        dim3 grid((unsigned)((n + 127) / 128), 1u << rate_bits);
+        ZKB_COUNT_LAUNCH();
+        coset_table_kernel<<<grid, 128, 0, st>>>(t.full, lg_n, rate_bits, shift, w_N);
+    } else {
+        const LargePlan p = large_plan(lg_n);
+        ZKB_CUDA_CHECK(cudaMalloc(&t.pre1, (sizeof(u64) << p.lg_n1) << rate_bits));
+        ZKB_CUDA_CHECK(cudaMalloc(&t.pre2, (sizeof(u64) << p.lb) << rate_bits));
+        const unsigned m = 1u << (p.lb > p.lg_n1 ? p.lb : p.lg_n1);
+        dim3 grid((m + 127) / 128, 1u << rate_bits);
+        ZKB_COUNT_LAUNCH();
+        coset_table2_kernel<<<grid, 128, 0, st>>>(t.pre1, t.pre2, p.lg_n1, p.lb, rate_bits, shift, w_N);
+    }
+    ZKB_CUDA_CHECK(cudaStreamSynchronize(st));       // other streams may use the tables as soon as they are in the cache
+    cache[key] = t;
+    return t;
 }
-static void run_block_pass(const BlockNttArgs& a, int ncols, cudaStream_t st) {
-    unsigned mb = 1u << a.lb;
-    unsigned threads = mb / 2 < 1024 ? (mb / 2 < 32 ? 32 : mb / 2) : 1024;
-    dim3 grid(a.blocks_per_col, (unsigned)ncols);
+// the two steps for n > 2^14; z = number of coset blocks written (block jb of dst at + jb * n)
+static void run_large_transform(const u64* src, size_t src_stride, u64* dst, size_t dst_stride, int ncols, unsigned lg_n,
+                                unsigned nblk, const u64* pre1, const u64* pre2, bool inv, cudaStream_t st) {
+    const LargePlan p = large_plan(lg_n);
+    ColsNttArgs a{src, src_stride, dst, dst_stride, lg_n, p.lg_n1, p.lg_tb, pre1, pre2, inv ? 1 : 0};
+    dim3 g1(1u << (p.lb - p.lg_tb), (unsigned)ncols, nblk);
     ZKB_COUNT_LAUNCH();
-    ntt_block_kernel<<<grid, threads, sizeof(u64) * mb, st>>>(a);
-}
-static void run_strided_pass(u64* data, size_t stride, int ncols, unsigned lg_m, unsigned lb, bool dit, bool inverse, cudaStream_t st) {
-    unsigned lT = lg_m - lb;
-    if (lT > 12) throw std::runtime_error("NTT size too large for the two-pass decomposition");
-    unsigned ltb = lT >= 12 ? 1 : (12 - lT);        // tile = 4096 elements (32 KB) ...
-    if (ltb < 4 && lT <= 9) ltb = 4;                // ... but keep >= 128 B per row when it fits 64 KB
-    if (ltb > lb) ltb = lb;
-    StridedNttArgs a{data, stride, lg_m, lb, ltb, dit ? 1 : 0, inverse ? 1 : 0};
-    size_t smem = sizeof(u64) << (lT + ltb);
-    dim3 grid(1u << (lb - ltb), (unsigned)ncols);
+    ntt_cols_kernel<<<g1, 256, ntt_smem_bytes(p.lg_n1 + p.lg_tb), st>>>(a);
+    dim3 g2(nblk << p.lg_n1, (unsigned)ncols);
     ZKB_COUNT_LAUNCH();
-    ntt_strided_kernel<<<grid, 1024, smem, st>>>(a);
+    lde_block_kernel<<<g2, ntt_block_threads(p.lb), ntt_smem_bytes(p.lb), st>>>(dst, dst_stride, dst, dst_stride, p.lb, nullptr,
+                                                                                size_t(1) << p.lb, inv ? 1 : 0);
 }
 
 // in-place bit-reversal permutation with scaling
@@ -463,12 +376,14 @@ __global__ void bitrev_scale_kernel(u64* data, size_t stride, unsigned lg_n, u64
         col[k] = gl_mul(col[k], scale);
     }
 }
-
-void launch_bitrev_permute(u64* data, size_t stride, int ncols, unsigned lg_n, cudaStream_t st) {
-    if (ncols <= 0) return;
+static void run_bitrev_scale(u64* data, size_t stride, int ncols, unsigned lg_n, u64 scale, cudaStream_t st) {
     dim3 grid((unsigned)(((size_t(1) << lg_n) + 255) / 256), (unsigned)ncols);
     ZKB_COUNT_LAUNCH();
-    bitrev_scale_kernel<<<grid, 256, 0, st>>>(data, stride, lg_n, 1);
+    bitrev_scale_kernel<<<grid, 256, 0, st>>>(data, stride, lg_n, scale);
+}
+void launch_bitrev_permute(u64* data, size_t stride, int ncols, unsigned lg_n, cudaStream_t st) {
+    if (ncols <= 0) return;
+    run_bitrev_scale(data, stride, ncols, lg_n, 1, st);
 }
 
 void launch_intt_natural(const u64* src, size_t src_stride, u64* dst, size_t dst_stride, int ncols, unsigned lg_n,
@@ -481,62 +396,23 @@ void launch_intt_natural(const u64* src, size_t src_stride, u64* dst, size_t dst
         intt_block_kernel<<<(unsigned)ncols, ntt_block_threads(lg_n), ntt_smem_bytes(lg_n), st>>>(src, src_stride, dst, dst_stride, lg_n, 0, ninv);
         return;
     }
-    if (src != dst)
-        ZKB_CUDA_CHECK(cudaMemcpy2DAsync(dst, dst_stride * 8, src, src_stride * 8, (size_t(8) << lg_n), ncols, cudaMemcpyDeviceToDevice, st));
-    unsigned lb = 13;
-    run_strided_pass(dst, dst_stride, ncols, lg_n, lb, false, true, st);
-    BlockNttArgs a{dst, dst_stride, dst, dst_stride, lb, 1u << (lg_n - lb), 0, 1, 0, 1};
-    run_block_pass(a, ncols, st);
-    dim3 grid((unsigned)(((size_t(1) << lg_n) + 255) / 256), (unsigned)ncols);
-    ZKB_COUNT_LAUNCH();
-    bitrev_scale_kernel<<<grid, 256, 0, st>>>(dst, dst_stride, lg_n, ninv);
-}
-
-// out[c][jb * n + k] = coeff[c][k] * (shift * w_M^j)^k, j = bitrev_r(jb)
-__global__ void lde_prescale_kernel(const u64* __restrict__ coeffs, size_t coeff_stride, u64* __restrict__ out, size_t out_stride,
-                                    int ncols, unsigned lg_n, unsigned rate_bits, u64 shift, int cols_per_group) {
-    size_t k = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
-    size_t n = size_t(1) << lg_n;
-    if (k >= n) return;
-    u64 sk = gl_pow(shift, k);
-    int c0 = blockIdx.y * cols_per_group, c1 = min(ncols, c0 + cols_per_group);
-    unsigned lgM = lg_n + rate_bits;
-    for (unsigned jb = 0; jb < (1u << rate_bits); ++jb) {
-        unsigned j = bitrev32(jb, rate_bits);
-        u64 m = gl_mul(sk, root_pow_lg(lgM, (u32)(((u64)j * k) & ((u64(1) << lgM) - 1)), false));
-        for (int c = c0; c < c1; ++c)
-            out[(size_t)c * out_stride + (size_t)jb * n + k] = gl_mul(coeffs[(size_t)c * coeff_stride + k], m);
-    }
+    run_large_transform(src, src_stride, dst, dst_stride, ncols, lg_n, 1, nullptr, nullptr, true, st);   // bit-reversed result
+    run_bitrev_scale(dst, dst_stride, ncols, lg_n, ninv, st);
 }
 
 void launch_lde(const u64* coeffs, size_t coeff_stride, u64* out, size_t out_stride, int ncols, unsigned lg_n,
                 unsigned rate_bits, u64 shift, cudaStream_t st) {
     if (ncols <= 0) return;
-    size_t n = size_t(1) << lg_n;
+    const bool plain = rate_bits == 0 && shift == 1;
+    CosetTables t;
+    if (!plain) t = coset_tables(lg_n, rate_bits, shift, st);
     if (lg_n <= NTT_SM_LG) {
-        const u64* tab = (rate_bits == 0 && shift == 1) ? nullptr : coset_table(lg_n, rate_bits, shift, st);
         dim3 grid(1u << rate_bits, (unsigned)ncols);
         ZKB_COUNT_LAUNCH();
-        lde_block_kernel<<<grid, ntt_block_threads(lg_n), ntt_smem_bytes(lg_n), st>>>(coeffs, coeff_stride, out, out_stride, lg_n, tab);
+        lde_block_kernel<<<grid, ntt_block_threads(lg_n), ntt_smem_bytes(lg_n), st>>>(coeffs, coeff_stride, out, out_stride, lg_n, t.full, 0, 0);
         return;
     }
-    int groups = ncols < 8 ? ncols : 8;
-    int cpg = (ncols + groups - 1) / groups;
-    dim3 grid((unsigned)((n + 127) / 128), (unsigned)((ncols + cpg - 1) / cpg));
-    ZKB_COUNT_LAUNCH();
-    lde_prescale_kernel<<<grid, 128, 0, st>>>(coeffs, coeff_stride, out, out_stride, ncols, lg_n, rate_bits, shift, cpg);
-    unsigned nblk = 1u << rate_bits;
-    if (lg_n <= NTT_MAX_LB) {
-        BlockNttArgs a{out, out_stride, out, out_stride, lg_n, nblk, 0, 0, 0, 1};
-        run_block_pass(a, ncols, st);
-    } else {
-        unsigned lb = 13;
-        // each of the 2^rate_bits coset blocks is an independent size-n transform: treat them as extra columns
-        for (unsigned jb = 0; jb < nblk; ++jb)
-            run_strided_pass(out + (size_t)jb * n, out_stride, ncols, lg_n, lb, false, false, st);
-        BlockNttArgs a{out, out_stride, out, out_stride, lb, nblk << (lg_n - lb), 0, 0, 0, 1};
-        run_block_pass(a, ncols, st);
-    }
+    run_large_transform(coeffs, coeff_stride, out, out_stride, ncols, lg_n, 1u << rate_bits, t.pre1, t.pre2, false, st);
 }
 
 // data[k] *= c0 * base^k
@@ -554,10 +430,9 @@ void launch_coset_intt_bitrev(u64* data, size_t stride, int ncols, unsigned lg_m
         ZKB_COUNT_LAUNCH();
         intt_block_kernel<<<(unsigned)ncols, ntt_block_threads(lg_m), ntt_smem_bytes(lg_m), st>>>(data, stride, data, stride, lg_m, 1, 1);
     } else {
-        unsigned lb = 13;
-        BlockNttArgs a{data, stride, data, stride, lb, 1u << (lg_m - lb), 1, 1, 0, 1};
-        run_block_pass(a, ncols, st);
-        run_strided_pass(data, stride, ncols, lg_m, lb, true, true, st);
+        run_bitrev_scale(data, stride, ncols, lg_m, 1, st);                                             // leaf order -> natural
+        run_large_transform(data, stride, data, stride, ncols, lg_m, 1, nullptr, nullptr, true, st);   // -> bit-reversed coefficients
+        run_bitrev_scale(data, stride, ncols, lg_m, 1, st);
     }
     ZKB_COUNT_LAUNCH();
     scale_pows_kernel<<<(unsigned)((m + 255) / 256), 256, 0, st>>>(data, stride, ncols, m, gl_inv(u64(1) << lg_m), gl_inv(shift));

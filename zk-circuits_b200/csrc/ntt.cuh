@@ -17,7 +17,7 @@ namespace zkb {
 
 constexpr unsigned NTT_SM_LG = 14;                       // largest transform held in shared memory
 __device__ u64 d_W14[1u << NTT_SM_LG];                   // w_{2^14}^t, 0 <= t < 2^14
-__constant__ u64 c_w16[8];                               // w_16^k, k < 8
+__constant__ u64 c_w16[16];                              // w_16^k, k < 8, then w_16^-k, k < 8
 
 // canonical in, canonical out
 ZKB_D u64 f_sub(u64 a, u64 b) {
@@ -56,9 +56,9 @@ ZKB_D u64 f_mul(u64 a, u64 b) { return f_canon(gl_mul_lazy(a, b)); }
 ZKB_D unsigned ntt_pad(unsigned i) { return i + (i >> 4); }          // one spare word per 16: keeps small-stride passes off one bank
 inline size_t ntt_smem_bytes(unsigned lg) { return sizeof(u64) * ((size_t(1) << lg) + (size_t(1) << lg) / 16 + 1); }
 
-// in-register DIF of 2^K elements (K <= 4); r[p] ends up holding output index bitrev_K(p)
+// in-register DIF of 2^K elements (K <= 4); r[p] ends up holding output index bitrev_K(p). w16 = c_w16 (+8 for inverse)
 template <int K>
-ZKB_D void radix_dif(u64* r) {
+ZKB_D void radix_dif(u64* r, const u64* w16) {
 #pragma unroll
     for (int t = 0; t < K; ++t) {
         const int half = 1 << (K - 1 - t);
@@ -69,33 +69,39 @@ ZKB_D void radix_dif(u64* r) {
                 u64 a = r[g + j], b = r[g + j + half];
                 r[g + j] = f_add(a, b);
                 u64 d = f_sub(a, b);
-                r[g + j + half] = j ? f_mul(d, c_w16[j * (8 / half)]) : d;
+                r[g + j + half] = j ? f_mul(d, w16[j * (8 / half)]) : d;
             }
         }
     }
 }
 
-// one radix-2^K pass over sm[0 .. 2^L): sub-transforms of size 2^s, tile = elements b + e * 2^(s-K).
-// The pass twiddles are fetched BEFORE the butterflies so that their L1/L2 latency hides behind the arithmetic.
+// One radix-2^K pass over sm[0 .. 2^L). The array is 2^lgC interleaved transforms (element index = row * 2^lgC + c;
+// lgC = 0 for a single transform): sub-transforms of 2^(s - lgC) rows, tile = elements b + e * 2^(s-K).
+// The pass twiddles w^(row(b) * bitrev(p)) are fetched BEFORE the butterflies so their latency hides behind the arithmetic.
 template <int K>
-ZKB_D void ntt_dif_pass(u64* sm, unsigned L, unsigned s) {
+ZKB_D void ntt_dif_pass(u64* sm, unsigned L, unsigned s, unsigned lgC, bool inv) {
     constexpr int R = 1 << K;
     const unsigned lgM = s - K, M = 1u << lgM, ntiles = 1u << (L - K);
+    const u64* w16 = c_w16 + (inv ? 8 : 0);
+    const unsigned tmask = (1u << NTT_SM_LG) - 1;
     for (unsigned t = threadIdx.x; t < ntiles; t += blockDim.x) {
         const unsigned b = t & (M - 1), base = ((t >> lgM) << s) + b;
         u64 tw[R];
-        if (lgM) {
+        if (lgM > lgC) {
+            const unsigned brow = b >> lgC;
 #pragma unroll
             for (int p = 1; p < R; ++p) {
                 const unsigned q = __brev((unsigned)p) >> (32 - K);
-                tw[p] = __ldg(&d_W14[(b * q) << (NTT_SM_LG - s)]);
+                unsigned idx = (brow * q) << (NTT_SM_LG - (s - lgC));
+                if (inv) idx = (0u - idx) & tmask;
+                tw[p] = __ldg(&d_W14[idx]);
             }
         }
         u64 r[R];
 #pragma unroll
         for (int e = 0; e < R; ++e) r[e] = sm[ntt_pad(base + ((unsigned)e << lgM))];
-        radix_dif<K>(r);
-        if (lgM) {
+        radix_dif<K>(r, w16);
+        if (lgM > lgC) {
 #pragma unroll
             for (int p = 1; p < R; ++p) r[p] = f_mul(r[p], tw[p]);
         }
@@ -103,30 +109,35 @@ ZKB_D void ntt_dif_pass(u64* sm, unsigned L, unsigned s) {
         for (int p = 0; p < R; ++p) sm[ntt_pad(base + ((unsigned)p << lgM))] = r[p];
     }
 }
-// forward transform in place: natural order in, sm[pad(i)] = X[bitrev_L(i)] out. Ends with a barrier.
-ZKB_D void ntt_dif_smem(u64* sm, unsigned L) {
+// transform in place (forward, or inverse without the 1/n): natural order in, bit-reversed rows out
+// (sm[pad(i * 2^lgC + c)] = X_c[bitrev(i)]). Ends with a barrier.
+ZKB_D void ntt_dif_smem(u64* sm, unsigned L, unsigned lgC = 0, bool inv = false) {
     unsigned s = L;
-    while (s >= 4) { ntt_dif_pass<4>(sm, L, s); s -= 4; __syncthreads(); }
-    if (s == 3) ntt_dif_pass<3>(sm, L, s);
-    else if (s == 2) ntt_dif_pass<2>(sm, L, s);
-    else if (s == 1) ntt_dif_pass<1>(sm, L, s);
-    if (s) __syncthreads();
+    while (s >= lgC + 4) { ntt_dif_pass<4>(sm, L, s, lgC, inv); s -= 4; __syncthreads(); }
+    const unsigned rem = s - lgC;
+    if (rem == 3) ntt_dif_pass<3>(sm, L, s, lgC, inv);
+    else if (rem == 2) ntt_dif_pass<2>(sm, L, s, lgC, inv);
+    else if (rem == 1) ntt_dif_pass<1>(sm, L, s, lgC, inv);
+    if (rem) __syncthreads();
 }
 
 // coset LDE of one column block: out[jb * n + i] = sum_k coeff[k] (shift w_N^j)^k w_n^(k bitrev(i)),  j = bitrev_r(jb)
 // prescale: [2^rate_bits][n] table of (shift w_N^j)^k, or null for the plain transform (shift 1, rate 0)
-__global__ void __launch_bounds__(512) lde_block_kernel(const u64* __restrict__ coeffs, size_t coeff_stride, u64* __restrict__ out,
-                                                        size_t out_stride, unsigned lg_n, const u64* __restrict__ prescale) {
+// src_block_stride = 0: every block jb transforms the same n coefficients (LDE); = n: block jb transforms its own
+// contiguous run (second step of the two-step transform for n > 2^14; coeffs may alias out). inv: inverse twiddles.
+__global__ void __launch_bounds__(512) lde_block_kernel(const u64* coeffs, size_t coeff_stride, u64* out,
+                                                        size_t out_stride, unsigned lg_n, const u64* __restrict__ prescale,
+                                                        size_t src_block_stride, int inv) {
     extern __shared__ u64 sm[];
     const unsigned n = 1u << lg_n, jb = blockIdx.x;
-    const u64* src = coeffs + (size_t)blockIdx.y * coeff_stride;
+    const u64* src = coeffs + (size_t)blockIdx.y * coeff_stride + (size_t)jb * src_block_stride;
     const u64* ps = prescale ? prescale + (size_t)jb * n : nullptr;
     // n is a multiple of 8 * blockDim whenever n >= 4096 (512 threads): 8 independent loads in flight per thread
     if ((n & (8 * blockDim.x - 1)) == 0) {
         for (unsigned i0 = threadIdx.x; i0 < n; i0 += 8 * blockDim.x) {
             u64 v[8], w[8];
 #pragma unroll
-            for (int u = 0; u < 8; ++u) v[u] = __ldg(src + i0 + u * blockDim.x);
+            for (int u = 0; u < 8; ++u) v[u] = src[i0 + u * blockDim.x];
             if (ps) {
 #pragma unroll
                 for (int u = 0; u < 8; ++u) w[u] = __ldg(ps + i0 + u * blockDim.x);
@@ -144,10 +155,45 @@ __global__ void __launch_bounds__(512) lde_block_kernel(const u64* __restrict__ 
         }
     }
     __syncthreads();
-    ntt_dif_smem(sm, lg_n);
+    ntt_dif_smem(sm, lg_n, 0, inv != 0);
     u64* dst = out + (size_t)blockIdx.y * out_stride + (size_t)jb * n;
 #pragma unroll 8
     for (unsigned i = threadIdx.x; i < n; i += blockDim.x) dst[i] = sm[ntt_pad(i)];
+}
+
+// First step of the two-step transform for n = n1 * n2 > 2^14 (view a column as an n1 x n2 matrix, row r = elements
+// [r n2, (r+1) n2)): a CTA takes a tile of TB consecutive matrix columns, runs the n1-point DIF down each of them in
+// shared memory, multiplies entry (row, b) by w_n^(+-b * bitrev(row)) and writes it back; the rows are then independent
+// n2-point transforms (lde_block_kernel). pre1/pre2: optional coset pre-scale factors (s^n2)^r and s^b, s = shift w_N^j.
+struct ColsNttArgs {
+    const u64* src; size_t src_stride;      // column c, coset-independent source (n elements)
+    u64* dst; size_t dst_stride;            // column c, block jb at + jb * n
+    unsigned lg_n, lg_n1, lg_tb;
+    const u64* pre1; const u64* pre2;       // [2^rate][n1], [2^rate][n2] or null
+    int inv;
+};
+__global__ void __launch_bounds__(256) ntt_cols_kernel(ColsNttArgs a) {
+    extern __shared__ u64 sm[];
+    const unsigned lg_n2 = a.lg_n - a.lg_n1, n1 = 1u << a.lg_n1, n2 = 1u << lg_n2, TB = 1u << a.lg_tb;
+    const unsigned b0 = blockIdx.x << a.lg_tb, jb = blockIdx.z;
+    const u64* src = a.src + (size_t)blockIdx.y * a.src_stride;
+    u64* dst = a.dst + (size_t)blockIdx.y * a.dst_stride + ((size_t)jb << a.lg_n);
+    const unsigned tot = n1 << a.lg_tb;
+    for (unsigned idx = threadIdx.x; idx < tot; idx += blockDim.x) {
+        const unsigned r = idx >> a.lg_tb, c = idx & (TB - 1);
+        u64 v = src[(size_t)r * n2 + b0 + c];
+        if (a.pre1) v = f_mul(v, f_mul(a.pre1[(size_t)jb * n1 + r], a.pre2[(size_t)jb * n2 + b0 + c]));
+        sm[ntt_pad(idx)] = v;
+    }
+    __syncthreads();
+    ntt_dif_smem(sm, a.lg_n1 + a.lg_tb, a.lg_tb, a.inv != 0);
+    for (unsigned idx = threadIdx.x; idx < tot; idx += blockDim.x) {
+        const unsigned r = idx >> a.lg_tb, c = idx & (TB - 1);
+        const unsigned q1 = bitrev32(r, a.lg_n1), b = b0 + c;
+        u32 E = (u32)(((u64)b * q1) << (32 - a.lg_n));       // b q1 < n
+        if (a.inv) E = 0u - E;
+        dst[(size_t)r * n2 + b] = f_mul(sm[ntt_pad(idx)], root_pow(E));
+    }
 }
 
 // inverse transform of one column: values on <w_n> (natural order, or bit-reversed if in_bitrev) -> coefficients

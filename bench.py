@@ -89,6 +89,7 @@ def reference_arm(args, rank):
     import oracle as O
 
     O.build()
+    O.set_num_threads(os.cpu_count() or 1)     # torchrun exports OMP_NUM_THREADS=1; the CPU arm gets every host core
     s = O.Synth(zk=True, seed=1, **O.Synth.WORMHOLE)
     c = O.Circuit(s.common, s.const_sigma_values)
     steps = max(1, args.steps)
@@ -111,10 +112,32 @@ def reference_arm(args, rank):
                          "sample": f"{steps} full proofs of the bench circuit with the oracle's restated Plonky2 prover (OpenMP)"},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
+
+
+_REAL_STDOUT = None
+
+
+def emit(line):
+    """The ONE JSON line goes to the process's original stdout; everything else written to fd 1 by libraries
+    (e.g. NCCL's version banner) was redirected to stderr by quiet_stdout()."""
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, data)
+
+
+def quiet_stdout():
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
 
 
 def main():
+    quiet_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
@@ -292,6 +315,7 @@ def main():
         import oracle as O   # CPU baseline leg only
 
         O.build()
+        O.set_num_threads(os.cpu_count() or 1)
         os_ = O.Synth(zk=True, seed=1, **O.Synth.WORMHOLE)
         oc = O.Circuit(os_.common, os_.const_sigma_values)
         t0 = time.perf_counter()
@@ -300,7 +324,7 @@ def main():
         line["cpu_baseline"] = {"value": 1.0 / dt, "unit": UNIT, "cores": O.num_threads(), "kind": "port",
                                 "sample": "1 full proof of the bench circuit, oracle's restated Plonky2 prover (OpenMP)",
                                 "bytes_identical_to_gpu_proof": bool(ref == proof)}
-    print(json.dumps(line), flush=True)
+    emit(line)
     if dist is not None:
         dist.destroy_process_group()
 

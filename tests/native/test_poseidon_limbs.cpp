@@ -69,7 +69,8 @@ int main(int argc, char** argv) {
         for (int t = 0; t < 20000; ++t) {
             int x[12]; u32 y[12];
             for (int i = 0; i < 12; ++i) { int m = rng() % 4; x[i] = m == 0 ? lo : m == 1 ? hi : lo + (int)(rng() % (u64)(hi - lo + 1)); y[i] = (u32)x[i]; }
-            mds_limb12(y);
+            static const u32 zeros[36] = {0};
+            mds_limb12(y, zeros);
             for (int r = 0; r < 12; ++r) {
                 long long acc = r == 0 ? 8ll * x[0] : 0;
                 for (int i = 0; i < 12; ++i) acc += (long long)x[(i + r) % 12] * C[i];

@@ -68,3 +68,13 @@ def test_no_cpu_fallback(zkb):
     with pytest.raises(zkb.ZkbError) as e:
         zkb.lde_batch(np.zeros((1, 8), dtype=np.uint64))
     assert e.value.status == "ZKB_E_CUDA"
+
+
+def test_rust_sys_crate_declares_every_header_symbol():
+    """rust/zkb200-sys cannot be compiled here (no Rust toolchain); keep it at least in step with the header."""
+    rs = open(os.path.join(ROOT, "rust", "zkb200-sys", "src", "lib.rs")).read()
+    declared = set(re.findall(r"pub fn (zkb_[a-z_0-9]+)\s*\(", rs))
+    assert declared == set(declared_symbols())
+    hdr = open(os.path.join(ROOT, "include", "zkb200.h")).read()
+    for name, val in re.findall(r"pub const (ZKB_E_[A-Z_]+): c_int = (-?\d+);", rs):
+        assert re.search(name + r"\s*=\s*" + val + r"\b", hdr), name

@@ -29,7 +29,7 @@ unsigned long long kernel_launch_count() { return g_kernel_launches.load(); }
 // ---------------------------------------------------------------------------------------------
 // T = 2^32-th root of unity; T^E = rootA[E & 2047] * rootB[(E >> 11) & 2047] * rootC[E >> 22]
 __device__ u64 d_rootA[2048], d_rootB[2048], d_rootC[1024];
-__device__ u32 d_rc3[3 * P_WIDTH * P_ROUNDS];       // Poseidon round constants as limbs, for per-lane (divergent) indexing
+__device__ u32 d_rc3[RC3_WORDS];       // Poseidon round constants as limbs, for per-lane (divergent) indexing
 
 ZKB_D u64 root_pow(u32 E) {
     u64 r = gl_mul(d_rootA[E & 2047], d_rootB[(E >> 11) & 2047]);
@@ -57,8 +57,8 @@ void device_tables_init(int device) {
     ZKB_CUDA_CHECK(cudaGetDevice(&prev));
     ZKB_CUDA_CHECK(cudaSetDevice(device));
     ZKB_CUDA_CHECK(cudaMemcpyToSymbol(c_rc, host_round_constants(), sizeof(u64) * P_WIDTH * P_ROUNDS));
-    ZKB_CUDA_CHECK(cudaMemcpyToSymbol(c_rc3, host_round_constant_limbs(), sizeof(u32) * 3 * P_WIDTH * P_ROUNDS));
-    ZKB_CUDA_CHECK(cudaMemcpyToSymbol(d_rc3, host_round_constant_limbs(), sizeof(u32) * 3 * P_WIDTH * P_ROUNDS));
+    ZKB_CUDA_CHECK(cudaMemcpyToSymbol(c_rc3, host_round_constant_limbs(), sizeof(u32) * RC3_WORDS));
+    ZKB_CUDA_CHECK(cudaMemcpyToSymbol(d_rc3, host_round_constant_limbs(), sizeof(u32) * RC3_WORDS));
     {
         std::vector<u64> rc2(2 * P_WIDTH * (P_ROUNDS + 1), 0);
         for (int i = 0; i < P_WIDTH * P_ROUNDS; ++i) {
@@ -181,10 +181,15 @@ __global__ void __launch_bounds__(128) merkle_leaves_ext_kernel(const u64* __res
     }
     store_digest(digests, l, s);
 }
+__global__ void merkle_leaves_ext_wide_kernel(const u64* __restrict__ a, const u64* __restrict__ b, int arity, size_t num_leaves,
+                                              u64* __restrict__ digests);   // defined with the lane-parallel kernels below
 void launch_merkle_leaves_ext(const u64* a, const u64* b, int arity, size_t num_leaves, u64* digests, cudaStream_t st) {
     if (!num_leaves) return;
     ZKB_COUNT_LAUNCH();
-    merkle_leaves_ext_kernel<<<(unsigned)((num_leaves + 127) / 128), 128, 0, st>>>(a, b, arity, num_leaves, digests);
+    if (num_leaves <= 4096 && 2 * arity > 4)   // MERKLE_WIDE_MAX_NODES: latency-bound with one leaf per thread
+        merkle_leaves_ext_wide_kernel<<<(unsigned)((num_leaves + 7) / 8), 128, 0, st>>>(a, b, arity, num_leaves, digests);
+    else
+        merkle_leaves_ext_kernel<<<(unsigned)((num_leaves + 127) / 128), 128, 0, st>>>(a, b, arity, num_leaves, digests);
 }
 
 // one parent per thread: parent = permute(left ‖ right ‖ 0000)[0..4]
@@ -215,15 +220,8 @@ size_t merkle_digest_count(size_t num_leaves, unsigned cap_height) {
 // a single dependency chain (~45 us per level measured): here 12 lanes hold the 12 state words of one node (two nodes
 // per warp, lanes 0-11 and 16-27), every lane runs the same S-box code on its own word, and the circulant MDS is
 // out_j = sum_i C[i] * x_{(j+i) mod 12}, i.e. 11 warp shuffles per limb. ~4x the issue slots per node, ~1/5 the latency.
-__global__ void __launch_bounds__(128) merkle_level_wide_kernel(const u64* __restrict__ in, u64* __restrict__ out, size_t n_out) {
-    __shared__ u32 s_rc[3 * P_WIDTH * P_ROUNDS];
-    for (unsigned i = threadIdx.x; i < 3 * P_WIDTH * P_ROUNDS; i += blockDim.x) s_rc[i] = d_rc3[i];
-    __syncthreads();
-    const unsigned lane = threadIdx.x & 31, j = lane & 15, jj = j < 12 ? j : 11;
-    const size_t node = ((size_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * 2 + (lane >> 4);
-    const bool live = node < n_out;
-    u32 x0, x1, x2;
-    limb_split((live && j < 8) ? in[node * 8 + j] : 0, x0, x1, x2);
+// the 30 rounds on one word per lane; jj = this lane's word index (lanes 12-15 of a half-warp shadow word 11)
+ZKB_D void wide_permute(u32& x0, u32& x1, u32& x2, const u32* s_rc, unsigned jj) {
 #pragma unroll 1
     for (int r = 0; r < P_ROUNDS; ++r) {
         const u32* rc = s_rc + 36 * r + 3 * jj;
@@ -245,7 +243,39 @@ __global__ void __launch_bounds__(128) merkle_level_wide_kernel(const u64* __res
         }
         if (jj == 0) { x0 += 8 * y0; x1 += 8 * y1; x2 += 8 * y2; }
     }
+}
+ZKB_D void wide_load_rc(u32* s_rc) {
+    for (unsigned i = threadIdx.x; i < 3 * P_WIDTH * P_ROUNDS; i += blockDim.x) s_rc[i] = d_rc3[i];
+    __syncthreads();
+}
+__global__ void __launch_bounds__(128) merkle_level_wide_kernel(const u64* __restrict__ in, u64* __restrict__ out, size_t n_out) {
+    __shared__ u32 s_rc[3 * P_WIDTH * P_ROUNDS];
+    wide_load_rc(s_rc);
+    const unsigned lane = threadIdx.x & 31, j = lane & 15, jj = j < 12 ? j : 11;
+    const size_t node = ((size_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * 2 + (lane >> 4);
+    const bool live = node < n_out;
+    u32 x0, x1, x2;
+    limb_split((live && j < 8) ? in[node * 8 + j] : 0, x0, x1, x2);
+    wide_permute(x0, x1, x2, s_rc, jj);
     if (live && j < 4) out[node * 4 + j] = gl_canon(limb_to_u64(x0, x1, x2));
+}
+// lane-parallel sponge over FRI-layer leaves (2 * arity words per leaf, interleaved (a, b) pairs) for the small layers
+__global__ void __launch_bounds__(128) merkle_leaves_ext_wide_kernel(const u64* __restrict__ a, const u64* __restrict__ b, int arity,
+                                                                     size_t num_leaves, u64* __restrict__ digests) {
+    __shared__ u32 s_rc[3 * P_WIDTH * P_ROUNDS];
+    wide_load_rc(s_rc);
+    const unsigned lane = threadIdx.x & 31, j = lane & 15, jj = j < 12 ? j : 11;
+    const size_t l = ((size_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * 2 + (lane >> 4);
+    const bool live = l < num_leaves;
+    const int width = 2 * arity;                       // > 4 (the launcher keeps hash_or_noop leaves on the other kernel)
+    u32 x0 = 0, x1 = 0, x2 = 0;
+#pragma unroll 1
+    for (int c = 0; c < width; c += 8) {
+        const int k = c + (int)j;
+        if (live && j < 8 && k < width) limb_split(((k & 1) ? b : a)[l * arity + (k >> 1)], x0, x1, x2);
+        wide_permute(x0, x1, x2, s_rc, jj);
+    }
+    if (live && j < 4) digests[l * 4 + j] = gl_canon(limb_to_u64(x0, x1, x2));
 }
 
 constexpr size_t MERKLE_WIDE_MAX_NODES = 4096;   // levels this small are latency-bound with one node per thread

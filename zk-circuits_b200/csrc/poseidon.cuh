@@ -32,9 +32,9 @@ constexpr int P_ROUNDS = 30;
 constexpr u32 P_M22 = (1u << 22) - 1, P_M20 = (1u << 20) - 1;
 
 ZKB_HD u64 gl_sbox7(u64 x) {
-    u64 x2 = gl_mul_lazy(x, x);
+    u64 x2 = gl_sqr_lazy(x);
     u64 x3 = gl_mul_lazy(x2, x);
-    u64 x4 = gl_mul_lazy(x2, x2);
+    u64 x4 = gl_sqr_lazy(x2);
     return gl_mul_lazy(x3, x4);
 }
 
@@ -84,9 +84,29 @@ ZKB_HD u64 limb_to_u64(u32 x0, u32 x1, u32 x2) {
     return r;
 }
 
+// Same, for raw limbs that carry the round-constant bias (see host_round_constant_limbs): the top carry is >= 0 by
+// construction, so there is no sign case and no branch.
+ZKB_HD u64 limb_to_u64_biased(u32 x0, u32 x1, u32 x2) {
+    int c0 = (int)x0 >> 22;
+    x0 &= P_M22;
+    x1 += (u32)c0;
+    int c1 = (int)x1 >> 22;
+    x1 &= P_M22;
+    x2 += (u32)c1;
+    u32 top = x2 >> 20;                      // >= 1: the bias puts 2^20 into limb 2
+    x2 &= P_M20;
+    u32 lo = x0 | (x1 << 22), hi = (x1 >> 10) | (x2 << 12);
+    u64 w = ((u64)hi << 32) | lo;
+    u64 k = ((u64)top << 32) - top;          // top * (2^32 - 1) < 2^44
+    u64 r = w + k;
+    if (r < k) r += GL_EPS;
+    return r;
+}
+
 // o = circ(17,15,41,16,2,28,13,13,39,18,34,20) x + 8 x[0] e_0 on one limb vector, arithmetic mod 2^32
 // (out[r] = sum_i x[(i+r) % 12] C[i]); derivation and the Python check of these formulas: DESIGN.md §4.1.
-ZKB_HD void mds_limb12(u32* x) {
+// rc: limb k of the next round's 12 constants at rc[3 * j], added into the output sums (free third IADD3 operand)
+ZKB_HD void mds_limb12(u32* x, const u32* __restrict__ rc) {
     u32 P[3], M[3], R[3], I[3];
 #pragma unroll
     for (int b = 0; b < 3; ++b) {
@@ -112,27 +132,29 @@ ZKB_HD void mds_limb12(u32* x) {
 #pragma unroll
     for (int b = 0; b < 3; ++b) {
         u32 U = 16 * G[b] + F[b], V = 16 * G[b] - F[b];
-        x[b] = U + Re[b];
-        x[6 + b] = U - Re[b];
-        x[3 + b] = V + Im[b];
-        x[9 + b] = V - Im[b];
+        x[b] = U + Re[b] + rc[3 * b];
+        x[6 + b] = U - Re[b] + rc[3 * (6 + b)];
+        x[3 + b] = V + Im[b] + rc[3 * (3 + b)];
+        x[9 + b] = V - Im[b] + rc[3 * (9 + b)];
     }
     x[0] += 8 * x0;
 }
 
-// The permutation on limb-form state. rc3[36 * r + 3 * j + k] = limb k of round constant (r, j).
-// In: raw limbs WITHOUT the first round's constants. Out: raw limbs of the last MDS layer (read with limb_to_u64).
+// The permutation on limb-form state. rc3[36 * r + 3 * j + k] = limb k of the BIASED round constant (r, j), r = 0..30:
+// value = rc(r, j) for r < 30 and 0 for r = 30, written as limbs((value - (2^32 - 1)) mod p) + 2^20 in limb 2, which is
+// the same field element (2^64 = 2^32 - 1 mod p) but keeps every top carry non-negative.
+// In: raw limbs WITHOUT the first round's constants. Out: raw limbs of the last MDS layer plus the biased zero.
 ZKB_HD void poseidon_permute_limbs(u32* o0, u32* o1, u32* o2, const u32* __restrict__ rc3) {
+#pragma unroll
+    for (int j = 0; j < 12; ++j) { o0[j] += rc3[3 * j]; o1[j] += rc3[3 * j + 1]; o2[j] += rc3[3 * j + 2]; }
 #pragma unroll 1
     for (int r = 0; r < P_ROUNDS; ++r) {
-        const u32* rc = rc3 + 36 * r;
         if (r < P_HALF_FULL || r >= P_HALF_FULL + P_PARTIAL) {
 #pragma unroll 1
             for (int pass = 0; pass < 3; ++pass) {
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
-                    const u32* c = rc + 12 * pass + 3 * i;
-                    u64 v = gl_sbox7(limb_to_u64(o0[i] + c[0], o1[i] + c[1], o2[i] + c[2]));
+                    u64 v = gl_sbox7(limb_to_u64_biased(o0[i], o1[i], o2[i]));
                     limb_split(v, o0[i], o1[i], o2[i]);
                 }
                 u32 t;
@@ -144,23 +166,21 @@ ZKB_HD void poseidon_permute_limbs(u32* o0, u32* o1, u32* o2, const u32* __restr
                 }
             }
         } else {
-            u64 v = gl_sbox7(limb_to_u64(o0[0] + rc[0], o1[0] + rc[1], o2[0] + rc[2]));
+            u64 v = gl_sbox7(limb_to_u64_biased(o0[0], o1[0], o2[0]));
             limb_split(v, o0[0], o1[0], o2[0]);
 #pragma unroll
-            for (int j = 1; j < 12; ++j) {
-                o0[j] += rc[3 * j]; o1[j] += rc[3 * j + 1]; o2[j] += rc[3 * j + 2];
-                limb_normalize(o0[j], o1[j], o2[j]);
-            }
+            for (int j = 1; j < 12; ++j) limb_normalize(o0[j], o1[j], o2[j]);
         }
-        mds_limb12(o0);
-        mds_limb12(o1);
-        mds_limb12(o2);
+        const u32* rc = rc3 + 36 * (r + 1);
+        mds_limb12(o0, rc);
+        mds_limb12(o1, rc + 1);
+        mds_limb12(o2, rc + 2);
     }
 }
 
 #if defined(__CUDACC__)
 __constant__ u64 c_rc[P_WIDTH * P_ROUNDS];                 // round constants as field elements (quotient kernel)
-__constant__ u32 c_rc3[3 * P_WIDTH * P_ROUNDS];            // the same as (22, 22, 20)-bit limbs
+__constant__ u32 c_rc3[3 * P_WIDTH * (P_ROUNDS + 1)];      // biased limb form, 31 rows (see poseidon_permute_limbs)
 __constant__ u64 c_rc2[2 * P_WIDTH * (P_ROUNDS + 1)];      // split 32-bit halves, + 24 zeros (see mds_layer_rc)
 
 // sponge state held in registers in limb form
@@ -171,7 +191,7 @@ struct PoseidonState {
         for (int j = 0; j < 12; ++j) o0[j] = o1[j] = o2[j] = 0;
     }
     ZKB_D void set(int j, u64 v) { limb_split(v, o0[j], o1[j], o2[j]); }      // v < 2^64 (lazy allowed)
-    ZKB_D u64 get(int j) const { return gl_canon(limb_to_u64(o0[j], o1[j], o2[j])); }
+    ZKB_D u64 get(int j) const { return gl_canon(limb_to_u64(o0[j], o1[j], o2[j])); }   // general form: valid before and after permute()
     ZKB_D void permute() { poseidon_permute_limbs(o0, o1, o2, c_rc3); }
 };
 

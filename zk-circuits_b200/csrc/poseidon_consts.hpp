@@ -52,16 +52,21 @@ inline const u64* host_round_constants() {
 }
 
 
-// limb form used by poseidon_permute_limbs: rc3[36 r + 3 j + k] = limb k (22, 22, 20 bits) of constant (r, j)
+// limb form used by poseidon_permute_limbs: rc3[36 r + 3 j + k], r = 0..30 (row 30 = the constant 0), BIASED:
+// limbs (22, 22, 20 bits) of (value - (2^32 - 1)) mod p, plus 2^20 in limb 2 — the same field element, since
+// 2^20 * 2^44 = 2^64 = 2^32 - 1 (mod p), but every word's top limb is then >= 2^20 and its carry never negative.
+constexpr int RC3_WORDS = 3 * 12 * 31;
 inline const u32* host_round_constant_limbs() {
-    static u32 rc3[3 * 360];
+    static u32 rc3[RC3_WORDS];
     static std::once_flag once;
     std::call_once(once, [] {
         const u64* rc = host_round_constants();
-        for (int i = 0; i < 360; ++i) {
-            rc3[3 * i] = (u32)(rc[i] & 0x3FFFFF);
-            rc3[3 * i + 1] = (u32)((rc[i] >> 22) & 0x3FFFFF);
-            rc3[3 * i + 2] = (u32)(rc[i] >> 44);
+        for (int i = 0; i < 12 * 31; ++i) {
+            const u64 v = i < 360 ? rc[i] : 0;
+            const u64 w = gl_sub(v, GL_EPS);
+            rc3[3 * i] = (u32)(w & 0x3FFFFF);
+            rc3[3 * i + 1] = (u32)((w >> 22) & 0x3FFFFF);
+            rc3[3 * i + 2] = (u32)(w >> 44) + (1u << 20);
         }
     });
     return rc3;

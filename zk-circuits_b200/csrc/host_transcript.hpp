@@ -8,28 +8,71 @@
 
 namespace zkb {
 
+// ---- fast host permutation. The transcript is on the critical path of every proof (~130 permutations between
+// kernel launches), so it gets the same algebra as the device code: branch-free lazy reduction, and the MDS layer as the
+// shift/add circulant of poseidon.cuh applied to the 32-bit halves of the state (sums stay below 2^41 in u64 lanes).
+inline u64 h_mul_lazy(u64 a, u64 b) {                       // any u64 in, result in [0, 2^64) with the same residue
+    unsigned __int128 x = (unsigned __int128)a * b;
+    u64 lo = (u64)x, hi = (u64)(x >> 64), hh = hi >> 32, hl = hi & GL_EPS;
+    u64 t0 = lo - hh;
+    t0 -= (lo < hh) ? GL_EPS : 0;                           // borrowed: subtract 2^64 mod p
+    u64 t1 = (hl << 32) - hl, r = t0 + t1;
+    r += (r < t1) ? GL_EPS : 0;
+    return r;
+}
 inline u64 h_sbox7(u64 x) {
-    u64 x2 = gl_mul(x, x), x4 = gl_mul(x2, x2), x3 = gl_mul(x2, x);
-    return gl_mul(x3, x4);
+    u64 x2 = h_mul_lazy(x, x), x4 = h_mul_lazy(x2, x2), x3 = h_mul_lazy(x2, x);
+    return h_mul_lazy(x3, x4);
+}
+// out[r] = sum_i x[(i+r) % 12] C[i] + 8 x[0] [r == 0], arithmetic mod 2^64 on values < 2^32 (true sums < 2^41)
+inline void h_mds_half(u64* x) {
+    u64 P[3], M[3], R[3], I[3];
+    for (int b = 0; b < 3; ++b) {
+        u64 t0 = x[b] + x[6 + b], t1 = x[3 + b] + x[9 + b];
+        P[b] = t0 + t1; M[b] = t0 - t1; R[b] = x[b] - x[6 + b]; I[b] = x[3 + b] - x[9 + b];
+    }
+    const u64 x0 = x[0], T = P[0] + P[1] + P[2];
+    const u64 G[3] = {T + P[2], T + P[0], T + P[1]};
+    const u64 F[3] = {8 * M[2] - M[0] - 2 * M[1], 0 - M[1] - 2 * M[2] - 8 * M[0], 2 * M[0] - M[2] - 8 * M[1]};
+    u64 Ar[3], Ai[3], Br[3], Bi[3], Dr[3], Di[3];
+    for (int b = 0; b < 3; ++b) {
+        Ar[b] = 2 * R[b] - I[b];  Ai[b] = R[b] + 2 * I[b];
+        Br[b] = R[b] - 16 * I[b]; Bi[b] = 16 * R[b] + I[b];
+        Dr[b] = R[b] + 4 * I[b];  Di[b] = I[b] - 4 * R[b];
+    }
+    const u64 Re[3] = {Ar[0] + Br[1] + Dr[2], Ar[1] + Br[2] + Di[0], Ar[2] + Bi[0] + Di[1]};
+    const u64 Im[3] = {Ai[0] + Bi[1] + Di[2], Ai[1] + Bi[2] - Dr[0], Ai[2] - Br[0] - Dr[1]};
+    for (int b = 0; b < 3; ++b) {
+        u64 U = 16 * G[b] + F[b], V = 16 * G[b] - F[b];
+        x[b] = U + Re[b]; x[6 + b] = U - Re[b]; x[3 + b] = V + Im[b]; x[9 + b] = V - Im[b];
+    }
+    x[0] += 8 * x0;
 }
 inline void h_poseidon_permute(u64* s) {
-    static const u64 C[12] = {17, 15, 41, 16, 2, 28, 13, 13, 39, 18, 34, 20};
     const u64* rc = host_round_constants();
     for (int r = 0; r < 30; ++r) {
-        for (int i = 0; i < 12; ++i) s[i] = gl_add(s[i], rc[12 * r + i]);
+        u64 t[12];
+        for (int i = 0; i < 12; ++i) {                      // lazy add of a canonical constant: at most one wrap
+            u64 v = s[i] + rc[12 * r + i];
+            t[i] = v + ((v < s[i]) ? GL_EPS : 0);
+        }
         if (r < 4 || r >= 26) {
-            for (int i = 0; i < 12; ++i) s[i] = h_sbox7(s[i]);
+            for (int i = 0; i < 12; ++i) t[i] = h_sbox7(t[i]);
         } else {
-            s[0] = h_sbox7(s[0]);
+            t[0] = h_sbox7(t[0]);
         }
-        u64 out[12];
-        for (int o = 0; o < 12; ++o) {
-            unsigned __int128 acc = o == 0 ? (unsigned __int128)s[0] * 8 : 0;
-            for (int i = 0; i < 12; ++i) acc += (unsigned __int128)s[(i + o) % 12] * C[i];
-            out[o] = gl_canon(gl_reduce128_lazy((u64)acc, (u64)(acc >> 64)));
+        u64 lo[12], hi[12];
+        for (int i = 0; i < 12; ++i) { lo[i] = t[i] & GL_EPS; hi[i] = t[i] >> 32; }
+        h_mds_half(lo);
+        h_mds_half(hi);
+        for (int o = 0; o < 12; ++o) {                      // lo + hi 2^32 with hi = hh 2^32 + hl: hh 2^64 = hh (2^32 - 1)
+            u64 hl = hi[o] & GL_EPS, hh = hi[o] >> 32;
+            u64 v = lo[o] + ((hh << 32) - hh);              // < 2^42
+            u64 w = v + (hl << 32);
+            s[o] = w + ((w < v) ? GL_EPS : 0);
         }
-        for (int o = 0; o < 12; ++o) s[o] = out[o];
     }
+    for (int i = 0; i < 12; ++i) s[i] = gl_canon(s[i]);
 }
 inline void h_hash_no_pad(const u64* v, size_t len, u64 out[4]) {
     u64 s[12] = {0};

@@ -80,6 +80,18 @@ class ClockSampler:
                 "reasons": sorted(self.reasons), "samples": len(self.samples)}
 
 
+def synth_columns(np, lg_n, cols):
+    """config #3 inputs: x[c][i] = SplitMix64-finalizer(SEED + c n + i) mod p."""
+    nn = 1 << lg_n
+    idx = np.arange(nn * cols, dtype=np.uint64) + np.uint64(0xB200000000000001)
+    with np.errstate(over="ignore"):
+        z = idx
+        z = (z ^ (z >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
+        z = (z ^ (z >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
+        z = z ^ (z >> np.uint64(31))
+    return np.where(z >= np.uint64(0xFFFFFFFF00000001), z - np.uint64(0xFFFFFFFF00000001), z).reshape(cols, nn)
+
+
 def reference_arm(args, rank):
     """CPU arm: the reference's own prover cannot be built here (Rust crate qp-plonky2, no toolchain), so this
     times the oracle's restatement of it (kind "port") on the host cores, same circuit, one proof per step."""
@@ -158,6 +170,7 @@ def main():
     import numpy as np
     import torch
     import zkb200 as Z
+    from zkb200 import batch as zbatch   # same max-over-ranks helper the CPU gloo test exercises
 
     if not torch.cuda.is_available() or Z.device_count() == 0:
         raise SystemExit("bench.py: no CUDA device — the product has no CPU fallback (use --impl reference for the CPU arm)")
@@ -255,10 +268,29 @@ def main():
     proof = proofs[0]
     barrier()
 
-    from zkb200 import batch as zbatch   # same max-over-ranks helper the CPU gloo test exercises
-
     t_res, t_e2e, t_single = zbatch.max_over_ranks([t_res, t_e2e, t_single], device="cuda")
     stages = {k: v / K for k, v in stage_sum.items()}
+
+    # ---- N > 1 only: ONE large commitment sharded by LDE coset across the GPUs (the mode where the path has a real
+    # exchange step: one NCCL all-gather of 16 cap digests; SURVEY.md §8e(2), config #3 shape) ----
+    sharded_line = None
+    if world > 1 and not args.no_sweep and (8 % world) == 0:
+        from zkb200 import sharded as zsh
+
+        lg_n, cols = 20, 100
+        vals = synth_columns(np, lg_n, cols)
+        barrier()
+        t0 = time.perf_counter()
+        cap, tm = zsh.sharded_commit(vals, 3, 4, device=local_rank, reps=1, gather_device="cuda")
+        torch.cuda.synchronize()
+        t_wall = time.perf_counter() - t0
+        lde_ms, merkle_ms, t_wall = zbatch.max_over_ranks([tm["lde_ms"], tm["merkle_ms"], t_wall], device="cuda")
+        nn = 1 << lg_n
+        sharded_line = {"lg_n": lg_n, "cols": cols, "ranks": world, "blocks_per_rank": 8 // world, "lde_ms": lde_ms,
+                        "merkle_ms": merkle_ms, "lde_gbs_aggregate": 80 * nn * cols / (lde_ms * 1e-3) / 1e9,
+                        "perms_per_sec_aggregate": (8 * nn * ((cols + 7) // 8) + 8 * nn - 16) / (merkle_ms * 1e-3),
+                        "collective": "all_gather of 16 x 32 B cap digests (NCCL)", "wall_ms_incl_h2d": 1000 * t_wall,
+                        "cap_word0": int(cap[0, 0])}
 
     if rank != 0:
         if dist is not None:
@@ -297,19 +329,15 @@ def main():
         sweep = []
         for lg_n, cols in ((16, 135), (18, 100), (20, 100)):
             nn = 1 << lg_n
-            idx = np.arange(nn * cols, dtype=np.uint64) + np.uint64(0xB200000000000001)
-            with np.errstate(over="ignore"):
-                z = idx
-                z = (z ^ (z >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
-                z = (z ^ (z >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
-                z = z ^ (z >> np.uint64(31))
-            vals = np.where(z >= np.uint64(0xFFFFFFFF00000001), z - np.uint64(0xFFFFFFFF00000001), z).reshape(cols, nn)
+            vals = synth_columns(np, lg_n, cols)
             _, tm = Z.commit_batch(vals, 3, 4, reps=3, device=local_rank)
             gbs = 80 * nn * cols / (tm["lde_ms"] * 1e-3) / 1e9
             pp = 8 * nn * ((cols + 7) // 8) + 8 * nn - 16
             sweep.append({"lg_n": lg_n, "cols": cols, "lde_ms": tm["lde_ms"], "lde_gbs": gbs, "lde_frac_hbm": gbs / peak,
                           "merkle_ms": tm["merkle_ms"], "perms_per_sec": pp / (tm["merkle_ms"] * 1e-3)})
         line["lde_merkle_sweep"] = sweep
+    if sharded_line is not None:
+        line["sharded_commit"] = sharded_line
     if world == 1 and not args.no_cpu_baseline:
         sys.path.insert(0, os.path.join(ROOT, "oracle"))
         import oracle as O   # CPU baseline leg only

@@ -102,6 +102,13 @@ int zkb_merkle_commit(const uint64_t* leaves, size_t width, size_t num_leaves, u
  * {lde_ms, merkle_ms} measured with CUDA events on the launching stream, inputs already resident */
 int zkb_commit_batch(const uint64_t* values, size_t ncols, size_t n, unsigned rate_bits, unsigned cap_height, int reps,
                      uint64_t* cap_out, float* times_ms, int device);
+/* One GPU's share of a COSET-SHARDED from_values commitment (multi-GPU mode for a single large batch): in leaf order LDE
+ * coset j is the contiguous leaf block bitrev(j), so a rank that owns leaf blocks [blk_lo, blk_hi) of the 2^rate_bits
+ * blocks computes the (cheap) iNTT of every column, the LDE of its blocks only, their leaf hashes and whole Merkle
+ * subtrees, and ends with its (blk_hi - blk_lo) * 2^(cap_height - rate_bits) cap digests — the caller all-gathers
+ * 16 x 32 bytes (NCCL) to obtain MerkleTree::cap. Needs cap_height >= rate_bits and a power-of-two aligned block range. */
+int zkb_commit_cosets(const uint64_t* values, size_t ncols, size_t n, unsigned rate_bits, unsigned cap_height, unsigned blk_lo,
+                      unsigned blk_hi, int reps, uint64_t* cap_part_out, float* times_ms, int device);
 /* wires_permutation_partial_products_and_zs: out [num_challenges*(1+num_partial_products)][n] */
 int zkb_partial_products(zkb_circuit* c, const uint64_t* wires, const uint64_t* betas, const uint64_t* gammas, uint64_t* out);
 /* compute_quotient_polys from wire / Z-partial-product VALUES (unsalted): out [num_challenges*qdf][n] coefficients */

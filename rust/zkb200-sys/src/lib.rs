@@ -52,6 +52,8 @@ extern "C" {
                              cap_out: *mut u64, device: c_int) -> c_int;
     pub fn zkb_commit_batch(values: *const u64, ncols: usize, n: usize, rate_bits: c_uint, cap_height: c_uint, reps: c_int,
                             cap_out: *mut u64, times_ms: *mut c_float, device: c_int) -> c_int;
+    pub fn zkb_commit_cosets(values: *const u64, ncols: usize, n: usize, rate_bits: c_uint, cap_height: c_uint, blk_lo: c_uint,
+                             blk_hi: c_uint, reps: c_int, cap_part_out: *mut u64, times_ms: *mut c_float, device: c_int) -> c_int;
     pub fn zkb_partial_products(c: *mut zkb_circuit, wires: *const u64, betas: *const u64, gammas: *const u64, out: *mut u64) -> c_int;
     pub fn zkb_quotient(c: *mut zkb_circuit, wires: *const u64, zs_pp: *const u64, public_inputs: *const u64, n_pi: usize,
                         betas: *const u64, gammas: *const u64, alphas: *const u64, out: *mut u64) -> c_int;

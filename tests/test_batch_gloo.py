@@ -69,3 +69,47 @@ def test_two_rank_batch_over_gloo(tmp_path):
     port = 29500 + (os.getpid() % 2000)
     mp.spawn(_rank_main, args=(2, port, str(tmp_path)), nprocs=2, join=True)
     assert (tmp_path / "ok").read_text() == "ok"
+
+
+def _sharded_rank_main(rank, world_size, port, tmpdir):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world_size))
+    for p in (os.path.join(ROOT, "oracle"), os.path.join(ROOT, "zk-circuits_b200")):
+        sys.path.insert(0, p)
+    import numpy as np
+    import torch.distributed as dist
+    import oracle as O
+    from zkb200 import sharded
+
+    dist.init_process_group("gloo", rank=rank, world_size=world_size)
+    try:
+        rng = np.random.default_rng(11)                     # same values on every rank
+        vals = rng.integers(0, O.P, size=(5, 64), dtype=np.uint64)
+        rb, ch = 3, 4
+        _, lde = O.lde_batch(vals, rb)
+        _, want = O.merkle_commit(lde, ch)
+
+        def cpu_commit(v, rate_bits, cap_height, lo, hi):   # oracle stand-in for zkb_commit_cosets: sub-range of the leaves
+            n = v.shape[1]
+            _, l = O.lde_batch(v, rate_bits)
+            nb = hi - lo
+            local = np.ascontiguousarray(l[:, lo * n:hi * n])
+            _, part = O.merkle_commit(local, cap_height - rate_bits + nb.bit_length() - 1)
+            return part, {}
+
+        cap, _ = sharded.sharded_commit(vals, rb, ch, commit_fn=cpu_commit)
+        assert cap.shape == want.shape and np.array_equal(cap, want)
+        assert sharded.block_range(rb, rank, world_size) == (rank * 8 // world_size, (rank + 1) * 8 // world_size)
+        if rank == 0:
+            open(os.path.join(tmpdir, "ok2"), "w").write("ok")
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world_size", [2, 4])
+def test_coset_sharded_commit_over_gloo(tmp_path, world_size):
+    """Sharding + the single all-gather of cap digests, with the oracle computing each rank's block range on the CPU."""
+    import torch.multiprocessing as mp
+
+    port = 31500 + (os.getpid() % 2000) + world_size
+    mp.spawn(_sharded_rank_main, args=(world_size, port, str(tmp_path)), nprocs=world_size, join=True)
+    assert (tmp_path / "ok2").read_text() == "ok"

@@ -155,3 +155,23 @@ def test_partial_products_and_quotient_match_oracle(zkb, oracle, tiny):
     assert np.array_equal(zs, tr.zs_pp_values)
     q = gc.quotient(s.wires, zs, s.public_inputs, tr.betas, tr.gammas, tr.alphas, 16, s.n)
     assert np.array_equal(q, tr.quotient_chunks)
+
+
+@pytest.mark.parametrize("lg_n,ncols", [(9, 7), (14, 3), (16, 2)])
+def test_coset_sharded_commit_parts_concatenate_to_the_full_cap(zkb, oracle, lg_n, ncols):
+    """zkb_commit_cosets (one GPU's share of a coset-sharded commitment) for G = 1, 2, 4, 8 emulated ranks on one GPU:
+    the parts, in rank order, are the cap of the unsharded commitment (which is bit-exact with the oracle)."""
+    rng = np.random.default_rng(lg_n)
+    vals = rand_felts(rng, (ncols, 1 << lg_n))
+    want, _ = zkb.commit_batch(vals, 3, 4)
+    _, lde = oracle.lde_batch(vals, 3)
+    _, ocap = oracle.merkle_commit(lde, 4)
+    assert np.array_equal(want, ocap)
+    for G in (1, 2, 4, 8):
+        per = 8 // G
+        parts = [zkb.commit_cosets(vals, 3, 4, r * per, (r + 1) * per)[0] for r in range(G)]
+        assert np.array_equal(np.concatenate(parts), want)
+    with pytest.raises(zkb.ZkbError):
+        zkb.commit_cosets(vals, 3, 4, 1, 3)          # unaligned block range
+    with pytest.raises(zkb.ZkbError):
+        zkb.commit_cosets(vals, 3, 2, 0, 4)          # cap_height < rate_bits

@@ -236,6 +236,48 @@ int zkb_commit_batch(const uint64_t* values, size_t ncols, size_t n, unsigned ra
     });
 }
 
+int zkb_commit_cosets(const uint64_t* values, size_t ncols, size_t n, unsigned rate_bits, unsigned cap_height, unsigned blk_lo,
+                      unsigned blk_hi, int reps, uint64_t* cap_part_out, float* times_ms, int device) {
+    return guarded([&] {
+        if (!values || !cap_part_out) throw ArgError("null argument");
+        if (!is_pow2(n) || n < 2 || rate_bits > 4 || !ncols) throw ArgError("bad shape");
+        const unsigned nblk_all = 1u << rate_bits;
+        if (blk_lo >= blk_hi || blk_hi > nblk_all || !is_pow2(blk_hi - blk_lo) || blk_lo % (blk_hi - blk_lo)) throw ArgError("bad block range");
+        if (cap_height < rate_bits) throw ArgError("coset sharding needs cap_height >= rate_bits (each block must hold whole cap subtrees)");
+        if (reps < 1) reps = 1;
+        require_device(device);
+        const unsigned lg_n = lg2(n), nb = blk_hi - blk_lo;
+        const size_t N = n << rate_bits, L = n * nb;                   // local leaves
+        if ((size_t(1) << cap_height) > N) throw ArgError("cap_height exceeds tree height");
+        const unsigned cap_local = cap_height - rate_bits + lg2(nb);    // this rank's cap digests = 2^cap_local
+        DevBuf v(ncols * n), c(ncols * n), l(ncols * L);
+        DevBuf dg(merkle_digest_count(L, cap_local) * 4);
+        cuda_check(cudaMemcpy(v.get(), values, ncols * n * 8, cudaMemcpyHostToDevice), "H2D");
+        cudaEvent_t e0, e1, e2;
+        cuda_check(cudaEventCreate(&e0), "event"); cuda_check(cudaEventCreate(&e1), "event"); cuda_check(cudaEventCreate(&e2), "event");
+        float t_lde = 0, t_merkle = 0;
+        size_t cap_off = 0;
+        for (int r = 0; r < reps; ++r) {
+            cuda_check(cudaEventRecord(e0, 0), "record");
+            launch_intt_natural(v.get(), n, c.get(), n, (int)ncols, lg_n, nullptr, 0);      // every rank needs all coefficients
+            launch_lde_blocks(c.get(), n, l.get(), L, (int)ncols, lg_n, rate_bits, GL_GEN, blk_lo, blk_hi, 0);
+            cuda_check(cudaEventRecord(e1, 0), "record");
+            launch_merkle_leaves(l.get(), L, (int)ncols, L, dg.get(), 0);
+            cap_off = launch_merkle_levels(dg.get(), L, cap_local, 0);
+            cuda_check(cudaEventRecord(e2, 0), "record");
+            cuda_check(cudaEventSynchronize(e2), "sync");
+            float a, b;
+            cuda_check(cudaEventElapsedTime(&a, e0, e1), "elapsed");
+            cuda_check(cudaEventElapsedTime(&b, e1, e2), "elapsed");
+            t_lde += a; t_merkle += b;
+        }
+        cudaEventDestroy(e0); cudaEventDestroy(e1); cudaEventDestroy(e2);
+        if (times_ms) { times_ms[0] = t_lde / reps; times_ms[1] = t_merkle / reps; }
+        cuda_check(cudaMemcpy(cap_part_out, dg.get() + cap_off * 4, (size_t(32)) << cap_local, cudaMemcpyDeviceToHost), "D2H cap");
+        return (int)ZKB_OK;
+    });
+}
+
 // ---- synthetic workloads ----
 int zkb_synth_create(unsigned min_degree_bits, int zk, size_t n_poseidon, size_t n_base_sum, size_t n_arith, size_t n_const,
                      size_t num_public_inputs, uint64_t seed, zkb_synth** out) {

@@ -380,16 +380,16 @@ static CosetTables coset_tables(unsigned lg_n, unsigned rate_bits, u64 shift, cu
 }
 // the two steps for n > 2^14; z = number of coset blocks written (block jb of dst at + jb * n)
 static void run_large_transform(const u64* src, size_t src_stride, u64* dst, size_t dst_stride, int ncols, unsigned lg_n,
-                                unsigned nblk, const u64* pre1, const u64* pre2, bool inv, cudaStream_t st) {
+                                unsigned nblk, const u64* pre1, const u64* pre2, bool inv, cudaStream_t st, unsigned jb0 = 0) {
     const LargePlan p = large_plan(lg_n);
-    ColsNttArgs a{src, src_stride, dst, dst_stride, lg_n, p.lg_n1, p.lg_tb, pre1, pre2, inv ? 1 : 0};
+    ColsNttArgs a{src, src_stride, dst, dst_stride, lg_n, p.lg_n1, p.lg_tb, pre1, pre2, inv ? 1 : 0, jb0};
     dim3 g1(1u << (p.lb - p.lg_tb), (unsigned)ncols, nblk);
     ZKB_COUNT_LAUNCH();
     ntt_cols_kernel<<<g1, 256, ntt_smem_bytes(p.lg_n1 + p.lg_tb), st>>>(a);
     dim3 g2(nblk << p.lg_n1, (unsigned)ncols);
     ZKB_COUNT_LAUNCH();
     lde_block_kernel<<<g2, ntt_block_threads(p.lb), ntt_smem_bytes(p.lb), st>>>(dst, dst_stride, dst, dst_stride, p.lb, nullptr,
-                                                                                size_t(1) << p.lb, inv ? 1 : 0);
+                                                                                size_t(1) << p.lb, inv ? 1 : 0, 0);
 }
 
 // in-place bit-reversal permutation with scaling
@@ -430,19 +430,23 @@ void launch_intt_natural(const u64* src, size_t src_stride, u64* dst, size_t dst
     run_bitrev_scale(dst, dst_stride, ncols, lg_n, ninv, st);
 }
 
-void launch_lde(const u64* coeffs, size_t coeff_stride, u64* out, size_t out_stride, int ncols, unsigned lg_n,
-                unsigned rate_bits, u64 shift, cudaStream_t st) {
-    if (ncols <= 0) return;
+void launch_lde_blocks(const u64* coeffs, size_t coeff_stride, u64* out, size_t out_stride, int ncols, unsigned lg_n,
+                       unsigned rate_bits, u64 shift, unsigned blk_lo, unsigned blk_hi, cudaStream_t st) {
+    if (ncols <= 0 || blk_hi <= blk_lo) return;
     const bool plain = rate_bits == 0 && shift == 1;
     CosetTables t;
     if (!plain) t = coset_tables(lg_n, rate_bits, shift, st);
     if (lg_n <= NTT_SM_LG) {
-        dim3 grid(1u << rate_bits, (unsigned)ncols);
+        dim3 grid(blk_hi - blk_lo, (unsigned)ncols);
         ZKB_COUNT_LAUNCH();
-        lde_block_kernel<<<grid, ntt_block_threads(lg_n), ntt_smem_bytes(lg_n), st>>>(coeffs, coeff_stride, out, out_stride, lg_n, t.full, 0, 0);
+        lde_block_kernel<<<grid, ntt_block_threads(lg_n), ntt_smem_bytes(lg_n), st>>>(coeffs, coeff_stride, out, out_stride, lg_n, t.full, 0, 0, blk_lo);
         return;
     }
-    run_large_transform(coeffs, coeff_stride, out, out_stride, ncols, lg_n, 1u << rate_bits, t.pre1, t.pre2, false, st);
+    run_large_transform(coeffs, coeff_stride, out, out_stride, ncols, lg_n, blk_hi - blk_lo, t.pre1, t.pre2, false, st, blk_lo);
+}
+void launch_lde(const u64* coeffs, size_t coeff_stride, u64* out, size_t out_stride, int ncols, unsigned lg_n,
+                unsigned rate_bits, u64 shift, cudaStream_t st) {
+    launch_lde_blocks(coeffs, coeff_stride, out, out_stride, ncols, lg_n, rate_bits, shift, 0, 1u << rate_bits, st);
 }
 
 // data[k] *= c0 * base^k

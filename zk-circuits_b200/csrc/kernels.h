@@ -36,6 +36,10 @@ void launch_intt_natural(const u64* src, size_t src_stride, u64* dst, size_t dst
 // coefficients (natural, n per column) -> evaluations on shift*<w_{n<<rate_bits}> in leaf (bit-reversed) order
 void launch_lde(const u64* coeffs, size_t coeff_stride, u64* out, size_t out_stride, int ncols, unsigned lg_n,
                 unsigned rate_bits, u64 shift, cudaStream_t st);
+// the same for the leaf blocks [blk_lo, blk_hi) only (block jb = LDE coset bitrev(jb) = leaves [jb n, (jb+1) n));
+// out points at the destination of block blk_lo (coset sharding across GPUs)
+void launch_lde_blocks(const u64* coeffs, size_t coeff_stride, u64* out, size_t out_stride, int ncols, unsigned lg_n,
+                       unsigned rate_bits, u64 shift, unsigned blk_lo, unsigned blk_hi, cudaStream_t st);
 // evaluations on shift*<w_m> given in bit-reversed order -> coefficients in natural order (in place)
 void launch_coset_intt_bitrev(u64* data, size_t stride, int ncols, unsigned lg_m, u64 shift, cudaStream_t st);
 

@@ -127,11 +127,11 @@ ZKB_D void ntt_dif_smem(u64* sm, unsigned L, unsigned lgC = 0, bool inv = false)
 // contiguous run (second step of the two-step transform for n > 2^14; coeffs may alias out). inv: inverse twiddles.
 __global__ void __launch_bounds__(512) lde_block_kernel(const u64* coeffs, size_t coeff_stride, u64* out,
                                                         size_t out_stride, unsigned lg_n, const u64* __restrict__ prescale,
-                                                        size_t src_block_stride, int inv) {
+                                                        size_t src_block_stride, int inv, unsigned jb0) {
     extern __shared__ u64 sm[];
-    const unsigned n = 1u << lg_n, jb = blockIdx.x;
+    const unsigned n = 1u << lg_n, jb = blockIdx.x;       // jb: destination block; jb0 + jb: coset (pre-scale table row)
     const u64* src = coeffs + (size_t)blockIdx.y * coeff_stride + (size_t)jb * src_block_stride;
-    const u64* ps = prescale ? prescale + (size_t)jb * n : nullptr;
+    const u64* ps = prescale ? prescale + (size_t)(jb0 + jb) * n : nullptr;
     // n is a multiple of 8 * blockDim whenever n >= 4096 (512 threads): 8 independent loads in flight per thread
     if ((n & (8 * blockDim.x - 1)) == 0) {
         for (unsigned i0 = threadIdx.x; i0 < n; i0 += 8 * blockDim.x) {
@@ -171,6 +171,7 @@ struct ColsNttArgs {
     unsigned lg_n, lg_n1, lg_tb;
     const u64* pre1; const u64* pre2;       // [2^rate][n1], [2^rate][n2] or null
     int inv;
+    unsigned jb0;                           // coset of destination block 0 (rows of pre1 / pre2)
 };
 __global__ void __launch_bounds__(256) ntt_cols_kernel(ColsNttArgs a) {
     extern __shared__ u64 sm[];
@@ -182,7 +183,7 @@ __global__ void __launch_bounds__(256) ntt_cols_kernel(ColsNttArgs a) {
     for (unsigned idx = threadIdx.x; idx < tot; idx += blockDim.x) {
         const unsigned r = idx >> a.lg_tb, c = idx & (TB - 1);
         u64 v = src[(size_t)r * n2 + b0 + c];
-        if (a.pre1) v = f_mul(v, f_mul(a.pre1[(size_t)jb * n1 + r], a.pre2[(size_t)jb * n2 + b0 + c]));
+        if (a.pre1) v = f_mul(v, f_mul(a.pre1[(size_t)(a.jb0 + jb) * n1 + r], a.pre2[(size_t)(a.jb0 + jb) * n2 + b0 + c]));
         sm[ntt_pad(idx)] = v;
     }
     __syncthreads();

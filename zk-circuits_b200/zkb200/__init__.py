@@ -31,6 +31,7 @@ TIMING_KEYS = ["h2d", "wires_lde", "wires_merkle", "partial_products", "zs_commi
 EXPORTS = ["zkb_version", "zkb_last_error", "zkb_device_count", "zkb_kernel_launch_count", "zkb_circuit_create", "zkb_circuit_destroy",
            "zkb_circuit_verifier_only", "zkb_proof_size", "zkb_prove", "zkb_witness_upload", "zkb_prove_resident",
            "zkb_last_timings", "zkb_poseidon_permute_batch", "zkb_lde_batch", "zkb_merkle_commit", "zkb_commit_batch",
+           "zkb_commit_cosets",
            "zkb_partial_products", "zkb_quotient", "zkb_synth_create", "zkb_synth_destroy", "zkb_synth_common_len",
            "zkb_synth_degree", "zkb_synth_get"]
 
@@ -76,6 +77,8 @@ def lib():
         L.zkb_lde_batch.argtypes = [u64p, ctypes.c_size_t, ctypes.c_size_t, ctypes.c_uint, ctypes.c_int, u64p, u64p, ctypes.c_int]
         L.zkb_merkle_commit.argtypes = [u64p, ctypes.c_size_t, ctypes.c_size_t, ctypes.c_uint, u64p, u64p, ctypes.c_int]
         L.zkb_commit_batch.argtypes = [u64p, ctypes.c_size_t, ctypes.c_size_t, ctypes.c_uint, ctypes.c_uint, ctypes.c_int, u64p, f32p, ctypes.c_int]
+        L.zkb_commit_cosets.argtypes = [u64p, ctypes.c_size_t, ctypes.c_size_t, ctypes.c_uint, ctypes.c_uint, ctypes.c_uint, ctypes.c_uint,
+                                        ctypes.c_int, u64p, f32p, ctypes.c_int]
         L.zkb_partial_products.argtypes = [ctypes.c_void_p, u64p, u64p, u64p, u64p]
         L.zkb_quotient.argtypes = [ctypes.c_void_p, u64p, u64p, u64p, ctypes.c_size_t, u64p, u64p, u64p, u64p]
         L.zkb_synth_create.argtypes = [ctypes.c_uint, ctypes.c_int] + [ctypes.c_size_t] * 5 + [ctypes.c_uint64, ctypes.POINTER(ctypes.c_void_p)]
@@ -156,6 +159,17 @@ def commit_batch(values, rate_bits=3, cap_height=4, reps=1, device=0):
     t = np.zeros(2, dtype=np.float32)
     _check(lib().zkb_commit_batch(p, ncols, n, rate_bits, cap_height, reps, cap.ctypes.data_as(u64p), t.ctypes.data_as(f32p), device))
     return cap, {"lde_ms": float(t[0]), "merkle_ms": float(t[1])}
+
+
+def commit_cosets(values, rate_bits, cap_height, blk_lo, blk_hi, reps=1, device=0):
+    """One rank's share of a coset-sharded commitment: cap digests of leaf blocks [blk_lo, blk_hi) (see zkb200.sharded)."""
+    a, p = _u64(values)
+    ncols, n = a.shape
+    part = np.zeros(((blk_hi - blk_lo) << (cap_height - rate_bits), 4), dtype=np.uint64)
+    t = np.zeros(2, dtype=np.float32)
+    _check(lib().zkb_commit_cosets(p, ncols, n, rate_bits, cap_height, blk_lo, blk_hi, reps, part.ctypes.data_as(u64p),
+                                   t.ctypes.data_as(f32p), device))
+    return part, {"lde_ms": float(t[0]), "merkle_ms": float(t[1])}
 
 
 class ProverCircuit:

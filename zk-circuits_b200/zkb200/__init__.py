@@ -165,7 +165,8 @@ def commit_cosets(values, rate_bits, cap_height, blk_lo, blk_hi, reps=1, device=
     """One rank's share of a coset-sharded commitment: cap digests of leaf blocks [blk_lo, blk_hi) (see zkb200.sharded)."""
     a, p = _u64(values)
     ncols, n = a.shape
-    part = np.zeros(((blk_hi - blk_lo) << (cap_height - rate_bits), 4), dtype=np.uint64)
+    rows = max(blk_hi - blk_lo, 1) << max(cap_height - rate_bits, 0)     # bad ranges are rejected by the library
+    part = np.zeros((rows, 4), dtype=np.uint64)
     t = np.zeros(2, dtype=np.float32)
     _check(lib().zkb_commit_cosets(p, ncols, n, rate_bits, cap_height, blk_lo, blk_hi, reps, part.ctypes.data_as(u64p),
                                    t.ctypes.data_as(f32p), device))

@@ -206,7 +206,25 @@ ZKB_HD u64 gl_pow(u64 a, u64 e) {
     }
     return r;
 }
-ZKB_HD u64 gl_inv(u64 a) { return gl_pow(a, GL_P - 2); }
+ZKB_HD u64 gl_sqr_n_lazy(u64 a, int k) {
+    for (int i = 0; i < k; ++i) a = gl_sqr_lazy(a);
+    return a;
+}
+// a^(p-2) with p - 2 = 2^64 - 2^32 - 1, by the chain e(k) = a^(2^k - 1): 74 squarings + 10 multiplies, lazy inside
+// (a plain square-and-multiply needs 64 + 63). gl_inv(0) = 0.
+ZKB_HD u64 gl_inv(u64 a) {
+    const u64 e2 = gl_mul_lazy(gl_sqr_lazy(a), a);
+    const u64 e3 = gl_mul_lazy(gl_sqr_lazy(e2), a);
+    const u64 e4 = gl_mul_lazy(gl_sqr_n_lazy(e2, 2), e2);
+    const u64 e7 = gl_mul_lazy(gl_sqr_n_lazy(e4, 3), e3);
+    const u64 e8 = gl_mul_lazy(gl_sqr_n_lazy(e4, 4), e4);
+    const u64 e15 = gl_mul_lazy(gl_sqr_n_lazy(e8, 7), e7);
+    const u64 e16 = gl_mul_lazy(gl_sqr_n_lazy(e8, 8), e8);
+    const u64 e31 = gl_mul_lazy(gl_sqr_n_lazy(e16, 15), e15);
+    const u64 b = gl_sqr_lazy(e31);                       // a^(2^32 - 2)
+    const u64 c = gl_mul_lazy(b, a);                      // a^(2^32 - 1)
+    return gl_canon(gl_mul_lazy(gl_sqr_n_lazy(b, 32), c));
+}
 inline u64 gl_root_of_unity(unsigned k) {
     u64 r = GL_TWO_ADIC_ROOT;
     for (unsigned i = k; i < 32; ++i) r = gl_mul(r, r);

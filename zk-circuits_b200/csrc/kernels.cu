@@ -489,6 +489,7 @@ struct PPArgs {
     u64* out; size_t out_stride;
 };
 
+constexpr int PP_MAX_CHUNKS = 16;
 __global__ void __launch_bounds__(128) pp_chunk_kernel(PPArgs a) {
     size_t n = size_t(1) << a.lg_n;
     size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
@@ -496,19 +497,45 @@ __global__ void __launch_bounds__(128) pp_chunk_kernel(PPArgs a) {
     if (i >= n) return;
     u64 beta = a.betas[ch], gamma = a.gammas[ch];
     u64 bx = gl_mul(beta, root_pow_lg(a.lg_n, (u32)i, false));
-    u64 tot = 1;
-    for (int k = 0; k < a.nchunks; ++k) {
-        u64 num = 1, den = 1;
-        int j1 = min(a.num_routed, (k + 1) * a.chunk);
-        for (int j = k * a.chunk; j < j1; ++j) {
-            u64 w = a.wires[(size_t)j * a.wire_stride + i];
-            u64 wg = gl_add(w, gamma);
-            num = gl_mul(num, gl_add(wg, gl_mul(bx, a.k_is[j])));
-            den = gl_mul(den, gl_add(wg, gl_mul(beta, a.sigmas[(size_t)j * a.sigma_stride + i])));
+    // numerators, and PREFIX PRODUCTS of the denominators: one inversion per row instead of one per chunk
+    u64 num[PP_MAX_CHUNKS], den[PP_MAX_CHUNKS], pre[PP_MAX_CHUNKS];
+    u64 run = 1;
+#pragma unroll
+    for (int k = 0; k < PP_MAX_CHUNKS; ++k) {
+        num[k] = den[k] = pre[k] = 1;
+        if (k < a.nchunks) {
+            u64 nu = 1, de = 1;
+            int j1 = min(a.num_routed, (k + 1) * a.chunk);
+            for (int j = k * a.chunk; j < j1; ++j) {
+                u64 w = a.wires[(size_t)j * a.wire_stride + i];
+                u64 wg = gl_add(w, gamma);
+                nu = gl_mul(nu, gl_add(wg, gl_mul(bx, a.k_is[j])));
+                de = gl_mul(de, gl_add(wg, gl_mul(beta, a.sigmas[(size_t)j * a.sigma_stride + i])));
+            }
+            num[k] = nu; den[k] = de;
+            pre[k] = run;                       // product of den[0..k)
+            run = gl_mul(run, de);
         }
-        u64 q = gl_mul(num, gl_inv(den));
-        a.chunkprod[((size_t)ch * a.nchunks + k) * n + i] = q;
-        tot = gl_mul(tot, q);
+    }
+    const bool degenerate = run == 0;            // some denominator is zero: keep the per-chunk definition (inv(0) = 0)
+    u64 inv_run = gl_inv(run);
+    u64 tot = 1;
+    u64 q[PP_MAX_CHUNKS];
+#pragma unroll
+    for (int k = PP_MAX_CHUNKS - 1; k >= 0; --k) {
+        q[k] = 1;
+        if (k < a.nchunks) {
+            u64 inv_k = degenerate ? gl_inv(den[k]) : gl_mul(inv_run, pre[k]);
+            inv_run = gl_mul(inv_run, den[k]);
+            q[k] = gl_mul(num[k], inv_k);
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < PP_MAX_CHUNKS; ++k) {
+        if (k < a.nchunks) {
+            a.chunkprod[((size_t)ch * a.nchunks + k) * n + i] = q[k];
+            tot = gl_mul(tot, q[k]);
+        }
     }
     a.rowtot[(size_t)ch * n + i] = tot;
 }
@@ -567,6 +594,7 @@ void launch_partial_products(const u64* wires, size_t wire_stride, const u64* si
     a.wires = wires; a.wire_stride = wire_stride; a.sigmas = sigma_values; a.sigma_stride = sigma_stride;
     a.k_is = k_is_dev; a.num_routed = num_routed; a.chunk = chunk; a.nchunks = (num_routed + chunk - 1) / chunk;
     a.nch = num_challenges; a.lg_n = lg_n;
+    if (a.nchunks > PP_MAX_CHUNKS) throw std::runtime_error("too many partial-product chunks");
     for (int c = 0; c < num_challenges; ++c) { a.betas[c] = betas_gammas[c]; a.gammas[c] = betas_gammas[num_challenges + c]; }
     size_t n = size_t(1) << lg_n;
     a.chunkprod = scratch;
@@ -810,6 +838,53 @@ void launch_eval_polys(const u64* coeffs, size_t stride, int ncols, unsigned lg_
     eval_polys_kernel<<<ncols, 256, 0, st>>>(coeffs, stride, lg_n, za, zb, out);
 }
 
+// all openings of a proof in two launches: powers of both points, then one CTA per (segment, polynomial)
+__global__ void ext_powers2_kernel(ext2 z0, ext2 z1, unsigned lg_n, u64* pw) {     // pw: [z0.a | z0.b | z1.a | z1.b], n each
+    size_t k = blockIdx.x * (size_t)blockDim.x + threadIdx.x, n = size_t(1) << lg_n;
+    if (k >= n) return;
+    ext2 r = e_pow(blockIdx.y ? z1 : z0, k);
+    pw[(2 * blockIdx.y) * n + k] = r.a;
+    pw[(2 * blockIdx.y + 1) * n + k] = r.b;
+}
+__global__ void __launch_bounds__(256) eval_polys_multi_kernel(OpeningsArgs a) {
+    __shared__ u64 sa[8], sb[8];
+    int c = blockIdx.x, seg = 0;
+    while (c >= a.seg[seg].ncols) { c -= a.seg[seg].ncols; ++seg; }
+    const size_t n = size_t(1) << a.lg_n;
+    const u64* cf = a.seg[seg].coeffs + (size_t)c * a.seg[seg].stride;
+    const u64* za = a.pw + (size_t)(2 * a.seg[seg].point) * n;
+    const u64* zb = za + n;
+    u64 x = 0, y = 0;
+    for (size_t k = threadIdx.x; k < n; k += blockDim.x) {
+        u64 v = cf[k];
+        x = gl_add(x, gl_mul(v, za[k]));
+        y = gl_add(y, gl_mul(v, zb[k]));
+    }
+    for (int off = 16; off > 0; off >>= 1) {
+        x = gl_add(x, __shfl_down_sync(0xffffffffu, x, off));
+        y = gl_add(y, __shfl_down_sync(0xffffffffu, y, off));
+    }
+    int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (lane == 0) { sa[warp] = x; sb[warp] = y; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int wv = 1; wv < (int)(blockDim.x >> 5); ++wv) { x = gl_add(x, sa[wv]); y = gl_add(y, sb[wv]); }
+        a.out[2 * blockIdx.x] = x;
+        a.out[2 * blockIdx.x + 1] = y;
+    }
+}
+void launch_openings(const OpeningsArgs& a, ext2 z0, ext2 z1, cudaStream_t st) {
+    const size_t n = size_t(1) << a.lg_n;
+    int total = 0;
+    for (int s = 0; s < a.nseg; ++s) total += a.seg[s].ncols;
+    dim3 g((unsigned)((n + 127) / 128), 2);
+    ZKB_COUNT_LAUNCH();
+    ext_powers2_kernel<<<g, 128, 0, st>>>(z0, z1, a.lg_n, a.pw);
+    if (total <= 0) return;
+    ZKB_COUNT_LAUNCH();
+    eval_polys_multi_kernel<<<total, 256, 0, st>>>(a);
+}
+
 // ---------------------------------------------------------------------------------------------
 // FRI (a10-a13)
 // ---------------------------------------------------------------------------------------------
@@ -819,30 +894,54 @@ struct FriCombineArgs {
     ext2 alpha_shift;                   // alpha^(#polys opened at g*zeta)
     u64* oa; u64* ob;
 };
-__global__ void __launch_bounds__(128) fri_combine_kernel(FriCombineArgs a) {
+// 32 points x 8 column groups per CTA: each thread sums every 8th column of its point, the groups are reduced through
+// shared memory, and one thread per point finishes with ONE field inversion for both quotients (a/(x - zeta) and
+// b/(x - g zeta) share inv(norm_0 norm_1)).
+__global__ void __launch_bounds__(256) fri_combine_kernel(FriCombineArgs a) {
+    __shared__ u64 red[4][8][32];
     const FriCombineParams& P = a.p;
-    size_t n = size_t(1) << P.lg_n;
-    size_t l = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
-    if (l >= n) return;
+    const size_t n = size_t(1) << P.lg_n;
+    const unsigned tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const size_t l = blockIdx.x * (size_t)32 + tx;
     u64 s0a = 0, s0b = 0, s1a = 0, s1b = 0;
-    int j = 0;
-    for (int t = 0; t < 4; ++t) {
-        const u64* col = P.lde[t] + l;
-        for (int c = 0; c < P.ncols[t]; ++c, ++j) {
-            u64 v = col[(size_t)c * P.stride[t]];
-            s0a = gl_add(s0a, gl_mul(v, a.apa[j]));
-            s0b = gl_add(s0b, gl_mul(v, a.apb[j]));
+    if (l < n) {
+        int j0 = 0;
+        for (int t = 0; t < 4; ++t) {
+            const u64* col = P.lde[t] + l;
+            const int nc = P.ncols[t];
+            int c = (int)((ty + 8 - (j0 & 7)) & 7);              // first column of this batch with (j0 + c) % 8 == ty
+            for (; c < nc; c += 8) {
+                const u64 v = col[(size_t)c * P.stride[t]];
+                const int j = j0 + c;
+                s0a = gl_add(s0a, gl_mul(v, a.apa[j]));
+                s0b = gl_add(s0b, gl_mul(v, a.apb[j]));
+            }
+            j0 += nc;
+        }
+        for (int c = (int)ty; c < P.num_zs; c += 8) {
+            const u64 v = P.lde[2][(size_t)c * P.stride[2] + l];
+            s1a = gl_add(s1a, gl_mul(v, a.apa[c]));
+            s1b = gl_add(s1b, gl_mul(v, a.apb[c]));
         }
     }
-    for (int c = 0; c < P.num_zs; ++c) {
-        u64 v = P.lde[2][(size_t)c * P.stride[2] + l];
-        s1a = gl_add(s1a, gl_mul(v, a.apa[c]));
-        s1b = gl_add(s1b, gl_mul(v, a.apb[c]));
+    red[0][ty][tx] = s0a; red[1][ty][tx] = s0b; red[2][ty][tx] = s1a; red[3][ty][tx] = s1b;
+    __syncthreads();
+    if (ty != 0 || l >= n) return;
+#pragma unroll
+    for (int g = 1; g < 8; ++g) {
+        s0a = gl_add(s0a, red[0][g][tx]); s0b = gl_add(s0b, red[1][g][tx]);
+        s1a = gl_add(s1a, red[2][g][tx]); s1b = gl_add(s1b, red[3][g][tx]);
     }
-    u64 x = gl_mul(GL_GEN, root_pow_lg(P.lg_n, bitrev32((u32)l, P.lg_n), false));
-    ext2 X = e_from(x);
-    ext2 q0 = e_mul(e_sub(e_make(s0a, s0b), P.reduced0), e_inv(e_sub(X, P.zeta)));
-    ext2 q1 = e_mul(e_sub(e_make(s1a, s1b), P.reduced1), e_inv(e_sub(X, P.zeta_next)));
+    const u64 x = gl_mul(GL_GEN, root_pow_lg(P.lg_n, bitrev32((u32)l, P.lg_n), false));
+    // 1 / (x - z) = conj(x - z) / norm(x - z), norm(u + v X) = u^2 - 7 v^2
+    const ext2 d0 = e_sub(e_from(x), P.zeta), d1 = e_sub(e_from(x), P.zeta_next);
+    const u64 n0 = gl_sub(gl_sqr(d0.a), gl_mul(GL_W, gl_sqr(d0.b))), n1 = gl_sub(gl_sqr(d1.a), gl_mul(GL_W, gl_sqr(d1.b)));
+    const u64 inv01 = gl_inv(gl_mul(n0, n1));
+    const u64 i0 = gl_mul(inv01, n1), i1 = gl_mul(inv01, n0);
+    const ext2 inv0 = e_make(gl_mul(d0.a, i0), gl_mul(gl_neg(d0.b), i0));
+    const ext2 inv1 = e_make(gl_mul(d1.a, i1), gl_mul(gl_neg(d1.b), i1));
+    ext2 q0 = e_mul(e_sub(e_make(s0a, s0b), P.reduced0), inv0);
+    ext2 q1 = e_mul(e_sub(e_make(s1a, s1b), P.reduced1), inv1);
     ext2 q = e_add(e_mul(q0, a.alpha_shift), q1);
     a.oa[l] = q.a;
     a.ob[l] = q.b;
@@ -851,7 +950,7 @@ void launch_fri_combine(const FriCombineParams& p, const u64* apa, const u64* ap
     FriCombineArgs a{p, apa, apb, e_pow(p.alpha, (u64)p.num_zs), oa, ob};
     size_t n = size_t(1) << p.lg_n;
     ZKB_COUNT_LAUNCH();
-    fri_combine_kernel<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(a);
+    fri_combine_kernel<<<(unsigned)((n + 31) / 32), 256, 0, st>>>(a);
 }
 
 __global__ void fri_fold_kernel(const u64* __restrict__ ca, const u64* __restrict__ cb, u64* __restrict__ oa, u64* __restrict__ ob,
@@ -891,7 +990,7 @@ __global__ void __launch_bounds__(128) pow_search_kernel(const u64* __restrict__
 void launch_pow_search(const u64* state12_dev, int pos, u64 base, u64 count, unsigned bits, unsigned long long* result, cudaStream_t st) {
     ZKB_COUNT_LAUNCH();
     u64 blocks = (count + 127) / 128;
-    if (blocks > 148 * 8) blocks = 148 * 8;      // one resident wave: 8 CTAs of 128 threads per SM
+    if (blocks > 148 * 4) blocks = 148 * 4;      // ~76 k candidates per sweep: the expected witness (2^16 for 16 bits) falls in the first or second
     pow_search_kernel<<<(unsigned)blocks, 128, 0, st>>>(state12_dev, pos, base, count, bits, result);
 }
 

@@ -77,6 +77,11 @@ void launch_quotient(const QuotientParams* params_dev, const QuotientParams& par
 // evaluate ncols coefficient polynomials (n each) at the ext point z: out[2*c], out[2*c+1]
 void launch_eval_polys(const u64* coeffs, size_t stride, int ncols, unsigned lg_n, const u64* zpow_a, const u64* zpow_b,
                        u64* out, cudaStream_t st);
+// every opening of a proof: out[2 i], out[2 i + 1] = P_i(point) for the polynomials of the segments in order.
+// pw: scratch of 4 n words (powers of the two points); point 0 = z0, 1 = z1
+struct OpeningsSeg { const u64* coeffs; size_t stride; int ncols; int point; };
+struct OpeningsArgs { OpeningsSeg seg[6]; int nseg; unsigned lg_n; u64* pw; u64* out; };
+void launch_openings(const OpeningsArgs& a, ext2 z0, ext2 z1, cudaStream_t st);
 // zpow[k] = z^k for k < n (SoA)
 void launch_ext_powers(ext2 z, unsigned lg_n, u64* zpow_a, u64* zpow_b, cudaStream_t st);
 

@@ -72,7 +72,7 @@ Circuit::Circuit(const uint8_t* common, size_t len, const u64* const_sigma, bool
     quot_.coeff_ptr = q_.get(); quot_.coeff_stride = n_;     // chunk (ch, m) = q[ch*N + m*n ..]
     pp_scratch_.alloc(partial_products_scratch_words((int)cd_.num_routed_wires, (int)cd_.quotient_degree_factor, nch, lg_n_));
     k_is_dev_.alloc(cd_.k_is.size());
-    zpow_.alloc(2 * n_);
+    zpow_.alloc(4 * n_);
     const int nall = ncs + nw + nzp + nq;
     openings_dev_.alloc(2 * (size_t)(nall + nch));
     const int nterms = nch * (2 + (int)cd_.num_partial_products) + (int)cd_.num_gate_constraints;
@@ -336,13 +336,16 @@ size_t Circuit::prove_resident(const u64* public_inputs, size_t n_pi, const u64*
 
     // (j) openings
     u64* od = openings_dev_.get();
-    launch_ext_powers(zeta, lg_n_, zpow_.get(), zpow_.get() + n_, st_);
-    launch_eval_polys(cs_.coeff_ptr, n_, ncs, lg_n_, zpow_.get(), zpow_.get() + n_, od, st_);
-    launch_eval_polys(wires_.coeff_ptr, n_, nw, lg_n_, zpow_.get(), zpow_.get() + n_, od + 2 * ncs, st_);
-    launch_eval_polys(zs_.coeff_ptr, n_, nzp, lg_n_, zpow_.get(), zpow_.get() + n_, od + 2 * (ncs + nw), st_);
-    launch_eval_polys(quot_.coeff_ptr, n_, nq, lg_n_, zpow_.get(), zpow_.get() + n_, od + 2 * (ncs + nw + nzp), st_);
-    launch_ext_powers(zeta_next, lg_n_, zpow_.get(), zpow_.get() + n_, st_);
-    launch_eval_polys(zs_.coeff_ptr, n_, nch, lg_n_, zpow_.get(), zpow_.get() + n_, od + 2 * nall, st_);
+    {
+        OpeningsArgs oa;
+        oa.seg[0] = {cs_.coeff_ptr, n_, ncs, 0};
+        oa.seg[1] = {wires_.coeff_ptr, n_, nw, 0};
+        oa.seg[2] = {zs_.coeff_ptr, n_, nzp, 0};
+        oa.seg[3] = {quot_.coeff_ptr, n_, nq, 0};
+        oa.seg[4] = {zs_.coeff_ptr, n_, nch, 1};          // Z polynomials again, at g * zeta
+        oa.nseg = 5; oa.lg_n = lg_n_; oa.pw = zpow_.get(); oa.out = od;
+        launch_openings(oa, zeta, zeta_next, st_);
+    }
     CK(cudaMemcpyAsync(h_open, od, 2 * (size_t)(nall + nch) * 8, cudaMemcpyDeviceToHost, st_));
     CK(cudaEventRecord(ev_[T_OPENINGS + 1], st_));
     sync();

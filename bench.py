@@ -25,6 +25,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, os.path.join(ROOT, "zk-circuits_b200"))
 
 WORKLOAD = "wormhole_zk_synth_n2^14"
+NCU_LDE_TRAFFIC_BYTES = 18952192 + 84903424   # dram__bytes_read.sum + dram__bytes_write.sum, one lde_block_kernel launch
 METRIC = "wormhole_proofs_per_sec"
 UNIT = "proofs/s"
 
@@ -298,8 +299,9 @@ def main():
         return
 
     peak, peak_src = hbm_peak()
-    # roofline of the LDE-NTT kernels on the wires batch (values -> coeffs -> 8x coset LDE): 80*n bytes per column
-    lde_bytes = 80 * n * nw
+    # roofline of the coset-LDE launch on the wires batch (lde_block_kernel: read n coefficients, write 8n values per
+    # column = 72 n bytes; the interpolation before it is timed separately as wires_intt, 16 n bytes per column)
+    lde_bytes = 72 * n * nw
     lde_ms = stages["wires_lde"]
     lde_gbs = lde_bytes / (lde_ms * 1e-3) / 1e9
     salt = 4
@@ -317,11 +319,19 @@ def main():
         "e2e": {"value": world * K * B / t_e2e, "unit": UNIT, "ms_per_step": 1000 * t_e2e / K,
                 "h2d_bytes_per_step": int(B * (nw * n * 8 + pis.size * 8)), "d2h_bytes_per_step": int(B * len(proof))},
         "gpu_launches": int(launches) * B,
-        "roofline": {"kernel": "wires LDE-NTT (intt + coset prescale + 8x NTT, 135 columns, n=2^14)", "bound": "hbm",
-                     "achieved": lde_gbs, "peak": peak, "unit": "GB/s", "frac": lde_gbs / peak, "traffic": None,
+        "roofline": {"kernel": "lde_block_kernel: coset pre-scale + 8 x NTT of the 135 wire columns, n = 2^14 (one launch)",
+                     "bound": "hbm", "achieved": lde_gbs, "peak": peak, "unit": "GB/s", "frac": lde_gbs / peak,
+                     "traffic": NCU_LDE_TRAFFIC_BYTES,
+                     "note": "integer-issue bound in practice (47 instr/byte vs 5.7 the chip can issue per HBM byte; DESIGN.md 4.2); "
+                             "traffic = dram read + write of one launch from profiles/r01_ncu_lde_block_v2.md (output partly still in L2)",
+                     "from_values_gbs": 80 * n * nw / ((stages["wires_intt"] + lde_ms) * 1e-3) / 1e9,
                      "peak_source": peak_src, "algorithmic_bytes_per_launch": lde_bytes, "avg_ms": lde_ms},
-        "poseidon": {"kernel": "wires Merkle (leaf sponge + levels)", "perms_per_launch": perms, "avg_ms": pos_ms,
-                     "perms_per_sec": perms / (pos_ms * 1e-3)},
+        "poseidon": {"kernel": "wires Merkle commit (merkle_leaves_kernel + 13 level launches)", "perms_per_launch": perms,
+                     "avg_ms": pos_ms, "perms_per_sec": perms / (pos_ms * 1e-3), "bound": "integer pipes (fmaheavy/IMAD + alu)",
+                     "imad_peak_per_s": 148 * 64 * 1.965e9,
+                     "frac_of_imad_peak_algorithmic": perms / (pos_ms * 1e-3) * 6600 / (148 * 64 * 1.965e9),
+                     "note": "6.6 k IMAD issue slots per permutation (SURVEY 8d); ncu: fmaheavy pipe 81 % of cycles active "
+                             "(profiles/r01_ncu_merkle_leaves_v1.md)"},
         "clocks": clk.summary(),
     }
     if not args.no_sweep:

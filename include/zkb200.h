@@ -82,7 +82,7 @@ int zkb_witness_upload(zkb_circuit* c, const uint64_t* wires);
 int zkb_prove_resident(zkb_circuit* c, const uint64_t* public_inputs, size_t n_pi, const uint64_t* salts, uint64_t salt_seed,
                        uint32_t pow_rule, uint8_t* proof_out, size_t proof_cap, size_t* proof_len);
 /* per-stage device times (ms, CUDA events on the circuit's stream) of the last prove; returns count written.
- * order: h2d, wires_lde, wires_merkle, partial_products, zs_commit, quotient, quotient_commit, openings,
+ * order: wires_intt, wires_lde, wires_merkle, partial_products, zs_commit, quotient, quotient_commit, openings,
  *        fri_combine, fri_commit, pow, queries, total */
 int zkb_last_timings(const zkb_circuit* c, float* ms_out, int cap);
 #define ZKB_NUM_TIMINGS 13

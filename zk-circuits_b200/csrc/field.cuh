@@ -207,6 +207,9 @@ ZKB_HD u64 gl_pow(u64 a, u64 e) {
     return r;
 }
 ZKB_HD u64 gl_sqr_n_lazy(u64 a, int k) {
+#if defined(__CUDA_ARCH__)
+#pragma unroll 1
+#endif
     for (int i = 0; i < k; ++i) a = gl_sqr_lazy(a);
     return a;
 }
@@ -230,6 +233,45 @@ inline u64 gl_root_of_unity(unsigned k) {
     for (unsigned i = k; i < 32; ++i) r = gl_mul(r, r);
     return r;
 }
+
+#if defined(__CUDACC__)
+// ---- device-only canonical arithmetic on carry flags (5 / 7 / ~25 instructions; the portable gl_add / gl_sub / gl_mul
+// compile to compare + select sequences of 9-12 on top) ----
+// canonical in, canonical out
+ZKB_D u64 f_sub(u64 a, u64 b) {
+    u32 o0, o1;
+    asm("{\n\t.reg .u32 m;\n\t"
+        "sub.cc.u32 %0, %2, %4;\n\t"
+        "subc.cc.u32 %1, %3, %5;\n\t"
+        "subc.u32 m, 0, 0;\n\t"              // borrow ? 0xffffffff : 0
+        "sub.cc.u32 %0, %0, m;\n\t"          // + p  ==  - (2^32 - 1)  (mod 2^64)
+        "subc.u32 %1, %1, 0;\n\t}"
+        : "=&r"(o0), "=&r"(o1) : "r"((u32)a), "r"((u32)(a >> 32)), "r"((u32)b), "r"((u32)(b >> 32)));
+    return ((u64)o1 << 32) | o0;
+}
+ZKB_D u64 f_add(u64 a, u64 b) {               // a - (p - b); p - b in (0, p], and a < p, so one borrow fix is exact
+    u32 o0, o1;
+    asm("{\n\t.reg .u32 m, n0, n1;\n\t"
+        "sub.cc.u32 n0, 1, %4;\n\t"
+        "subc.u32 n1, 0xffffffff, %5;\n\t"
+        "sub.cc.u32 %0, %2, n0;\n\t"
+        "subc.cc.u32 %1, %3, n1;\n\t"
+        "subc.u32 m, 0, 0;\n\t"
+        "sub.cc.u32 %0, %0, m;\n\t"
+        "subc.u32 %1, %1, 0;\n\t}"
+        : "=&r"(o0), "=&r"(o1) : "r"((u32)a), "r"((u32)(a >> 32)), "r"((u32)b), "r"((u32)(b >> 32)));
+    return ((u64)o1 << 32) | o0;
+}
+
+// r >= p  <=>  high word all ones and low word >= 1; then r - p = low - 1
+ZKB_D u64 f_canon(u64 r) {
+    u32 lo = (u32)r, hi = (u32)(r >> 32);
+    if (hi == 0xFFFFFFFFu && lo != 0) { lo -= 1; hi = 0; }
+    return ((u64)hi << 32) | lo;
+}
+ZKB_D u64 f_mul(u64 a, u64 b) { return f_canon(gl_mul_lazy(a, b)); }
+
+#endif
 
 // ---- quadratic extension, canonical components ----
 struct ext2 {

@@ -50,7 +50,7 @@ struct BatchDev {
     size_t cap_offset = 0;   // digest index of the cap level
 };
 
-enum Stage { T_H2D = 0, T_WIRES_LDE, T_WIRES_MERKLE, T_PP, T_ZS_COMMIT, T_QUOTIENT, T_QUOTIENT_COMMIT, T_OPENINGS,
+enum Stage { T_WIRES_INTT = 0, T_WIRES_LDE, T_WIRES_MERKLE, T_PP, T_ZS_COMMIT, T_QUOTIENT, T_QUOTIENT_COMMIT, T_OPENINGS,
              T_FRI_COMBINE, T_FRI_COMMIT, T_POW, T_QUERIES, T_TOTAL, T_COUNT };
 
 class Circuit {

@@ -103,3 +103,17 @@ def test_batch_of_proofs_on_two_streams(zkb, oracle):
     for seed, proof in zip(seeds, proofs):
         assert proof == oc.prove(s.wires, s.public_inputs, salt_seed=seed)
         assert oc.verify(proof) == ""
+
+
+@pytest.mark.gpu
+def test_non_canonical_witness_is_rejected(zkb):
+    """A wire value >= p is an argument error on both the one-shot and the split upload path (checked on the device)."""
+    s = zkb.SynthCircuit(zk=False, seed=4, **zkb.TINY)
+    c = zkb.ProverCircuit(s.common, s.const_sigma_values, is_values=True)
+    bad = s.wires.copy()
+    bad[3, 5] = np.uint64(0xFFFFFFFF00000001)          # = p
+    for call in (lambda: c.prove(bad, s.public_inputs), lambda: c.upload_witness(bad)):
+        with pytest.raises(zkb.ZkbError) as e:
+            call()
+        assert e.value.status == "ZKB_E_ARG"
+    assert len(c.prove(s.wires, s.public_inputs)) == c.proof_size      # the context is still usable

@@ -111,7 +111,11 @@ int zkb_prove_resident(zkb_circuit* c, const uint64_t* public_inputs, size_t n_p
 }
 int zkb_prove(zkb_circuit* c, const uint64_t* wires, const uint64_t* public_inputs, size_t n_pi, const uint64_t* salts,
               uint64_t salt_seed, uint32_t pow_rule, uint8_t* proof_out, size_t proof_cap, size_t* proof_len) {
-    int rc = zkb_witness_upload(c, wires);
+    int rc = guarded([&] {
+        if (!c) throw ArgError("circuit is null");
+        c->impl->upload_witness(wires, /*wait=*/false);      // the copy overlaps nothing here but saves one stream sync
+        return (int)ZKB_OK;
+    });
     if (rc != ZKB_OK) return rc;
     return zkb_prove_resident(c, public_inputs, n_pi, salts, salt_seed, pow_rule, proof_out, proof_cap, proof_len);
 }

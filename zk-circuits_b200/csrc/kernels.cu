@@ -295,6 +295,22 @@ size_t launch_merkle_levels(u64* digests, size_t num_leaves, unsigned cap_height
     return off;
 }
 
+// every element must be a canonical field element (< p): *flag |= 1 otherwise (the reference's types guarantee this; a
+// non-canonical u64 from a foreign caller would otherwise give a silently wrong proof)
+__global__ void canonical_check_kernel(const u64* __restrict__ v, size_t count, unsigned* flag) {
+    size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x, stride = (size_t)gridDim.x * blockDim.x;
+    bool bad = false;
+    for (; i < count; i += stride) bad |= v[i] >= GL_P;
+    if (__any_sync(0xffffffffu, bad) && (threadIdx.x & 31) == 0) atomicOr(flag, 1u);
+}
+void launch_canonical_check(const u64* v, size_t count, unsigned* flag_dev, cudaStream_t st) {
+    if (!count) return;
+    size_t blocks = (count + 1023) / 1024;
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    ZKB_COUNT_LAUNCH();
+    canonical_check_kernel<<<(unsigned)blocks, 256, 0, st>>>(v, count, flag_dev);
+}
+
 // ---------------------------------------------------------------------------------------------
 // salts (documented generator shared with the oracle: oracle/prover.hpp salt_value)
 // ---------------------------------------------------------------------------------------------

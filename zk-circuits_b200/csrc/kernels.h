@@ -46,6 +46,8 @@ void launch_coset_intt_bitrev(u64* data, size_t stride, int ncols, unsigned lg_m
 // in-place bit-reversal permutation of each column (leaf order <-> natural order)
 void launch_bitrev_permute(u64* data, size_t stride, int ncols, unsigned lg_n, cudaStream_t st);
 
+// *flag_dev |= 1 if any of the count elements is not a canonical field element
+void launch_canonical_check(const u64* v, size_t count, unsigned* flag_dev, cudaStream_t st);
 // salt columns: out[s * stride + l] = salt_value(seed, batch, s, l)  (documented SplitMix64 generator)
 void launch_salt_fill(u64* out, size_t stride, size_t num_leaves, u64 seed, unsigned batch, cudaStream_t st);
 

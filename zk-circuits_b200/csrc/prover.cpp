@@ -94,6 +94,7 @@ Circuit::Circuit(const uint8_t* common, size_t len, const u64* const_sigma, bool
         }
     }
     pow_dev_.alloc(16);
+    flag_dev_.alloc(1);
     const size_t nqr = cd_.num_query_rounds;
     query_idx_dev_.alloc(((1 + L) * nqr + 1) / 2 + 1);
     // query gather buffer
@@ -172,11 +173,27 @@ void Circuit::commit_batch(BatchDev& b, unsigned batch_id, const u64* salts_host
     CK(cudaMemcpyAsync(cap_host, b.digests.get() + b.cap_offset * 4, (size_t(32)) << cap_h, cudaMemcpyDeviceToHost, st_));
 }
 
-void Circuit::upload_witness(const u64* wires_host) {
+// H2D of the wire matrix + canonical check on the device. With wait = false nothing synchronises: the copy and the check
+// are queued ahead of the proof's kernels and the flag is read at the proof's first sync point (zkb_prove path).
+void Circuit::upload_witness(const u64* wires_host, bool wait) {
     if (!wires_host) throw ArgError("wires is null");
     DeviceGuard g(device_);
+    unsigned* flag = reinterpret_cast<unsigned*>(flag_dev_.get());
+    CK(cudaMemsetAsync(flag, 0, sizeof(u64), st_));
     CK(cudaMemcpyAsync(wires_vals_.get(), wires_host, cd_.num_wires * n_ * 8, cudaMemcpyHostToDevice, st_));
-    sync();
+    launch_canonical_check(wires_vals_.get(), cd_.num_wires * n_, flag, st_);
+    check_pending_ = true;
+    if (wait) {
+        sync();
+        finish_witness_check();
+    }
+}
+void Circuit::finish_witness_check() {     // stream must be idle
+    if (!check_pending_) return;
+    check_pending_ = false;
+    u64 f = 0;
+    CK(cudaMemcpy(&f, flag_dev_.get(), sizeof(u64), cudaMemcpyDeviceToHost));
+    if (f) throw ArgError("wires: non-canonical field element");
 }
 
 void Circuit::run_partial_products(const u64* betas, const u64* gammas) {
@@ -307,6 +324,7 @@ size_t Circuit::prove_resident(const u64* public_inputs, size_t n_pi, const u64*
     CK(cudaMemcpyAsync(wires_cap, wires_.digests.get() + wires_.cap_offset * 4, cap_words * 8, cudaMemcpyDeviceToHost, st_));
     CK(cudaEventRecord(ev_[T_WIRES_MERKLE + 1], st_));
     sync();
+    finish_witness_check();
     ch.observe_many(wires_cap, cap_words);
     u64 betas[2], gammas[2], alphas[2];
     for (int c = 0; c < nch; ++c) betas[c] = ch.get();

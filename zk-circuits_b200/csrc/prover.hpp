@@ -60,7 +60,8 @@ public:
 
     const CommonData& common() const { return cd_; }
     void verifier_only(u64* cap_out, u64 digest_out[4]) const;
-    void upload_witness(const u64* wires_host);
+    void upload_witness(const u64* wires_host, bool wait = true);
+    void finish_witness_check();
     size_t prove_resident(const u64* public_inputs, size_t n_pi, const u64* salts, u64 salt_seed, u32 pow_rule,
                           uint8_t* out, size_t cap);
     void partial_products(const u64* wires_host, const u64* betas, const u64* gammas, u64* out_host);
@@ -98,6 +99,8 @@ private:
     std::vector<DevBuf> fri_digests_;
     std::vector<size_t> fri_cap_off_;
     DevBuf pow_dev_;             // 12 state words + 1 result
+    DevBuf flag_dev_;            // witness canonical-check flag
+    bool check_pending_ = false;
     DevBuf query_idx_dev_;       // u32 indices: (1 + layers) * nq, packed in u64 words
     DevBuf query_out_dev_;
     // pinned host staging

@@ -22,6 +22,7 @@ namespace zkb {
 
 static std::atomic<unsigned long long> g_kernel_launches{0};
 unsigned long long kernel_launch_count() { return g_kernel_launches.load(); }
+void kernel_launch_count_add(unsigned long long n) { g_kernel_launches.fetch_add(n, std::memory_order_relaxed); }
 #define ZKB_COUNT_LAUNCH() (g_kernel_launches.fetch_add(1, std::memory_order_relaxed))
 
 // ---------------------------------------------------------------------------------------------

@@ -16,6 +16,7 @@ namespace zkb {
 // ---- one-time init (per device): Poseidon constants + twiddle tables ----
 void device_tables_init(int device);            // idempotent, thread-safe
 unsigned long long kernel_launch_count();       // kernels launched by this library so far (process-wide)
+void kernel_launch_count_add(unsigned long long n);   // replayed CUDA-graph kernel nodes
 
 // ---- Poseidon / Merkle ----
 void launch_poseidon_permute(u64* states, size_t count, cudaStream_t st);

@@ -147,12 +147,32 @@ Circuit::Circuit(const uint8_t* common, size_t len, const u64* const_sigma, bool
 Circuit::~Circuit() {
     cudaSetDevice(device_);
     if (st_) cudaStreamSynchronize(st_);
+    for (auto& kv : level_graphs_) if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
     for (auto& e : ev_) if (e) cudaEventDestroy(e);
     if (h_stage_) cudaFreeHost(h_stage_);
     if (st_) cudaStreamDestroy(st_);
 }
 
 void Circuit::sync() { CK(cudaStreamSynchronize(st_)); }
+
+size_t Circuit::run_merkle_levels(u64* digests, size_t num_leaves, unsigned cap_height) {
+    LevelGraph& g = level_graphs_[digests];
+    if (!g.exec) {
+        const unsigned long long before = kernel_launch_count();
+        cudaGraph_t graph = nullptr;
+        CK(cudaStreamBeginCapture(st_, cudaStreamCaptureModeThreadLocal));
+        g.cap_offset = launch_merkle_levels(digests, num_leaves, cap_height, st_);
+        CK(cudaStreamEndCapture(st_, &graph));
+        g.kernels = kernel_launch_count() - before;      // counted once at capture; every replay adds them again
+        if (!graph) return g.cap_offset;                 // a tree with no level above the leaves
+        CK(cudaGraphInstantiate(&g.exec, graph, 0));
+        CK(cudaGraphDestroy(graph));
+    } else {
+        kernel_launch_count_add(g.kernels);
+    }
+    CK(cudaGraphLaunch(g.exec, st_));
+    return g.cap_offset;
+}
 
 void Circuit::verifier_only(u64* cap_out, u64 digest_out[4]) const {
     if (cap_out) std::memcpy(cap_out, cs_cap_.data(), cs_cap_.size() * 8);
@@ -169,7 +189,7 @@ void Circuit::commit_batch(BatchDev& b, unsigned batch_id, const u64* salts_host
         else launch_salt_fill(sp, N_, N_, salt_seed, batch_id, st_);
     }
     launch_merkle_leaves(b.lde.get(), N_, b.ncols + b.salt, N_, b.digests.get(), st_);
-    b.cap_offset = launch_merkle_levels(b.digests.get(), N_, cap_h, st_);
+    b.cap_offset = run_merkle_levels(b.digests.get(), N_, cap_h);
     CK(cudaMemcpyAsync(cap_host, b.digests.get() + b.cap_offset * 4, (size_t(32)) << cap_h, cudaMemcpyDeviceToHost, st_));
 }
 
@@ -319,7 +339,7 @@ size_t Circuit::prove_resident(const u64* public_inputs, size_t n_pi, const u64*
         else launch_salt_fill(sp, N_, N_, salt_seed, 0, st_);
     }
     launch_merkle_leaves(wires_.lde.get(), N_, nw + wires_.salt, N_, wires_.digests.get(), st_);
-    wires_.cap_offset = launch_merkle_levels(wires_.digests.get(), N_, cap_h, st_);
+    wires_.cap_offset = run_merkle_levels(wires_.digests.get(), N_, cap_h);
     u64* wires_cap = h_caps;
     CK(cudaMemcpyAsync(wires_cap, wires_.digests.get() + wires_.cap_offset * 4, cap_words * 8, cudaMemcpyDeviceToHost, st_));
     CK(cudaEventRecord(ev_[T_WIRES_MERKLE + 1], st_));
@@ -413,7 +433,7 @@ size_t Circuit::prove_resident(const u64* public_inputs, size_t n_pi, const u64*
         launch_lde(ca, m, va, M, 2, lg_m, rate_bits, shift, st_);
         const size_t leaves = M >> ab;
         launch_merkle_leaves_ext(va, va + M, arity, leaves, fri_digests_[i].get(), st_);
-        fri_cap_off_[i] = launch_merkle_levels(fri_digests_[i].get(), leaves, cap_h, st_);
+        fri_cap_off_[i] = run_merkle_levels(fri_digests_[i].get(), leaves, cap_h);
         u64* lcap = h_caps + (3 + i) * cap_words;
         CK(cudaMemcpyAsync(lcap, fri_digests_[i].get() + fri_cap_off_[i] * 4, cap_words * 8, cudaMemcpyDeviceToHost, st_));
         sync();

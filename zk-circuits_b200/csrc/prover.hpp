@@ -6,6 +6,7 @@
 #include <cuda_runtime.h>
 #include <memory>
 #include <string>
+#include <map>
 #include <vector>
 #include "common_data.hpp"
 #include "kernels.h"
@@ -100,6 +101,11 @@ private:
     std::vector<size_t> fri_cap_off_;
     DevBuf pow_dev_;             // 12 state words + 1 result
     DevBuf flag_dev_;            // witness canonical-check flag
+    // The level chain of every Merkle tree (13 short, strictly dependent launches on fixed buffers) is captured once
+    // into a CUDA graph and replayed: one host call per tree instead of 13, no launch bubbles between 7-45 us kernels.
+    struct LevelGraph { cudaGraphExec_t exec = nullptr; size_t cap_offset = 0; unsigned long long kernels = 0; };
+    std::map<const u64*, LevelGraph> level_graphs_;
+    size_t run_merkle_levels(u64* digests, size_t num_leaves, unsigned cap_height);
     bool check_pending_ = false;
     DevBuf query_idx_dev_;       // u32 indices: (1 + layers) * nq, packed in u64 words
     DevBuf query_out_dev_;

@@ -83,9 +83,10 @@ int zkb_prove_resident(zkb_circuit* c, const uint64_t* public_inputs, size_t n_p
                        uint32_t pow_rule, uint8_t* proof_out, size_t proof_cap, size_t* proof_len);
 /* per-stage device times (ms, CUDA events on the circuit's stream) of the last prove; returns count written.
  * order: wires_intt, wires_lde, wires_merkle, partial_products, zs_commit, quotient, quotient_commit, openings,
- *        fri_combine, fri_commit, pow, queries, total */
+ *        fri_combine, fri_commit, pow, queries, total, then two host-side figures: milliseconds spent in the Fiat-Shamir
+ *        sponge (serial, between launches) and its permutation count */
 int zkb_last_timings(const zkb_circuit* c, float* ms_out, int cap);
-#define ZKB_NUM_TIMINGS 13
+#define ZKB_NUM_TIMINGS 15
 
 /* ---- stage-level entry points (parity tests + microbenchmarks); host pointers, run on `device` ---- */
 /* width-12 Poseidon permutation of `count` states (12 u64 each), in place */

@@ -24,7 +24,7 @@ pub const ZKB_E_NCCL: c_int = -7;
 pub const ZKB_E_BUFFER: c_int = -8;
 pub const ZKB_E_DIGEST: c_int = -9;
 pub const ZKB_POW_MIN: u32 = 0;
-pub const ZKB_NUM_TIMINGS: usize = 13;
+pub const ZKB_NUM_TIMINGS: usize = 15;
 
 extern "C" {
     pub fn zkb_version() -> *const c_char;

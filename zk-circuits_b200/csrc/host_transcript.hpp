@@ -2,6 +2,7 @@
 // (qp-plonky2 1.1.1 `iop::challenger::Challenger<F, PoseidonHash>`). The transcript is
 // strictly serial (~100 permutations per proof), so it runs on the host between kernel launches.
 #pragma once
+#include <chrono>
 #include <vector>
 #include "field.cuh"
 #include "kernels.h"
@@ -97,10 +98,15 @@ struct Challenger {
     int in_len = 0;
     u64 out_buf[8];
     int out_len = 0;
+    unsigned permutations = 0;      // host permutations so far (bench reports them: they sit on the proof's critical path)
+    double seconds = 0;
     void duplex() {
         for (int i = 0; i < in_len; ++i) sponge[i] = in_buf[i];
         in_len = 0;
+        const auto t0 = std::chrono::steady_clock::now();
         h_poseidon_permute(sponge);
+        seconds += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+        ++permutations;
         for (int i = 0; i < 8; ++i) out_buf[i] = sponge[i];
         out_len = 8;
     }

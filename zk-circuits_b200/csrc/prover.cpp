@@ -571,6 +571,8 @@ size_t Circuit::prove_resident(const u64* public_inputs, size_t n_pi, const u64*
     sync();
     for (int s = T_WIRES_INTT; s <= T_QUERIES; ++s) CK(cudaEventElapsedTime(&timings[s], ev_[s], ev_[s + 1]));
     CK(cudaEventElapsedTime(&timings[T_TOTAL], ev_[0], ev_[T_QUERIES + 1]));
+    timings[T_HOST_TRANSCRIPT] = (float)(ch.seconds * 1e3);      // wall time inside the Fiat-Shamir sponge (host, serial)
+    timings[T_HOST_PERMS] = (float)ch.permutations;
     return psize;
 }
 

@@ -52,7 +52,7 @@ struct BatchDev {
 };
 
 enum Stage { T_WIRES_INTT = 0, T_WIRES_LDE, T_WIRES_MERKLE, T_PP, T_ZS_COMMIT, T_QUOTIENT, T_QUOTIENT_COMMIT, T_OPENINGS,
-             T_FRI_COMBINE, T_FRI_COMMIT, T_POW, T_QUERIES, T_TOTAL, T_COUNT };
+             T_FRI_COMBINE, T_FRI_COMMIT, T_POW, T_QUERIES, T_TOTAL, T_HOST_TRANSCRIPT, T_HOST_PERMS, T_COUNT };
 
 class Circuit {
 public:

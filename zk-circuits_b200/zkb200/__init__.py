@@ -26,7 +26,7 @@ f32p = ctypes.POINTER(ctypes.c_float)
 STATUS = {0: "ZKB_OK", -1: "ZKB_E_ARG", -2: "ZKB_E_PARSE", -3: "ZKB_E_UNSUPPORTED_GATE", -4: "ZKB_E_UNSAT",
           -5: "ZKB_E_ZETA_IN_SUBGROUP", -6: "ZKB_E_CUDA", -7: "ZKB_E_NCCL", -8: "ZKB_E_BUFFER", -9: "ZKB_E_DIGEST"}
 TIMING_KEYS = ["wires_intt", "wires_lde", "wires_merkle", "partial_products", "zs_commit", "quotient", "quotient_commit",
-               "openings", "fri_combine", "fri_commit", "pow", "queries", "total"]
+               "openings", "fri_combine", "fri_commit", "pow", "queries", "total", "host_transcript", "host_permutations"]
 
 EXPORTS = ["zkb_version", "zkb_last_error", "zkb_device_count", "zkb_kernel_launch_count", "zkb_circuit_create", "zkb_circuit_destroy",
            "zkb_circuit_verifier_only", "zkb_proof_size", "zkb_prove", "zkb_witness_upload", "zkb_prove_resident",

@@ -80,6 +80,7 @@ private:
     CommonData cd_;
     int device_ = 0;
     cudaStream_t st_ = nullptr;
+    cudaEvent_t sync_ev_ = nullptr;       // blocking-sync event (see Circuit::sync)
     size_t n_ = 0, N_ = 0;
     unsigned lg_n_ = 0, lg_N_ = 0;
 

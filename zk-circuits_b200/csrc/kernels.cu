@@ -652,6 +652,10 @@ __device__ __noinline__ ulonglong2 q_acc2(ulonglong2 g, u64 c, u64 p0, u64 p1) {
     return g;
 }
 __device__ __noinline__ u64 q_sbox7(u64 x) { return gl_sbox7(x); }
+// The work of a point is split over two launches so that each has a small register and code footprint:
+// PART 1 = L0 term + permutation checks + every gate except Poseidon (stores the raw sums), PART 2 = Poseidon gates
+// (adds its sums and divides by Z_H). The constraint-to-alpha-power mapping is the same in both.
+template <int PART>
 __global__ void __launch_bounds__(128, 8) quotient_kernel(QuotientArgs a) {
     const QuotientParams& P = *a.p;
     const unsigned lgN = P.lg_n + P.rate_bits;
@@ -675,6 +679,8 @@ __global__ void __launch_bounds__(128, 8) quotient_kernel(QuotientArgs a) {
         acc0 = g.x; acc1 = g.y;
         ++term;
     };
+    const int nterm_perm = nch * (1 + nchunks);     // L0 terms + partial-product checks come first
+    if (PART == 1) {
     // L0(x) (Z - 1)
     u64 l0 = f_mul(P.zh[i & rate_mask], gl_inv(f_mul(gl_canon(u64(1) << P.lg_n), f_sub(x, 1))));
     for (int ch = 0; ch < nch; ++ch) add_term(f_mul(l0, f_sub(z[(size_t)ch * a.z_stride], 1)));
@@ -696,11 +702,13 @@ __global__ void __launch_bounds__(128, 8) quotient_kernel(QuotientArgs a) {
             prev = next;
         }
     }
+    }
     // gate constraints, filtered
-    const int goff = term;
+    const int goff = nterm_perm;
     const int nsel = P.num_selectors;
     for (int g = 0; g < P.num_gates; ++g) {
         const GateDesc gd = P.gates[g];
+        if ((gd.tag == TAG_POSEIDON) != (PART == 2)) continue;
         u64 s = cs[(size_t)gd.selector_index * a.cs_stride];
         u64 filter = 1;
         for (u32 r = gd.group_lo; r < gd.group_hi; ++r)
@@ -785,9 +793,14 @@ __global__ void __launch_bounds__(128, 8) quotient_kernel(QuotientArgs a) {
         acc0 = f_add(acc0, f_mul(filter, g0));
         if (nch > 1) acc1 = f_add(acc1, f_mul(filter, g1));
     }
-    u64 zi = P.zh_inv[i & rate_mask];
-    a.out[l] = f_mul(acc0, zi);
-    if (nch > 1) a.out[a.out_stride + l] = f_mul(acc1, zi);
+    if (PART == 1) {
+        a.out[l] = acc0;
+        if (nch > 1) a.out[a.out_stride + l] = acc1;
+    } else {
+        u64 zi = P.zh_inv[i & rate_mask];
+        a.out[l] = f_mul(f_add(acc0, a.out[l]), zi);
+        if (nch > 1) a.out[a.out_stride + l] = f_mul(f_add(acc1, a.out[a.out_stride + l]), zi);
+    }
 }
 
 void launch_quotient(const QuotientParams* params_dev, const QuotientParams& ph, const u64* apow_dev, int nterms,
@@ -796,7 +809,9 @@ void launch_quotient(const QuotientParams* params_dev, const QuotientParams& ph,
     QuotientArgs a{params_dev, apow_dev, nterms, cs_lde, cs_stride, wires_lde, w_stride, zs_lde, z_stride, out, out_stride};
     size_t N = size_t(1) << (ph.lg_n + ph.rate_bits);
     ZKB_COUNT_LAUNCH();
-    quotient_kernel<<<(unsigned)((N + 127) / 128), 128, 0, st>>>(a);
+    quotient_kernel<1><<<(unsigned)((N + 127) / 128), 128, 0, st>>>(a);
+    ZKB_COUNT_LAUNCH();
+    quotient_kernel<2><<<(unsigned)((N + 127) / 128), 128, 0, st>>>(a);
 }
 
 // ---------------------------------------------------------------------------------------------

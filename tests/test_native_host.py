@@ -9,7 +9,8 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 def test_limb_poseidon_matches_plain_permutation(tmp_path):
     exe = tmp_path / "test_poseidon_limbs"
-    subprocess.check_call(["/usr/bin/g++", "-O2", "-std=c++17", "-o", str(exe),
+    # -DZKB_CHECK_BOUNDS: abort if a limb ever leaves the range the 32-bit wrap-around argument assumes
+    subprocess.check_call(["/usr/bin/g++", "-O2", "-std=c++17", "-DZKB_CHECK_BOUNDS", "-o", str(exe),
                            os.path.join(ROOT, "tests", "native", "test_poseidon_limbs.cpp")])
     out = subprocess.run([str(exe), "5000"], capture_output=True, text=True, timeout=600)
     assert out.returncode == 0, out.stdout + out.stderr

@@ -31,6 +31,14 @@ constexpr int P_PARTIAL = 22;
 constexpr int P_ROUNDS = 30;
 constexpr u32 P_M22 = (1u << 22) - 1, P_M20 = (1u << 20) - 1;
 
+// host-only self-check of the range argument behind the 32-bit limb arithmetic (tests/native build with -DZKB_CHECK_BOUNDS)
+#if defined(ZKB_CHECK_BOUNDS) && !defined(__CUDA_ARCH__)
+#include <cstdlib>
+#define ZKB_BOUND_CHECK(cond) do { if (!(cond)) { std::abort(); } } while (0)
+#else
+#define ZKB_BOUND_CHECK(cond) do { } while (0)
+#endif
+
 ZKB_HD u64 gl_sbox7(u64 x) {
     u64 x2 = gl_sqr_lazy(x);
     u64 x3 = gl_mul_lazy(x2, x);
@@ -93,6 +101,7 @@ ZKB_HD u64 limb_to_u64_biased(u32 x0, u32 x1, u32 x2) {
     int c1 = (int)x1 >> 22;
     x1 &= P_M22;
     x2 += (u32)c1;
+    ZKB_BOUND_CHECK((int)x2 >= 0);           // the biased constants keep the top limb non-negative
     u32 top = x2 >> 20;                      // >= 1: the bias puts 2^20 into limb 2
     x2 &= P_M20;
     u32 lo = x0 | (x1 << 22), hi = (x1 >> 10) | (x2 << 12);
@@ -107,6 +116,9 @@ ZKB_HD u64 limb_to_u64_biased(u32 x0, u32 x1, u32 x2) {
 // (out[r] = sum_i x[(i+r) % 12] C[i]); derivation and the Python check of these formulas: DESIGN.md §4.1.
 // rc: limb k of the next round's 12 constants at rc[3 * j], added into the output sums (free third IADD3 operand)
 ZKB_HD void mds_limb12(u32* x, const u32* __restrict__ rc) {
+#if defined(ZKB_CHECK_BOUNDS) && !defined(__CUDA_ARCH__)
+    for (int j = 0; j < 12; ++j) ZKB_BOUND_CHECK((int)x[j] > -(1 << 21) - 1 && (int)x[j] < (1 << 22) + (1 << 21));   // normalised inputs
+#endif
     u32 P[3], M[3], R[3], I[3];
 #pragma unroll
     for (int b = 0; b < 3; ++b) {

@@ -340,7 +340,7 @@ def main():
     if not args.no_sweep:
         # config #3 points: fused from_values commit of synthetic columns, inputs resident in HBM
         sweep = []
-        for lg_n, cols in ((16, 135), (18, 100), (20, 100)):
+        for lg_n, cols in ((14, 400), (16, 135), (18, 100), (20, 100), (22, 100)):
             nn = 1 << lg_n
             vals = synth_columns(np, lg_n, cols)
             _, tm = Z.commit_batch(vals, 3, 4, reps=3, device=local_rank)

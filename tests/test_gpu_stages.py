@@ -175,3 +175,32 @@ def test_coset_sharded_commit_parts_concatenate_to_the_full_cap(zkb, oracle, lg_
         zkb.commit_cosets(vals, 3, 4, 1, 3)          # unaligned block range
     with pytest.raises(zkb.ZkbError):
         zkb.commit_cosets(vals, 3, 2, 0, 4)          # cap_height < rate_bits
+
+
+def test_lde_max_microbench_size_properties(zkb, oracle):
+    """BASELINE config #3's largest degree, n = 2^22 (two-step transform with n1 = 256, n2 = 2^14): linearity of the
+    whole from_values map, and one leaf + one subgroup value re-evaluated from the returned coefficients by Horner."""
+    rng = np.random.default_rng(22)
+    lg_n, rb = 22, 3
+    n = 1 << lg_n
+    a = rand_felts(rng, (1, n))
+    b = rand_felts(rng, (1, n))
+    s = ((a.astype(object) + b.astype(object)) % P).astype(np.uint64)
+    ca, la = zkb.lde_batch(np.concatenate([a, b, s]), rb)
+    assert np.array_equal(((la[0].astype(object) + la[1].astype(object)) % P).astype(np.uint64), la[2])
+    assert np.array_equal(((ca[0].astype(object) + ca[1].astype(object)) % P).astype(np.uint64), ca[2])
+    lgN = lg_n + rb
+    g, w = 0xC65C18B67785D900, oracle.root_of_unity(lgN)
+    coeffs = [int(x) for x in ca[0]]
+
+    def horner(x):
+        acc = 0
+        for c in reversed(coeffs):
+            acc = (acc * x + c) % P
+        return acc
+
+    l = 0x1234567
+    i = int(format(l, f"0{lgN}b")[::-1], 2)
+    assert horner(g * pow(w, i, P) % P) == int(la[0, l])
+    j = 3141592
+    assert horner(pow(oracle.root_of_unity(lg_n), j, P)) == int(a[0, j])

@@ -317,7 +317,9 @@ def main():
         "dtype": "u64 (Goldilocks field, F_p^2 extension)", "data": "synthetic",
         "config": {"workload": WORKLOAD, "degree_bits": 14, "zero_knowledge": True, "num_wires": nw, "proof_bytes": len(proof),
                    "proofs_per_step_per_gpu": B, "parallelism": f"replica x{world} (no collective), {B} proof streams per GPU",
-                   "l2": "no flush: one proof streams ~0.5 GB of LDE/leaf data, far above the 126 MB L2"},
+                   "l2": "no flush: one proof streams ~0.5 GB of LDE/leaf data, far above the 126 MB L2",
+                   "timer": "host clock between device synchronisations + rank barrier (a step contains host-side Fiat-Shamir "
+                            "work between launches); stage_ms and the roofline numbers are CUDA events on the proving stream"},
         "prove_ms_single_stream": 1000 * t_single / K, "device_ms_per_proof": stages["total"], "stage_ms": stages,
         "e2e": {"value": world * K * B / t_e2e, "unit": UNIT, "ms_per_step": 1000 * t_e2e / K,
                 "h2d_bytes_per_step": int(B * (nw * n * 8 + pis.size * 8)), "d2h_bytes_per_step": int(B * len(proof))},

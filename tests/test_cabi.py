@@ -78,3 +78,20 @@ def test_rust_sys_crate_declares_every_header_symbol():
     hdr = open(os.path.join(ROOT, "include", "zkb200.h")).read()
     for name, val in re.findall(r"pub const (ZKB_E_[A-Z_]+): c_int = (-?\d+);", rs):
         assert re.search(name + r"\s*=\s*" + val + r"\b", hdr), name
+
+
+def test_header_is_plain_c_and_the_c_example_links(zkb, tmp_path):
+    """include/zkb200.h must be usable from C (no C++ types in the ABI): compile and link examples/prove_example.c with
+    gcc -std=c11 against the built library. Without a GPU the program exits 2 after printing the library version."""
+    import subprocess
+
+    exe = tmp_path / "prove_example"
+    lib_dir = os.path.dirname(zkb.LIB_PATH)
+    subprocess.check_call(["gcc", "-std=c11", "-Wall", "-Werror", "-O2", "-I", os.path.join(ROOT, "include"),
+                           os.path.join(ROOT, "examples", "prove_example.c"), "-L", lib_dir, "-lzkb200",
+                           f"-Wl,-rpath,{lib_dir}", "-o", str(exe)])
+    out = subprocess.run([str(exe)], capture_output=True, text=True, timeout=120)
+    if zkb.device_count() == 0:
+        assert out.returncode == 2 and "no CUDA device" in out.stderr and "sm_100a" in out.stderr
+    else:
+        assert out.returncode == 0, out.stderr

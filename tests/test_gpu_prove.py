@@ -117,3 +117,23 @@ def test_non_canonical_witness_is_rejected(zkb):
             call()
         assert e.value.status == "ZKB_E_ARG"
     assert len(c.prove(s.wires, s.public_inputs)) == c.proof_size      # the context is still usable
+
+
+@pytest.mark.gpu
+def test_c_client_proof_is_accepted_and_byte_identical(zkb, oracle, tmp_path):
+    """examples/prove_example.c (plain C over the ABI, no Python in the loop) proves the same synthetic circuit; its bytes
+    are accepted by the pinned verifier and equal the oracle prover's."""
+    import os
+    import subprocess
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe, out = tmp_path / "prove_example", tmp_path / "proof.bin"
+    lib_dir = os.path.dirname(zkb.LIB_PATH)
+    subprocess.check_call(["gcc", "-std=c11", "-O2", "-I", os.path.join(root, "include"), os.path.join(root, "examples", "prove_example.c"),
+                           "-L", lib_dir, "-lzkb200", f"-Wl,-rpath,{lib_dir}", "-o", str(exe)])
+    subprocess.check_call([str(exe), "1", str(out)])
+    proof = out.read_bytes()
+    s = zkb.SynthCircuit(zk=True, seed=42, **zkb.TINY)
+    oc = oracle.Circuit(s.common, s.const_sigma_values)
+    assert oc.verify(proof) == ""
+    assert proof == oc.prove(s.wires, s.public_inputs, salt_seed=7)

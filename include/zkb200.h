@@ -32,7 +32,9 @@ typedef enum zkb_status {
     ZKB_E_ARG = -1,               /* null pointer, bad size, non-canonical field element            */
     ZKB_E_PARSE = -2,             /* malformed CommonCircuitData bytes                              */
     ZKB_E_UNSUPPORTED_GATE = -3,  /* gate tag / config outside the implemented set                  */
-    ZKB_E_UNSAT = -4,             /* self-check: vanishing identity fails at zeta (bad witness)     */
+    ZKB_E_UNSAT = -4,             /* reserved (optional vanishing-identity self-check at zeta); not returned by this
+                                     version: like the CPU prover, a witness that violates a constraint yields a
+                                     proof the verifier rejects (witness generation, which catches it, stays in Rust) */
     ZKB_E_ZETA_IN_SUBGROUP = -5,  /* reference: "Opening point is in the subgroup."                 */
     ZKB_E_CUDA = -6,
     ZKB_E_NCCL = -7,

@@ -3,6 +3,7 @@
 #include <atomic>
 #include <cstdlib>
 #include <cstring>
+#include <chrono>
 #include <thread>
 
 namespace zkb {
@@ -165,8 +166,9 @@ Circuit::~Circuit() {
 // prover contexts in a process than host cores available to it (8 ranks x 8 streams on a 32-core box) the wait polls
 // and yields instead, so that runnable threads are not starved by spinners. A blocking (interrupt) wait was measured
 // and is much worse here (708 vs 1355 proofs/s at 8 GPUs). ZKB_SYNC=spin|yield|block overrides the choice.
-static int sync_mode() {      // 0 spin, 1 yield, 2 block
+static int sync_mode() {      // 0 spin, 1 yield, 2 block, 3 sleep-poll
     if (const char* e = std::getenv("ZKB_SYNC")) {
+        if (!std::strcmp(e, "sleep")) return 3;
         if (!std::strcmp(e, "block")) return 2;
         if (!std::strcmp(e, "yield")) return 1;
         if (!std::strcmp(e, "spin")) return 0;
@@ -185,6 +187,10 @@ void Circuit::sync() {
     } else if (mode == 1) {
         cudaError_t e;
         while ((e = cudaStreamQuery(st_)) == cudaErrorNotReady) std::this_thread::yield();
+        CK(e);
+    } else if (mode == 3) {      // poll every ~20 us and sleep in between: frees the core, costs tens of microseconds per wait
+        cudaError_t e;
+        while ((e = cudaStreamQuery(st_)) == cudaErrorNotReady) std::this_thread::sleep_for(std::chrono::microseconds(20));
         CK(e);
     } else {
         CK(cudaStreamSynchronize(st_));

@@ -11,8 +11,18 @@ size_t Gate::num_constraints() const {
         case GATE_BASE_SUM_2: return 1 + param;
         case GATE_ARITHMETIC: return param;
         case GATE_POSEIDON: return 123;
+        // recursion gate set (D = 2)
+        case GATE_ARITHMETIC_EXT: case GATE_MUL_EXT: return 2 * param;
+        case GATE_REDUCING: case GATE_REDUCING_EXT: return 2 * param;
+        case GATE_RANDOM_ACCESS: return p2 * (param + 2) + p3;
+        case GATE_EXPONENTIATION: return param + 1;
+        case GATE_COSET_INTERP: return 2 + 2 * 2 * coset_interp_num_intermediates(*this) + 2;
+        case GATE_POSEIDON_MDS: return 24;
         default: throw std::runtime_error("unsupported gate tag " + std::to_string(tag));
     }
+}
+size_t coset_interp_num_intermediates(const Gate& g) {
+    return ((size_t(1) << g.param) - 2) / (g.p2 - 1);
 }
 unsigned Gate::degree() const {
     switch (tag) {
@@ -22,13 +32,21 @@ unsigned Gate::degree() const {
         case GATE_BASE_SUM_2: return 2;
         case GATE_ARITHMETIC: return 3;
         case GATE_POSEIDON: return 7;
+        case GATE_ARITHMETIC_EXT: case GATE_MUL_EXT: return 3;
+        case GATE_REDUCING: case GATE_REDUCING_EXT: return 2;
+        case GATE_RANDOM_ACCESS: return (unsigned)param + 1;
+        case GATE_EXPONENTIATION: return 4;
+        case GATE_COSET_INTERP: return (unsigned)p2;
+        case GATE_POSEIDON_MDS: return 1;
         default: throw std::runtime_error("unsupported gate tag " + std::to_string(tag));
     }
 }
 size_t Gate::num_constants() const {
     switch (tag) {
         case GATE_CONSTANT: return param;
-        case GATE_ARITHMETIC: return 2;
+        case GATE_ARITHMETIC: case GATE_ARITHMETIC_EXT: return 2;
+        case GATE_MUL_EXT: return 1;
+        case GATE_RANDOM_ACCESS: return p3;
         default: return 0;
     }
 }
@@ -167,6 +185,17 @@ CommonData parse_common(const u8* p, size_t len, size_t* consumed) {
         switch (g.tag) {
             case GATE_NOOP: case GATE_PUBLIC_INPUT: case GATE_POSEIDON: break;
             case GATE_CONSTANT: case GATE_BASE_SUM_2: case GATE_ARITHMETIC: g.param = r.r64(); break;
+            case GATE_POSEIDON_MDS: break;
+            case GATE_ARITHMETIC_EXT: case GATE_MUL_EXT: case GATE_REDUCING: case GATE_REDUCING_EXT:
+            case GATE_EXPONENTIATION: g.param = r.r64(); break;
+            case GATE_RANDOM_ACCESS: g.param = r.r64(); g.p2 = r.r64(); g.p3 = r.r64(); break;
+            case GATE_COSET_INTERP: {
+                g.param = r.r64(); g.p2 = r.r64();
+                u64 nw = r.r64();
+                if (g.param > 8 || nw != (u64(1) << g.param) || g.p2 < 2) throw std::runtime_error("bad CosetInterpolationGate");
+                for (u64 k = 0; k < nw; ++k) g.weights.push_back(r.felt());
+                break;
+            }
             default: throw std::runtime_error("unsupported gate tag " + std::to_string(g.tag));
         }
         c.gates.push_back(g);
@@ -197,7 +226,13 @@ std::vector<u8> write_common(const CommonData& c) {
     w.w64(c.gates.size());
     for (auto& g : c.gates) {
         w.w32(g.tag);
-        if (g.tag == GATE_CONSTANT || g.tag == GATE_BASE_SUM_2 || g.tag == GATE_ARITHMETIC) w.w64(g.param);
+        switch (g.tag) {
+            case GATE_CONSTANT: case GATE_BASE_SUM_2: case GATE_ARITHMETIC: case GATE_ARITHMETIC_EXT: case GATE_MUL_EXT:
+            case GATE_REDUCING: case GATE_REDUCING_EXT: case GATE_EXPONENTIATION: w.w64(g.param); break;
+            case GATE_RANDOM_ACCESS: w.w64(g.param); w.w64(g.p2); w.w64(g.p3); break;
+            case GATE_COSET_INTERP: w.w64(g.param); w.w64(g.p2); w.usize_vec(g.weights); break;
+            default: break;
+        }
     }
     return w.b;
 }

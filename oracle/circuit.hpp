@@ -35,11 +35,20 @@ enum GateTag : u32 {  // default gate-serializer tag order (B.1)
 
 struct Gate {
     u32 tag = GATE_NOOP;
-    u64 param = 0;  // Constant: num_consts; BaseSum: num_limbs; Arithmetic: num_ops
+    // Constant: num_consts; BaseSum: num_limbs; Arithmetic / ArithmeticExtension / MulExtension: num_ops;
+    // Reducing / ReducingExtension: num_coeffs; Exponentiation: num_power_bits; RandomAccess: bits;
+    // CosetInterpolation: subgroup_bits
+    u64 param = 0;
+    u64 p2 = 0, p3 = 0;       // RandomAccess: num_copies, num_extra_constants; CosetInterpolation: degree, -
+    std::vector<u64> weights; // CosetInterpolation: barycentric weights (2^subgroup_bits felts)
+    Gate() = default;
+    Gate(u32 t, u64 p, u64 q2 = 0, u64 q3 = 0) : tag(t), param(p), p2(q2), p3(q3) {}
     size_t num_constraints() const;
     unsigned degree() const;
     size_t num_constants() const;
 };
+
+size_t coset_interp_num_intermediates(const Gate& g);   // (2^subgroup_bits - 2) / (degree - 1)
 
 struct FriConfig {
     u64 rate_bits = 3, cap_height = 4, num_query_rounds = 28;

@@ -23,7 +23,9 @@ struct Rng {
     u64 felt() { return from_u64(next()); }
     u64 below(u64 m) { return next() % m; }
 };
-constexpr int G_NOOP = 0, G_CONST = 1, G_PI = 2, G_BASESUM = 3, G_ARITH = 4, G_POSEIDON = 5;
+// row kinds (indices into the per-circuit gate table are looked up through `gate_index`)
+enum Kind { G_NOOP = 0, G_CONST, G_PI, G_BASESUM, G_ARITH, G_POSEIDON,
+            G_ARITH_EXT, G_MUL_EXT, G_REDUCING, G_REDUCING_EXT, G_RANDOM_ACCESS, G_EXP, G_COSET, G_MDS, NUM_KINDS };
 
 struct Row {
     int gate = G_NOOP;
@@ -44,10 +46,50 @@ SynthCircuit make_synth_circuit(const SynthSpec& spec) {
     c.use_base_arithmetic_gate = true; c.zero_knowledge = spec.zk;
     c.fri_config = FriConfig{3, 4, 28, 16, 1, {4, 5}};
     c.hiding = spec.zk;
-    c.gates = {{GATE_NOOP, 0}, {GATE_CONSTANT, 2}, {GATE_PUBLIC_INPUT, 0}, {GATE_BASE_SUM_2, 63}, {GATE_ARITHMETIC, 20}, {GATE_POSEIDON, 0}};
-    c.selector_indices = {0, 0, 0, 0, 0, 1};
-    c.groups = {{0, 5}, {5, 6}};
-    c.quotient_degree_factor = 8; c.num_gate_constraints = 123; c.num_constants = 4;
+    // gate table sorted by (degree, id) as upstream's CircuitBuilder::build does, and selector groups by its greedy rule
+    // (selector_polynomials: extend a group while size + degree < max_quotient_degree_factor + 1)
+    const bool recursion = spec.n_arith_ext + spec.n_mul_ext + spec.n_reducing + spec.n_reducing_ext + spec.n_random_access +
+                           spec.n_exp + spec.n_coset + spec.n_mds > 0;
+    int gate_index[NUM_KINDS];
+    std::fill(gate_index, gate_index + NUM_KINDS, -1);
+    if (!recursion) {
+        c.gates = {{GATE_NOOP, 0}, {GATE_CONSTANT, 2}, {GATE_PUBLIC_INPUT, 0}, {GATE_BASE_SUM_2, 63}, {GATE_ARITHMETIC, 20}, {GATE_POSEIDON, 0}};
+        const Kind kinds[] = {G_NOOP, G_CONST, G_PI, G_BASESUM, G_ARITH, G_POSEIDON};
+        for (int i = 0; i < 6; ++i) gate_index[kinds[i]] = i;
+    } else {
+        // the set `verify_proof` instantiates under standard_recursion_config (135 wires, 80 routed, D = 2)
+        Gate coset(GATE_COSET_INTERP, 4, 6);      // arity 16, with_max_degree(4, 8): 2 intermediates, degree 6
+        {
+            u64 gen = root_of_unity(4), xi = 1;
+            std::vector<u64> xs(16);
+            for (auto& x : xs) { x = xi; xi = fmul(xi, gen); }
+            for (int i = 0; i < 16; ++i) {
+                u64 d = 1;
+                for (int j = 0; j < 16; ++j) if (j != i) d = fmul(d, fsub(xs[i], xs[j]));
+                coset.weights.push_back(finv(d));
+            }
+        }
+        struct KG { Kind k; Gate g; };
+        const KG table[] = {
+            {G_NOOP, {GATE_NOOP, 0}}, {G_CONST, {GATE_CONSTANT, 2}}, {G_MDS, {GATE_POSEIDON_MDS, 0}}, {G_PI, {GATE_PUBLIC_INPUT, 0}},
+            {G_BASESUM, {GATE_BASE_SUM_2, 63}}, {G_REDUCING_EXT, {GATE_REDUCING_EXT, 32}}, {G_REDUCING, {GATE_REDUCING, 43}},
+            {G_ARITH_EXT, {GATE_ARITHMETIC_EXT, 10}}, {G_ARITH, {GATE_ARITHMETIC, 20}}, {G_MUL_EXT, {GATE_MUL_EXT, 13}},
+            {G_EXP, {GATE_EXPONENTIATION, 66}}, {G_RANDOM_ACCESS, {GATE_RANDOM_ACCESS, 4, 4, 2}}, {G_COSET, coset},
+            {G_POSEIDON, {GATE_POSEIDON, 0}}};
+        for (const KG& e : table) { gate_index[e.k] = (int)c.gates.size(); c.gates.push_back(e.g); }
+    }
+    c.selector_indices.assign(c.gates.size(), 0);
+    for (size_t start = 0; start < c.gates.size();) {
+        size_t size = 0;
+        while (start + size < c.gates.size() && size + c.gates[start + size].degree() < c.max_quotient_degree_factor + 1) ++size;
+        if (size == 0) throw std::runtime_error("gate degree too high for the quotient degree factor");
+        for (size_t i = start; i < start + size; ++i) c.selector_indices[i] = c.groups.size();
+        c.groups.push_back({start, start + size});
+        start += size;
+    }
+    const size_t nsel = c.groups.size();
+    c.quotient_degree_factor = 8; c.num_gate_constraints = 0; c.num_constants = nsel + 2;
+    for (auto& g : c.gates) c.num_gate_constraints = std::max<u64>(c.num_gate_constraints, g.num_constraints());
     c.num_public_inputs = spec.num_public_inputs;
     c.k_is.resize(80);
     c.k_is[0] = 1;
@@ -71,6 +113,11 @@ SynthCircuit make_synth_circuit(const SynthSpec& spec) {
         }
         rows[row].w[col] = v;
         return v;
+    };
+    auto take_ext = [&](u32 row, u32 col) {     // two routed wires = one F_{p^2} value (sequenced: the RNG stream is part of the spec)
+        u64 a = take_input(row, col);
+        u64 b = take_input(row, col + 1);
+        return E2(a, b);
     };
     auto copy_from = [&](u32 row, u32 col, const Pooled& p) {
         rows[row].w[col] = p.value;
@@ -157,6 +204,14 @@ SynthCircuit make_synth_circuit(const SynthSpec& spec) {
     for (size_t i = 1; i < spec.n_const; ++i) todo.push_back(G_CONST);
     for (size_t i = 0; i < spec.n_base_sum; ++i) todo.push_back(G_BASESUM);
     for (size_t i = 0; i < spec.n_arith; ++i) todo.push_back(G_ARITH);
+    for (size_t i = 0; i < spec.n_arith_ext; ++i) todo.push_back(G_ARITH_EXT);
+    for (size_t i = 0; i < spec.n_mul_ext; ++i) todo.push_back(G_MUL_EXT);
+    for (size_t i = 0; i < spec.n_reducing; ++i) todo.push_back(G_REDUCING);
+    for (size_t i = 0; i < spec.n_reducing_ext; ++i) todo.push_back(G_REDUCING_EXT);
+    for (size_t i = 0; i < spec.n_random_access; ++i) todo.push_back(G_RANDOM_ACCESS);
+    for (size_t i = 0; i < spec.n_exp; ++i) todo.push_back(G_EXP);
+    for (size_t i = 0; i < spec.n_coset; ++i) todo.push_back(G_COSET);
+    for (size_t i = 0; i < spec.n_mds; ++i) todo.push_back(G_MDS);
     // Poseidon rows come in sponge chains (storage-proof-like, 24 rows) and single compressions
     size_t pos_left = spec.n_poseidon > poseidon_used ? spec.n_poseidon - poseidon_used : 0;
     const int CHAIN = -1;
@@ -205,6 +260,108 @@ SynthCircuit make_synth_circuit(const SynthSpec& spec) {
                 u64 out = fadd(fmul(rows[r].consts[0], fmul(m0, m1)), fmul(rows[r].consts[1], ad));
                 rows[r].w[4 * i + 3] = out;
                 pool.push_back({out, {r, 4 * i + 3}});
+            }
+        } else if (t == G_ARITH_EXT || t == G_MUL_EXT) {
+            // F_{p^2} multiply-add rows of the recursive verifier (reduce_with_powers, opening combination)
+            const bool addend = t == G_ARITH_EXT;
+            const u32 per = addend ? 8 : 6, ops = addend ? 10 : 13;
+            u32 r = new_row(t);
+            rows[r].consts[0] = rng.below(2) ? 1 : rng.felt();
+            if (addend) rows[r].consts[1] = rng.below(2) ? 1 : rng.felt();
+            for (u32 i = 0; i < ops; ++i) {
+                E2 a = take_ext(r, per * i);
+                E2 b = take_ext(r, per * i + 2);
+                E2 o = emul_base(a * b, rows[r].consts[0]);
+                if (addend) o = o + emul_base(take_ext(r, per * i + 4), rows[r].consts[1]);
+                rows[r].w[per * i + per - 2] = o.a;
+                rows[r].w[per * i + per - 1] = o.b;
+                pool.push_back({o.a, {r, per * i + per - 2}});
+                pool.push_back({o.b, {r, per * i + per - 1}});
+            }
+        } else if (t == G_REDUCING || t == G_REDUCING_EXT) {
+            // acc <- acc * alpha + coeff chains (FRI batch reduction inside the recursive verifier)
+            const bool ext = t == G_REDUCING_EXT;
+            const u32 nc = ext ? 32 : 43, start_accs = 6 + (ext ? 2 * nc : nc);
+            u32 r = new_row(t);
+            E2 alpha = take_ext(r, 2);
+            E2 acc = take_ext(r, 4);
+            for (u32 i = 0; i < nc; ++i) {
+                E2 coeff = ext ? take_ext(r, 6 + 2 * i) : E2(take_input(r, 6 + i));
+                acc = acc * alpha + coeff;
+                u32 at = i + 1 == nc ? 0 : start_accs + 2 * i;
+                rows[r].w[at] = acc.a;
+                rows[r].w[at + 1] = acc.b;
+            }
+            pool.push_back({rows[r].w[0], {r, 0}});
+            pool.push_back({rows[r].w[1], {r, 1}});
+        } else if (t == G_RANDOM_ACCESS) {
+            // 4 copies of a 16-way lookup (Merkle cap / coset selection) + 2 extra constants
+            u32 r = new_row(t);
+            for (u32 cpy = 0; cpy < 4; ++cpy) {
+                const u32 base = 18 * cpy;
+                u64 idx = rng.below(16);
+                rows[r].w[base] = idx;
+                for (u32 i = 0; i < 16; ++i) take_input(r, base + 2 + i);
+                rows[r].w[base + 1] = rows[r].w[base + 2 + idx];
+                pool.push_back({rows[r].w[base + 1], {r, base + 1}});
+                for (u32 i = 0; i < 4; ++i) rows[r].w[74 + 4 * cpy + i] = (idx >> i) & 1;
+            }
+            for (u32 k = 0; k < 2; ++k) {
+                u64 v = rng.below(2) ? rng.felt() : rng.below(256);
+                rows[r].consts[k] = v;
+                rows[r].w[72 + k] = v;
+                pool.push_back({v, {r, 72 + k}});
+            }
+        } else if (t == G_EXP) {
+            // base^(66 power bits), square-and-multiply with intermediate wires
+            u32 r = new_row(t);
+            u64 base = take_input(r, 0), cur = 1;
+            for (u32 i = 0; i < 66; ++i) rows[r].w[1 + i] = rng.below(2);
+            for (u32 i = 0; i < 66; ++i) {
+                u64 prev = i == 0 ? 1 : fsqr(cur);
+                cur = rows[r].w[1 + (65 - i)] ? fmul(prev, base) : prev;
+                rows[r].w[68 + i] = cur;
+            }
+            rows[r].w[67] = cur;
+            pool.push_back({cur, {r, 67}});
+            for (u32 k = 0; k < 2; ++k) { u32 b = (u32)rng.below(66); bools.push_back({rows[r].w[1 + b], {r, 1 + b}}); }
+        } else if (t == G_COSET) {
+            // barycentric interpolation of 16 F_{p^2} values over a coset shift * <w_16> at an F_{p^2} point (FRI fold check)
+            u32 r = new_row(t);
+            const Gate& g = c.gates[gate_index[G_COSET]];
+            u64 shift;
+            do shift = rng.felt(); while (shift == 0);
+            rows[r].w[0] = shift;
+            for (u32 i = 0; i < 32; ++i) take_input(r, 1 + i);
+            E2 point = take_ext(r, 33);
+            E2 sh = emul_base(point, finv(shift));
+            rows[r].w[45] = sh.a;
+            rows[r].w[46] = sh.b;
+            using A = Alg<BaseOps>;
+            A shifted{sh.a, sh.b}, eval = A::zero(), prod = A::one();
+            const u64* w = rows[r].w.data();
+            partial_interpolate<BaseOps>(g, w, 0, 6, shifted, eval, prod);
+            for (u32 i = 0; i < 2; ++i) {
+                rows[r].w[37 + 2 * i] = eval.a; rows[r].w[38 + 2 * i] = eval.b;
+                rows[r].w[41 + 2 * i] = prod.a; rows[r].w[42 + 2 * i] = prod.b;
+                partial_interpolate<BaseOps>(g, rows[r].w.data(), 6 + 5 * i, 11 + 5 * i, shifted, eval, prod);
+            }
+            rows[r].w[35] = eval.a;
+            rows[r].w[36] = eval.b;
+            pool.push_back({eval.a, {r, 35}});
+            pool.push_back({eval.b, {r, 36}});
+        } else if (t == G_MDS) {
+            // the Poseidon MDS layer applied to 12 F_{p^2} values (recursive Poseidon gate evaluation)
+            u32 r = new_row(t);
+            E2 in[12];
+            for (u32 i = 0; i < 12; ++i) in[i] = take_ext(r, 2 * i);
+            for (u32 k = 0; k < 12; ++k) {
+                E2 acc = emul_base(in[k], MDS_DIAG[k]);
+                for (u32 i = 0; i < 12; ++i) acc = acc + emul_base(in[(i + k) % 12], MDS_CIRC[i]);
+                rows[r].w[24 + 2 * k] = acc.a;
+                rows[r].w[25 + 2 * k] = acc.b;
+                pool.push_back({acc.a, {r, 24 + 2 * k}});
+                pool.push_back({acc.b, {r, 25 + 2 * k}});
             }
         } else if (t == G_POSEIDON) {
             u32 r = new_row(G_POSEIDON);
@@ -270,14 +427,14 @@ SynthCircuit make_synth_circuit(const SynthSpec& spec) {
 
     // wires, constants
     sc.wires.assign(135, std::vector<u64>(n));
-    sc.const_sigma_values.assign(84, std::vector<u64>(n));
+    sc.const_sigma_values.assign(nsel + 2 + 80, std::vector<u64>(n));
     for (size_t r = 0; r < n; ++r) {
         for (int j = 0; j < 135; ++j) sc.wires[j][r] = rows[r].w[j];
-        int g = rows[r].gate;
-        sc.const_sigma_values[0][r] = g < 5 ? (u64)g : UNUSED_SELECTOR;
-        sc.const_sigma_values[1][r] = g == 5 ? 5 : UNUSED_SELECTOR;
-        sc.const_sigma_values[2][r] = rows[r].consts[0];
-        sc.const_sigma_values[3][r] = rows[r].consts[1];
+        const int g = gate_index[rows[r].gate];
+        if (g < 0) throw std::runtime_error("row kind outside the circuit's gate set");
+        for (size_t k = 0; k < nsel; ++k) sc.const_sigma_values[k][r] = c.selector_indices[g] == k ? (u64)g : UNUSED_SELECTOR;
+        sc.const_sigma_values[nsel][r] = rows[r].consts[0];
+        sc.const_sigma_values[nsel + 1][r] = rows[r].consts[1];
     }
     // sigma from the copy-constraint classes (cycle through each class)
     std::vector<u32> parent(80 * n);
@@ -307,7 +464,7 @@ SynthCircuit make_synth_circuit(const SynthSpec& spec) {
     for (u32 col = 0; col < 80; ++col)
         for (size_t r = 0; r < n; ++r) {
             u32 t = sigma[col * n + r];
-            sc.const_sigma_values[4 + col][r] = fmul(c.k_is[t / n], subgroup[t % n]);
+            sc.const_sigma_values[nsel + 2 + col][r] = fmul(c.k_is[t / n], subgroup[t % n]);
         }
     return sc;
 }
@@ -318,11 +475,13 @@ std::string check_witness(const SynthCircuit& sc) {
     Digest pi_hash = hash_no_pad(sc.public_inputs);
     std::vector<u64> out, w(135);
     for (size_t r = 0; r < n; ++r) {
-        u64 s0 = sc.const_sigma_values[0][r], s1 = sc.const_sigma_values[1][r];
-        size_t g = s0 != UNUSED_SELECTOR ? s0 : s1;
+        const size_t nsel = c.num_selectors();
+        size_t g = c.gates.size();
+        for (size_t k = 0; k < nsel; ++k)
+            if (sc.const_sigma_values[k][r] != UNUSED_SELECTOR) g = sc.const_sigma_values[k][r];
         if (g >= c.gates.size()) return "bad selector at row " + std::to_string(r);
         for (int j = 0; j < 135; ++j) w[j] = sc.wires[j][r];
-        u64 consts[2] = {sc.const_sigma_values[2][r], sc.const_sigma_values[3][r]};
+        u64 consts[2] = {sc.const_sigma_values[nsel][r], sc.const_sigma_values[nsel + 1][r]};
         eval_gate_unfiltered<BaseOps>(c.gates[g], consts, w.data(), pi_hash, out);
         for (size_t k = 0; k < out.size(); ++k)
             if (out[k] != 0) return "gate constraint " + std::to_string(k) + " fails at row " + std::to_string(r);
@@ -337,7 +496,7 @@ std::string check_witness(const SynthCircuit& sc) {
     for (size_t r = 0; r < n; ++r)
         for (size_t j = 0; j < 80; ++j) {
             num = fmul(num, fadd(fadd(sc.wires[j][r], fmul(beta, fmul(c.k_is[j], subgroup[r]))), gamma));
-            den = fmul(den, fadd(fadd(sc.wires[j][r], fmul(beta, sc.const_sigma_values[4 + j][r])), gamma));
+            den = fmul(den, fadd(fadd(sc.wires[j][r], fmul(beta, sc.const_sigma_values[c.num_constants + j][r])), gamma));
         }
     if (num != den) return "permutation grand product does not telescope";
     return "";

@@ -233,11 +233,29 @@ class Synth:
     VOTING = dict(n_poseidon=34, n_base_sum=33, n_arith=120, n_const=12, num_public_inputs=13)
     TINY = dict(n_poseidon=6, n_base_sum=5, n_arith=6, n_const=3, num_public_inputs=5)
 
+    # recursion-shaped: rows of ArithmeticExtension, MulExtension, Reducing, ReducingExtension, RandomAccess,
+    # Exponentiation, CosetInterpolation, PoseidonMds on top of the base counts
+    RECURSION_KEYS = ("n_arith_ext", "n_mul_ext", "n_reducing", "n_reducing_ext", "n_random_access", "n_exp", "n_coset", "n_mds")
+    RECURSION = dict(n_poseidon=1900, n_base_sum=260, n_arith=600, n_const=60, num_public_inputs=16, n_arith_ext=900,
+                     n_mul_ext=160, n_reducing=120, n_reducing_ext=120, n_random_access=230, n_exp=60, n_coset=112, n_mds=8)
+    RECURSION_TINY = dict(n_poseidon=5, n_base_sum=3, n_arith=4, n_const=3, num_public_inputs=5, n_arith_ext=4, n_mul_ext=3,
+                          n_reducing=3, n_reducing_ext=3, n_random_access=3, n_exp=3, n_coset=3, n_mds=2)
+
     def __init__(self, zk=False, seed=1, min_degree_bits=0, n_poseidon=488, n_base_sum=3800, n_arith=2520, n_const=100,
-                 num_public_inputs=16):
+                 num_public_inputs=16, **recursion):
         L = lib()
-        L.orc_synth_make.argtypes = [ctypes.c_uint, ctypes.c_int] + [ctypes.c_size_t] * 5 + [ctypes.c_uint64]
-        self._h = L.orc_synth_make(min_degree_bits, int(zk), n_poseidon, n_base_sum, n_arith, n_const, num_public_inputs, seed)
+        if recursion:
+            unknown = set(recursion) - set(self.RECURSION_KEYS)
+            if unknown or zk:
+                raise ValueError(f"bad recursion spec {unknown} (recursion circuits are not zero-knowledge)")
+            counts = (ctypes.c_size_t * 8)(*[int(recursion.get(k, 0)) for k in self.RECURSION_KEYS])
+            L.orc_synth_make_recursion.restype = ctypes.c_void_p
+            L.orc_synth_make_recursion.argtypes = [ctypes.c_uint] + [ctypes.c_size_t] * 5 + [ctypes.c_uint64, ctypes.c_void_p]
+            self._h = L.orc_synth_make_recursion(min_degree_bits, n_poseidon, n_base_sum, n_arith, n_const, num_public_inputs, seed,
+                                                 ctypes.cast(counts, ctypes.c_void_p))
+        else:
+            L.orc_synth_make.argtypes = [ctypes.c_uint, ctypes.c_int] + [ctypes.c_size_t] * 5 + [ctypes.c_uint64]
+            self._h = L.orc_synth_make(min_degree_bits, int(zk), n_poseidon, n_base_sum, n_arith, n_const, num_public_inputs, seed)
         if not self._h:
             raise RuntimeError(_err())
         h = ctypes.c_void_p(self._h)

@@ -88,10 +88,14 @@ struct SynthSpec {
     size_t n_poseidon = 488, n_base_sum = 3800, n_arith = 2520, n_const = 100;
     size_t num_public_inputs = 16;
     u64 seed = 1;
+    // rows of the recursion gate set; any non-zero count switches the circuit to the 14-gate set that
+    // `verify_proof` (aggregator/src/circuits/tree.rs:119) instantiates, with 4 selector groups
+    size_t n_arith_ext = 0, n_mul_ext = 0, n_reducing = 0, n_reducing_ext = 0, n_random_access = 0, n_exp = 0, n_coset = 0,
+           n_mds = 0;
 };
 struct SynthCircuit {
     CommonData common;
-    std::vector<std::vector<u64>> const_sigma_values;  // [4+80][n]
+    std::vector<std::vector<u64>> const_sigma_values;  // [num_constants + 80][n] (selectors, 2 gate constants, sigmas)
     std::vector<std::vector<u64>> wires;               // [135][n]
     std::vector<u64> public_inputs;
 };

@@ -76,9 +76,21 @@ ZKB_HD void mul128(u64 a, u64 b, u64& lo, u64& hi) {
 // ---- device fast paths: 32-bit limbs, carry flags through add.cc/addc (IADD3/IADD3.X/IMAD.X in SASS), no
 // compare+select sequences. The limb algorithms were checked exhaustively on edge values on the host. ----
 
+// 64-bit <-> 2 x 32-bit through mov.b64: a C-level (u32)(v >> 32) makes ptxas emit a stray "VIADD hi, hi, 0" per use
+__device__ __forceinline__ void gl_unpack(u64 v, u32& lo, u32& hi) { asm("mov.b64 {%0, %1}, %2;" : "=r"(lo), "=r"(hi) : "l"(v)); }
+__device__ __forceinline__ u64 gl_pack(u32 lo, u32 hi) { u64 v; asm("mov.b64 %0, {%1, %2};" : "=l"(v) : "r"(lo), "r"(hi)); return v; }
+__device__ __forceinline__ void gl_wide(u32 a, u32 b, u32& lo, u32& hi) {
+    u64 v;
+    asm("mul.wide.u32 %0, %1, %2;" : "=l"(v) : "r"(a), "r"(b));
+    gl_unpack(v, lo, hi);
+}
 // (a1:a0) * (b1:b0) -> 128-bit product limbs r0..r3: 4 x IMAD.WIDE.U32 + two 3-limb carry chains
 __device__ __forceinline__ void gl_mul128_limbs(u32 a0, u32 a1, u32 b0, u32 b1, u32& r0, u32& r1, u32& r2, u32& r3) {
-    u64 p00 = (u64)a0 * b0, p01 = (u64)a0 * b1, p10 = (u64)a1 * b0, p11 = (u64)a1 * b1;
+    u32 p00h, p01l, p01h, p10l, p10h, p11l, p11h;
+    gl_wide(a0, b0, r0, p00h);
+    gl_wide(a0, b1, p01l, p01h);
+    gl_wide(a1, b0, p10l, p10h);
+    gl_wide(a1, b1, p11l, p11h);
     asm("{\n\t"
         "add.cc.u32 %0, %3, %4;\n\t"        // r1 = p00.hi + p01.lo
         "addc.cc.u32 %1, %5, %7;\n\t"       // r2 = p01.hi + p10.hi + c
@@ -87,16 +99,16 @@ __device__ __forceinline__ void gl_mul128_limbs(u32 a0, u32 a1, u32 b0, u32 b1, 
         "addc.cc.u32 %1, %1, %8;\n\t"       // r2 += p11.lo + c
         "addc.u32 %2, %2, 0;\n\t"
         "}" : "=&r"(r1), "=&r"(r2), "=&r"(r3)
-            : "r"((u32)(p00 >> 32)), "r"((u32)p01), "r"((u32)(p01 >> 32)), "r"((u32)p10), "r"((u32)(p10 >> 32)),
-              "r"((u32)p11), "r"((u32)(p11 >> 32)));
-    r0 = (u32)p00;
+            : "r"(p00h), "r"(p01l), "r"(p01h), "r"(p10l), "r"(p10h), "r"(p11l), "r"(p11h));
 }
 // T = (r1:r0) + r2*(2^32-1) - r3 lies in (-2^32, 2^65): result = (T mod 2^64) + EPS*[T >= 2^64] - EPS*[T < 0],
 // which needs exactly one correction and cannot wrap again. r2*EPS + r0 is one IMAD.WIDE
 // (cannot overflow), so the fold costs 1 FMA-pipe + 10 ALU-pipe instructions.
 __device__ __forceinline__ u64 gl_reduce_limbs(u32 r0, u32 r1, u32 r2, u32 r3) {
-    u64 A = (u64)r2 * 0xFFFFFFFFu + r0;
-    u32 o0, o1;
+    u64 A;
+    asm("mad.wide.u32 %0, %1, 0xffffffff, %2;" : "=l"(A) : "r"(r2), "l"(gl_pack(r0, 0)));
+    u32 A0, A1, o0, o1;
+    gl_unpack(A, A0, A1);
     asm("{\n\t"
         ".reg .u32 mb, mc;\n\t"
         "add.cc.u32 %1, %3, %4;\n\t"        // high limb + r1 -> carry
@@ -109,8 +121,8 @@ __device__ __forceinline__ u64 gl_reduce_limbs(u32 r0, u32 r1, u32 r2, u32 r3) {
         "addc.u32 %1, %1, 0;\n\t"
         "sub.cc.u32 %0, %0, mb;\n\t"        // - EPS on borrow
         "subc.u32 %1, %1, 0;\n\t"
-        "}" : "=&r"(o0), "=&r"(o1) : "r"((u32)A), "r"((u32)(A >> 32)), "r"(r1), "r"(r3));
-    return ((u64)o1 << 32) | o0;
+        "}" : "=&r"(o0), "=&r"(o1) : "r"(A0), "r"(A1), "r"(r1), "r"(r3));
+    return gl_pack(o0, o1);
 }
 #endif
 
@@ -143,9 +155,11 @@ ZKB_HD u64 gl_mul_lazy(u64 a, u64 b) {
 // squaring: 3 wide multiplies (the cross product once, doubled with shifts) instead of 4
 ZKB_HD u64 gl_sqr_lazy(u64 a) {
 #if defined(__CUDA_ARCH__)
-    const u32 a0 = (u32)a, a1 = (u32)(a >> 32);
-    const u64 p00 = (u64)a0 * a0, m = (u64)a0 * a1, p11 = (u64)a1 * a1;
-    const u32 m0 = (u32)m, m1 = (u32)(m >> 32);
+    u32 a0, a1, p00l, p00h, m0, m1, p11l, p11h;
+    gl_unpack(a, a0, a1);
+    gl_wide(a0, a0, p00l, p00h);
+    gl_wide(a0, a1, m0, m1);
+    gl_wide(a1, a1, p11l, p11h);
     const u32 d0 = m0 << 1, d1 = __funnelshift_l(m0, m1, 1), d2 = m1 >> 31;      // 2m as three limbs
     u32 r1, r2, r3;
     asm("{\n\t"
@@ -153,8 +167,8 @@ ZKB_HD u64 gl_sqr_lazy(u64 a) {
         "addc.cc.u32 %1, %5, %6;\n\t"       // r2 = p11.lo + d1 + c
         "addc.u32 %2, %7, %8;\n\t"          // r3 = p11.hi + d2 + c   (cannot overflow: a^2 < 2^128)
         "}" : "=&r"(r1), "=&r"(r2), "=&r"(r3)
-            : "r"((u32)(p00 >> 32)), "r"(d0), "r"((u32)p11), "r"(d1), "r"((u32)(p11 >> 32)), "r"(d2));
-    return gl_reduce_limbs((u32)p00, r1, r2, r3);
+            : "r"(p00h), "r"(d0), "r"(p11l), "r"(d1), "r"(p11h), "r"(d2));
+    return gl_reduce_limbs(p00l, r1, r2, r3);
 #else
     return gl_mul_lazy(a, a);
 #endif

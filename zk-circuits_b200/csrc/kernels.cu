@@ -6,6 +6,7 @@
 #include <map>
 #include <tuple>
 #include <atomic>
+#include <cstdlib>
 #include <mutex>
 #include <stdexcept>
 #include <string>
@@ -348,13 +349,29 @@ static LargePlan large_plan(unsigned lg_n) {
     return p;
 }
 static void ntt_set_func_attributes() {   // per device: opt in to > 48 KB dynamic shared memory
-    ZKB_CUDA_CHECK(cudaFuncSetAttribute(lde_block_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ntt_smem_bytes(NTT_SM_LG)));
+    ZKB_CUDA_CHECK(cudaFuncSetAttribute(lde_block_kernel_t<4, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ntt_smem_bytes(NTT_SM_LG)));
+    ZKB_CUDA_CHECK(cudaFuncSetAttribute(lde_block_kernel_t<3, 1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ntt_smem_bytes(NTT_SM_LG)));
     ZKB_CUDA_CHECK(cudaFuncSetAttribute(intt_block_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ntt_smem_bytes(NTT_SM_LG)));
     ZKB_CUDA_CHECK(cudaFuncSetAttribute(ntt_cols_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ntt_smem_bytes(NTT_SM_LG)));
 }
 static unsigned ntt_block_threads(unsigned lg_n) {
     unsigned t = lg_n >= 4 ? (1u << (lg_n - 4)) : 1u;
     return t < 32 ? 32 : (t > 512 ? 512 : t);
+}
+// EXPERIMENT switch: ZKB_NTT_RADIX8=1 runs full-size (n >= 2^13) blocks with radix-8 passes and 1024 threads
+static bool ntt_radix8() {
+    static const bool on = [] { const char* e = std::getenv("ZKB_NTT_RADIX8"); return e && e[0] == '1'; }();
+    return on;
+}
+static void launch_lde_block(dim3 grid, unsigned lg_n, cudaStream_t st, const u64* coeffs, size_t coeff_stride, u64* out,
+                             size_t out_stride, const u64* prescale, size_t src_block_stride, int inv, unsigned jb0) {
+    ZKB_COUNT_LAUNCH();
+    if (lg_n >= 13 && ntt_radix8())
+        lde_block_kernel_t<3, 1024><<<grid, 1024, ntt_smem_bytes(lg_n), st>>>(coeffs, coeff_stride, out, out_stride, lg_n, prescale,
+                                                                             src_block_stride, inv, jb0);
+    else
+        lde_block_kernel_t<4, 512><<<grid, ntt_block_threads(lg_n), ntt_smem_bytes(lg_n), st>>>(coeffs, coeff_stride, out, out_stride,
+                                                                                               lg_n, prescale, src_block_stride, inv, jb0);
 }
 // Coset pre-scale tables (shift * w_N^j)^k, cached per device for the lifetime of the process. n <= 2^14: one table
 // [2^rate][n] (1 MB for the wormhole circuit). Larger n: the exponent is split k = r * n2 + b, tables [2^rate][n1], [2^rate][n2].
@@ -404,9 +421,7 @@ static void run_large_transform(const u64* src, size_t src_stride, u64* dst, siz
     ZKB_COUNT_LAUNCH();
     ntt_cols_kernel<<<g1, 256, ntt_smem_bytes(p.lg_n1 + p.lg_tb), st>>>(a);
     dim3 g2(nblk << p.lg_n1, (unsigned)ncols);
-    ZKB_COUNT_LAUNCH();
-    lde_block_kernel<<<g2, ntt_block_threads(p.lb), ntt_smem_bytes(p.lb), st>>>(dst, dst_stride, dst, dst_stride, p.lb, nullptr,
-                                                                                size_t(1) << p.lb, inv ? 1 : 0, 0);
+    launch_lde_block(g2, p.lb, st, dst, dst_stride, dst, dst_stride, nullptr, size_t(1) << p.lb, inv ? 1 : 0, 0);
 }
 
 // in-place bit-reversal permutation with scaling
@@ -455,8 +470,7 @@ void launch_lde_blocks(const u64* coeffs, size_t coeff_stride, u64* out, size_t 
     if (!plain) t = coset_tables(lg_n, rate_bits, shift, st);
     if (lg_n <= NTT_SM_LG) {
         dim3 grid(blk_hi - blk_lo, (unsigned)ncols);
-        ZKB_COUNT_LAUNCH();
-        lde_block_kernel<<<grid, ntt_block_threads(lg_n), ntt_smem_bytes(lg_n), st>>>(coeffs, coeff_stride, out, out_stride, lg_n, t.full, 0, 0, blk_lo);
+        launch_lde_block(grid, lg_n, st, coeffs, coeff_stride, out, out_stride, t.full, 0, 0, blk_lo);
         return;
     }
     run_large_transform(coeffs, coeff_stride, out, out_stride, ncols, lg_n, blk_hi - blk_lo, t.pre1, t.pre2, false, st, blk_lo);

@@ -76,12 +76,15 @@ ZKB_D void ntt_dif_pass(u64* sm, unsigned L, unsigned s, unsigned lgC, bool inv)
     }
 }
 // transform in place (forward, or inverse without the 1/n): natural order in, bit-reversed rows out
-// (sm[pad(i * 2^lgC + c)] = X_c[bitrev(i)]). Ends with a barrier.
+// (sm[pad(i * 2^lgC + c)] = X_c[bitrev(i)]). Ends with a barrier. KMAX = 4: radix-16 passes (16 elements + 15 twiddles in
+// registers: 128 registers, 512 threads); KMAX = 3: radix-8 passes (one more shared-memory round trip, the same number of
+// multiplies, 64 registers so that 1024 threads = 32 warps share the column).
+template <int KMAX = 4>
 ZKB_D void ntt_dif_smem(u64* sm, unsigned L, unsigned lgC = 0, bool inv = false) {
     unsigned s = L;
-    while (s >= lgC + 4) { ntt_dif_pass<4>(sm, L, s, lgC, inv); s -= 4; __syncthreads(); }
+    while (s >= lgC + KMAX) { ntt_dif_pass<KMAX>(sm, L, s, lgC, inv); s -= KMAX; __syncthreads(); }
     const unsigned rem = s - lgC;
-    if (rem == 3) ntt_dif_pass<3>(sm, L, s, lgC, inv);
+    if (KMAX > 3 && rem == 3) ntt_dif_pass<3>(sm, L, s, lgC, inv);
     else if (rem == 2) ntt_dif_pass<2>(sm, L, s, lgC, inv);
     else if (rem == 1) ntt_dif_pass<1>(sm, L, s, lgC, inv);
     if (rem) __syncthreads();
@@ -91,27 +94,29 @@ ZKB_D void ntt_dif_smem(u64* sm, unsigned L, unsigned lgC = 0, bool inv = false)
 // prescale: [2^rate_bits][n] table of (shift w_N^j)^k, or null for the plain transform (shift 1, rate 0)
 // src_block_stride = 0: every block jb transforms the same n coefficients (LDE); = n: block jb transforms its own
 // contiguous run (second step of the two-step transform for n > 2^14; coeffs may alias out). inv: inverse twiddles.
-__global__ void __launch_bounds__(512) lde_block_kernel(const u64* coeffs, size_t coeff_stride, u64* out,
-                                                        size_t out_stride, unsigned lg_n, const u64* __restrict__ prescale,
-                                                        size_t src_block_stride, int inv, unsigned jb0) {
+template <int KMAX, int THREADS>
+__global__ void __launch_bounds__(THREADS) lde_block_kernel_t(const u64* coeffs, size_t coeff_stride, u64* out,
+                                                              size_t out_stride, unsigned lg_n, const u64* __restrict__ prescale,
+                                                              size_t src_block_stride, int inv, unsigned jb0) {
     extern __shared__ u64 sm[];
     const unsigned n = 1u << lg_n, jb = blockIdx.x;       // jb: destination block; jb0 + jb: coset (pre-scale table row)
     const u64* src = coeffs + (size_t)blockIdx.y * coeff_stride + (size_t)jb * src_block_stride;
     const u64* ps = prescale ? prescale + (size_t)(jb0 + jb) * n : nullptr;
-    // n is a multiple of 8 * blockDim whenever n >= 4096 (512 threads): 8 independent loads in flight per thread
-    if ((n & (8 * blockDim.x - 1)) == 0) {
-        for (unsigned i0 = threadIdx.x; i0 < n; i0 += 8 * blockDim.x) {
-            u64 v[8], w[8];
+    // n is a multiple of U * blockDim for the large sizes: U independent loads in flight per thread
+    constexpr int U = KMAX == 4 ? 8 : 4;
+    if ((n & (U * blockDim.x - 1)) == 0) {
+        for (unsigned i0 = threadIdx.x; i0 < n; i0 += U * blockDim.x) {
+            u64 v[U], w[U];
 #pragma unroll
-            for (int u = 0; u < 8; ++u) v[u] = src[i0 + u * blockDim.x];
+            for (int u = 0; u < U; ++u) v[u] = src[i0 + u * blockDim.x];
             if (ps) {
 #pragma unroll
-                for (int u = 0; u < 8; ++u) w[u] = __ldg(ps + i0 + u * blockDim.x);
+                for (int u = 0; u < U; ++u) w[u] = __ldg(ps + i0 + u * blockDim.x);
 #pragma unroll
-                for (int u = 0; u < 8; ++u) v[u] = f_mul(v[u], w[u]);
+                for (int u = 0; u < U; ++u) v[u] = f_mul(v[u], w[u]);
             }
 #pragma unroll
-            for (int u = 0; u < 8; ++u) sm[ntt_pad(i0 + u * blockDim.x)] = v[u];
+            for (int u = 0; u < U; ++u) sm[ntt_pad(i0 + u * blockDim.x)] = v[u];
         }
     } else {
         for (unsigned i = threadIdx.x; i < n; i += blockDim.x) {
@@ -121,7 +126,7 @@ __global__ void __launch_bounds__(512) lde_block_kernel(const u64* coeffs, size_
         }
     }
     __syncthreads();
-    ntt_dif_smem(sm, lg_n, 0, inv != 0);
+    ntt_dif_smem<KMAX>(sm, lg_n, 0, inv != 0);
     u64* dst = out + (size_t)blockIdx.y * out_stride + (size_t)jb * n;
 #pragma unroll 8
     for (unsigned i = threadIdx.x; i < n; i += blockDim.x) dst[i] = sm[ntt_pad(i)];

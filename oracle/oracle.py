@@ -236,7 +236,7 @@ class Synth:
     # recursion-shaped: rows of ArithmeticExtension, MulExtension, Reducing, ReducingExtension, RandomAccess,
     # Exponentiation, CosetInterpolation, PoseidonMds on top of the base counts
     RECURSION_KEYS = ("n_arith_ext", "n_mul_ext", "n_reducing", "n_reducing_ext", "n_random_access", "n_exp", "n_coset", "n_mds")
-    RECURSION = dict(n_poseidon=1900, n_base_sum=260, n_arith=600, n_const=60, num_public_inputs=16, n_arith_ext=900,
+    RECURSION = dict(n_poseidon=1600, n_base_sum=260, n_arith=500, n_const=60, num_public_inputs=16, n_arith_ext=800,
                      n_mul_ext=160, n_reducing=120, n_reducing_ext=120, n_random_access=230, n_exp=60, n_coset=112, n_mds=8)
     RECURSION_TINY = dict(n_poseidon=5, n_base_sum=3, n_arith=4, n_const=3, num_public_inputs=5, n_arith_ext=4, n_mul_ext=3,
                           n_reducing=3, n_reducing_ext=3, n_random_access=3, n_exp=3, n_coset=3, n_mds=2)

@@ -16,8 +16,8 @@ def zkb():
     return zkb200
 
 
-def run_case(zkb, oracle, spec, zk, seed, salt_seed=77):
-    s = oracle.Synth(zk=zk, seed=seed, **spec)
+def run_case(zkb, oracle, spec, zk, seed, salt_seed=77, min_degree_bits=0):
+    s = oracle.Synth(zk=zk, seed=seed, min_degree_bits=min_degree_bits, **spec)
     oc = oracle.Circuit(s.common, s.const_sigma_values)
     gc = zkb.ProverCircuit(s.common, s.const_sigma_values, is_values=True, circuit_digest=oc.digest)
     want = oc.prove(s.wires, s.public_inputs, salt_seed=salt_seed)
@@ -39,6 +39,26 @@ def test_tiny_circuit_proof_bytes(zkb, oracle, zk):
 
 def test_voting_shaped_proof_bytes(zkb, oracle):
     run_case(zkb, oracle, oracle.Synth.VOTING, False, seed=2)
+
+
+def test_recursion_gate_set_proof_bytes(zkb, oracle):
+    """Config #4/#5 gate set (the 14 gates of a recursive-verifier circuit, 4 selector groups): the CUDA
+    quotient's third launch evaluates ArithmeticExtension, MulExtension, Reducing(Extension), RandomAccess, Exponentiation,
+    CosetInterpolation and PoseidonMds; proof bytes equal the oracle's. (These gates are unpinned against qp-plonky2 —
+    oracle/gates.hpp — so this is GPU-vs-oracle parity plus acceptance by the restated verifier.)"""
+    s, oc, gc, proof = run_case(zkb, oracle, oracle.Synth.RECURSION_TINY, False, seed=3)
+    assert s.info["num_gates"] == 14
+    # a tampered wire of a recursion gate gives the same (unverifiable) bytes on both sides
+    w = s.wires.copy()
+    w[70, int(np.nonzero(s.const_sigma_values[0] == 5)[0][0])] ^= np.uint64(1)      # ReducingExtension accumulator
+    bad = gc.prove(w, s.public_inputs, salt_seed=77)
+    assert bad == oc.prove(w, s.public_inputs, salt_seed=77) and oc.verify(bad) != ""
+
+
+def test_recursion_shaped_circuit_proof_bytes(zkb, oracle):
+    """A recursion-shaped circuit at the size class of one aggregation chunk (n = 2^12, non-zk)."""
+    s, oc, gc, proof = run_case(zkb, oracle, oracle.Synth.RECURSION, False, seed=4)
+    assert s.info["degree_bits"] == 12 and len(proof) == gc.proof_size
 
 
 def test_explicit_salts(zkb, oracle):

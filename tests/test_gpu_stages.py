@@ -157,6 +157,19 @@ def test_partial_products_and_quotient_match_oracle(zkb, oracle, tiny):
     assert np.array_equal(q, tr.quotient_chunks)
 
 
+def test_recursion_gate_quotient_matches_oracle(zkb, oracle):
+    """compute_quotient_polys over the recursion gate set: every quotient chunk bit-exact against the oracle."""
+    s = oracle.Synth(seed=9, n_poseidon=20, n_base_sum=6, n_arith=10, n_const=4, num_public_inputs=7, n_arith_ext=20, n_mul_ext=8,
+                     n_reducing=6, n_reducing_ext=6, n_random_access=9, n_exp=5, n_coset=7, n_mds=3)
+    oc = oracle.Circuit(s.common, s.const_sigma_values)
+    gc = zkb.ProverCircuit(s.common, s.const_sigma_values, is_values=True, circuit_digest=oc.digest)
+    _, tr = oc.prove(s.wires, s.public_inputs, trace=True)
+    zs = gc.partial_products(s.wires, tr.betas, tr.gammas, 20, s.n)
+    assert np.array_equal(zs, tr.zs_pp_values)
+    q = gc.quotient(s.wires, zs, s.public_inputs, tr.betas, tr.gammas, tr.alphas, 16, s.n)
+    assert np.array_equal(q, tr.quotient_chunks)
+
+
 @pytest.mark.parametrize("lg_n,ncols", [(9, 7), (14, 3), (16, 2)])
 def test_coset_sharded_commit_parts_concatenate_to_the_full_cap(zkb, oracle, lg_n, ncols):
     """zkb_commit_cosets (one GPU's share of a coset-sharded commitment) for G = 1, 2, 4, 8 emulated ranks on one GPU:

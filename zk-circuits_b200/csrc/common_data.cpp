@@ -72,10 +72,21 @@ CommonData parse_common_data(const uint8_t* p, size_t len) {
     if (num_lookup_polys || num_lookup_selectors || num_luts) throw UnsupportedError("lookup tables are not supported");
     u64 ngates = c.count(4);
     for (u64 i = 0; i < ngates; ++i) {
-        GateInfo g{c.le32(), 0};
+        GateInfo g;
+        g.tag = c.le32();
         switch (g.tag) {
-            case GT_NOOP: case GT_PUBLIC_INPUT: case GT_POSEIDON: break;
-            case GT_CONSTANT: case GT_BASE_SUM: case GT_ARITHMETIC: g.param = c.le64(); break;
+            case GT_NOOP: case GT_PUBLIC_INPUT: case GT_POSEIDON: case GT_POSEIDON_MDS: break;
+            case GT_CONSTANT: case GT_BASE_SUM: case GT_ARITHMETIC: case GT_ARITHMETIC_EXT: case GT_MUL_EXT: case GT_REDUCING:
+            case GT_REDUCING_EXT: case GT_EXPONENTIATION: g.param = c.le64(); break;
+            case GT_RANDOM_ACCESS: g.param = c.le64(); g.p2 = c.le64(); g.p3 = c.le64(); break;
+            case GT_COSET_INTERP: {
+                g.param = c.le64(); g.p2 = c.le64();
+                g.weights = c.vec64();
+                if (g.param == 0 || g.param > 4) throw UnsupportedError("CosetInterpolationGate: subgroup_bits must be 1..4");
+                if (g.p2 < 2 || g.weights.size() != (size_t(1) << g.param)) throw ParseError("CosetInterpolationGate: bad degree / weights");
+                for (u64 w : g.weights) if (w >= GL_P) throw ParseError("CosetInterpolationGate: non-canonical weight");
+                break;
+            }
             default: throw UnsupportedError("gate tag " + std::to_string(g.tag) + " is outside the implemented gate set");
         }
         d.gates.push_back(g);
@@ -105,13 +116,18 @@ CommonData parse_common_data(const uint8_t* p, size_t len) {
         size_t nc = g.num_constraints();
         maxc = nc > maxc ? nc : maxc;
         totc += nc;
-        if (g.tag == GT_POSEIDON && d.num_wires < 135) throw ParseError("Poseidon gate needs 135 wires");
-        if (g.tag == GT_BASE_SUM && 1 + g.param > d.num_wires) throw ParseError("BaseSum gate exceeds wires");
-        if (g.tag == GT_ARITHMETIC && 4 * g.param > d.num_wires) throw ParseError("Arithmetic gate exceeds wires");
-        if (g.tag == GT_CONSTANT && g.param + d.groups.size() > d.num_constants) throw ParseError("Constant gate exceeds constants");
-        if (g.tag == GT_ARITHMETIC && 2 + d.groups.size() > d.num_constants) throw ParseError("Arithmetic gate exceeds constants");
+        if (g.param > 4096 || g.p2 > 4096 || g.p3 > 4096) throw ParseError("gate parameter out of range");
+        if (g.num_wires() > d.num_wires) throw ParseError("gate tag " + std::to_string(g.tag) + " needs more wires than the circuit has");
+        if (g.num_constants() + d.groups.size() > d.num_constants)
+            throw ParseError("gate tag " + std::to_string(g.tag) + " needs more constants than the circuit has");
+        if (g.tag == GT_RANDOM_ACCESS && (g.param == 0 || g.param > 5)) throw UnsupportedError("RandomAccessGate: bits must be 1..5");
+        if ((g.tag == GT_REDUCING || g.tag == GT_REDUCING_EXT || g.tag == GT_EXPONENTIATION) && g.param == 0)
+            throw ParseError("gate with zero coefficients / power bits");
     }
     (void)totc;
+    size_t ncoset = 0;
+    for (auto& g : d.gates) ncoset += g.tag == GT_COSET_INTERP;
+    if (ncoset > 1) throw UnsupportedError("more than one CosetInterpolationGate parameter set");
     if (maxc != d.num_gate_constraints) throw ParseError("num_gate_constraints inconsistent with the gate list");
     return d;
 }

@@ -358,9 +358,11 @@ static unsigned ntt_block_threads(unsigned lg_n) {
     unsigned t = lg_n >= 4 ? (1u << (lg_n - 4)) : 1u;
     return t < 32 ? 32 : (t > 512 ? 512 : t);
 }
-// EXPERIMENT switch: ZKB_NTT_RADIX8=1 runs full-size (n >= 2^13) blocks with radix-8 passes and 1024 threads
+// Blocks of n >= 2^13 run radix-8 passes with 1024 threads (64 registers, 32 warps per SM) — measured 5 % faster than
+// radix-16 passes with 512 threads (128 registers) on the 135-column wormhole batch (profiles/r01_bench_v6_ntt_variants.json:
+// 0.368 vs 0.389 ms); ZKB_NTT_RADIX8=0 selects the radix-16 form.
 static bool ntt_radix8() {
-    static const bool on = [] { const char* e = std::getenv("ZKB_NTT_RADIX8"); return e && e[0] == '1'; }();
+    static const bool on = [] { const char* e = std::getenv("ZKB_NTT_RADIX8"); return !(e && e[0] == '0'); }();
     return on;
 }
 static void launch_lde_block(dim3 grid, unsigned lg_n, cudaStream_t st, const u64* coeffs, size_t coeff_stride, u64* out,
@@ -647,6 +649,23 @@ void launch_partial_products(const u64* wires, size_t wire_stride, const u64* si
 // the circuit's gate list (warp-uniform dispatch). Gate formulas: SURVEY App. C.1.
 // ---------------------------------------------------------------------------------------------
 constexpr u32 TAG_ARITHMETIC = 0, TAG_BASE_SUM = 2, TAG_CONSTANT = 3, TAG_NOOP = 9, TAG_POSEIDON = 11, TAG_PUBLIC_INPUT = 12;
+// recursion gate set, evaluated by the third launch
+constexpr u32 TAG_ARITHMETIC_EXT = 1, TAG_COSET_INTERP = 4, TAG_EXPONENTIATION = 5, TAG_MUL_EXT = 8, TAG_POSEIDON_MDS = 10,
+              TAG_RANDOM_ACCESS = 13, TAG_REDUCING_EXT = 14, TAG_REDUCING = 15;
+__host__ __device__ constexpr bool tag_is_recursion(u32 t) {
+    return t == TAG_ARITHMETIC_EXT || t == TAG_COSET_INTERP || t == TAG_EXPONENTIATION || t == TAG_MUL_EXT || t == TAG_POSEIDON_MDS ||
+           t == TAG_RANDOM_ACCESS || t == TAG_REDUCING_EXT || t == TAG_REDUCING;
+}
+// F_{p^2} = F_p[X] / (X^2 - 7) on canonical components: in the prover's base-field evaluation a gate's "extension algebra"
+// wires (pairs of columns) are plain F_{p^2} elements
+struct QE { u64 a, b; };
+ZKB_D QE qe_add(QE x, QE y) { return QE{f_add(x.a, y.a), f_add(x.b, y.b)}; }
+ZKB_D QE qe_sub(QE x, QE y) { return QE{f_sub(x.a, y.a), f_sub(x.b, y.b)}; }
+ZKB_D QE qe_scale(QE x, u64 s) { return QE{f_mul(x.a, s), f_mul(x.b, s)}; }
+__device__ __noinline__ QE qe_mul(QE x, QE y) {
+    const u64 bb = f_mul(x.b, y.b);
+    return QE{f_add(f_mul(x.a, y.a), f_mul(bb, GL_W)), f_add(f_mul(x.a, y.b), f_mul(x.b, y.a))};
+}
 
 struct QuotientArgs {
     const QuotientParams* p;
@@ -666,11 +685,12 @@ __device__ __noinline__ ulonglong2 q_acc2(ulonglong2 g, u64 c, u64 p0, u64 p1) {
     return g;
 }
 __device__ __noinline__ u64 q_sbox7(u64 x) { return gl_sbox7(x); }
-// The work of a point is split over two launches so that each has a small register and code footprint:
-// PART 1 = L0 term + permutation checks + every gate except Poseidon (stores the raw sums), PART 2 = Poseidon gates
-// (adds its sums and divides by Z_H). The constraint-to-alpha-power mapping is the same in both.
+// The work of a point is split over launches so that each has a small register and code footprint:
+// PART 1 = L0 term + permutation checks + the simple gates (stores the raw sums), PART 3 = the recursion gate set (adds its
+// sums; launched only for circuits that have such gates), PART 2 = Poseidon gates (adds its sums and divides by Z_H).
+// The constraint-to-alpha-power mapping is the same in all of them.
 template <int PART>
-__global__ void __launch_bounds__(128, 8) quotient_kernel(QuotientArgs a) {
+__global__ void __launch_bounds__(128, PART == 3 ? 4 : 8) quotient_kernel(QuotientArgs a) {
     const QuotientParams& P = *a.p;
     const unsigned lgN = P.lg_n + P.rate_bits;
     const size_t N = size_t(1) << lgN;
@@ -722,7 +742,7 @@ __global__ void __launch_bounds__(128, 8) quotient_kernel(QuotientArgs a) {
     const int nsel = P.num_selectors;
     for (int g = 0; g < P.num_gates; ++g) {
         const GateDesc gd = P.gates[g];
-        if ((gd.tag == TAG_POSEIDON) != (PART == 2)) continue;
+        if ((gd.tag == TAG_POSEIDON ? 2 : tag_is_recursion(gd.tag) ? 3 : 1) != PART) continue;
         u64 s = cs[(size_t)gd.selector_index * a.cs_stride];
         u64 filter = 1;
         for (u32 r = gd.group_lo; r < gd.group_hi; ++r)
@@ -740,12 +760,15 @@ __global__ void __launch_bounds__(128, 8) quotient_kernel(QuotientArgs a) {
         switch (gd.tag) {
             case TAG_NOOP: break;
             case TAG_CONSTANT:
+                if (PART != 1) break;      // PART is a template constant: the other launches' cases compile to nothing
                 for (u32 j = 0; j < gd.param; ++j) add_c(f_sub(K(j), W(j)));
                 break;
             case TAG_PUBLIC_INPUT:
+                if (PART != 1) break;
                 for (int j = 0; j < 4; ++j) add_c(f_sub(W(j), P.pi_hash[j]));
                 break;
             case TAG_BASE_SUM: {
+                if (PART != 1) break;
                 u64 sum = 0;
                 for (int j = (int)gd.param; j-- > 0;) sum = f_add(f_add(sum, sum), W(1 + j));
                 add_c(f_sub(sum, W(0)));
@@ -753,6 +776,7 @@ __global__ void __launch_bounds__(128, 8) quotient_kernel(QuotientArgs a) {
                 break;
             }
             case TAG_ARITHMETIC: {
+                if (PART != 1) break;
                 u64 c0 = K(0), c1 = K(1);
                 for (u32 j = 0; j < gd.param; ++j) {
                     u64 prod = f_mul(f_mul(W(4 * j), W(4 * j + 1)), c0);
@@ -761,6 +785,7 @@ __global__ void __launch_bounds__(128, 8) quotient_kernel(QuotientArgs a) {
                 break;
             }
             case TAG_POSEIDON: {
+                if (PART != 2) break;
                 u64 swap = W(24);
                 add_c(f_mul(swap, f_sub(swap, 1)));
                 u64 st[12];
@@ -802,6 +827,125 @@ __global__ void __launch_bounds__(128, 8) quotient_kernel(QuotientArgs a) {
                 for (int j = 0; j < 12; ++j) add_c(gl_sub_lazy_c(st[j], W(12 + j)));
                 break;
             }
+            case TAG_ARITHMETIC_EXT:       // per op: a[2] b[2] addend[2] out[2];  out - (c0 a b + c1 addend)
+            case TAG_MUL_EXT: {            // per op: a[2] b[2] out[2];            out - c0 a b
+                if (PART != 3) break;
+                const bool addend = gd.tag == TAG_ARITHMETIC_EXT;
+                const int per = addend ? 8 : 6;
+                const u64 c0 = K(0), c1 = addend ? K(1) : 0;
+                for (u32 j = 0; j < gd.param; ++j) {
+                    const int b = per * (int)j;
+                    QE t = qe_scale(qe_mul(QE{W(b), W(b + 1)}, QE{W(b + 2), W(b + 3)}), c0);
+                    if (addend) t = qe_add(t, qe_scale(QE{W(b + 4), W(b + 5)}, c1));
+                    const QE c = qe_sub(QE{W(b + per - 2), W(b + per - 1)}, t);
+                    add_c(c.a); add_c(c.b);
+                }
+                break;
+            }
+            case TAG_REDUCING:             // out[0..2) alpha[2..4) old_acc[4..6) coeffs, then the intermediate accumulators;
+            case TAG_REDUCING_EXT: {       // acc_i = acc_{i-1} alpha + coeff_i, the last accumulator is the output
+                if (PART != 3) break;
+                const bool ext = gd.tag == TAG_REDUCING_EXT;
+                const int nc = (int)gd.param, start_accs = 6 + (ext ? 2 * nc : nc);
+                const QE alpha{W(2), W(3)};
+                QE acc{W(4), W(5)};
+                for (int j = 0; j < nc; ++j) {
+                    QE t = qe_mul(acc, alpha);
+                    if (ext) t = qe_add(t, QE{W(6 + 2 * j), W(7 + 2 * j)});
+                    else t.a = f_add(t.a, W(6 + j));
+                    const int at = j + 1 == nc ? 0 : start_accs + 2 * j;
+                    acc = QE{W(at), W(at + 1)};
+                    const QE c = qe_sub(acc, t);
+                    add_c(c.a); add_c(c.b);
+                }
+                break;
+            }
+            case TAG_RANDOM_ACCESS: {      // per copy: index, claimed element, 2^bits items; extra constants; then the bit wires
+                if (PART != 3) break;
+                const int bits = (int)gd.param, vec = 1 << bits, copies = (int)gd.p2, extra = (int)gd.p3;
+                const int routed = (2 + vec) * copies + extra;
+                for (int cpy = 0; cpy < copies; ++cpy) {
+                    const int base = (2 + vec) * cpy, wb = routed + cpy * bits;
+                    u64 idx = 0;
+                    for (int j = 0; j < bits; ++j) { const u64 b = W(wb + j); add_c(f_mul(b, f_sub(b, 1))); }
+                    for (int j = bits; j-- > 0;) idx = f_add(f_add(idx, idx), W(wb + j));
+                    add_c(f_sub(idx, W(base)));
+                    // fold the list pairwise, level j with bit j: x + b (y - x); streamed through a stack of one partial
+                    // result per level so that the items are read once and never all live at once
+                    u64 stack[6];
+                    for (int k = 0; k < vec; k += 2) {
+                        u64 x = W(base + 2 + k), y = W(base + 3 + k);
+                        u64 v = f_add(x, f_mul(W(wb), f_sub(y, x)));
+                        int lvl = 1;
+                        for (int m = k >> 1; m & 1; m >>= 1, ++lvl) v = f_add(stack[lvl], f_mul(W(wb + lvl), f_sub(v, stack[lvl])));
+                        stack[lvl] = v;
+                    }
+                    add_c(f_sub(stack[bits], W(base + 1)));
+                }
+                for (int j = 0; j < extra; ++j) add_c(f_sub(K(j), W((2 + vec) * copies + j)));
+                break;
+            }
+            case TAG_EXPONENTIATION: {     // base 0, power bits 1..nb (little endian), output nb+1, intermediates nb+2..
+                if (PART != 3) break;
+                const int nb = (int)gd.param;
+                const u64 bm1 = f_sub(W(0), 1);
+                u64 prev = 1;
+                for (int j = 0; j < nb; ++j) {
+                    const u64 factor = f_add(f_mul(W(nb - j), bm1), 1);      // bit * base + (1 - bit)
+                    const u64 cur = W(nb + 2 + j);
+                    add_c(f_sub(f_mul(prev, factor), cur));
+                    prev = f_mul(cur, cur);
+                }
+                add_c(f_sub(W(nb + 1), W(2 * nb + 1)));
+                break;
+            }
+            case TAG_COSET_INTERP: {       // shift 0; 2^bits values; point; value; intermediates (evals, then products); shifted point
+                if (PART != 3) break;
+                const int np = 1 << gd.param, deg = (int)gd.p2, ni = (np - 2) / (deg - 1);
+                const int at_point = 1 + 2 * np, at_value = at_point + 2, at_inter = at_value + 2, at_shifted = at_inter + 4 * ni;
+                const QE shifted{W(at_shifted), W(at_shifted + 1)};
+                {
+                    const QE c = qe_sub(QE{W(at_point), W(at_point + 1)}, qe_scale(shifted, W(0)));
+                    add_c(c.a); add_c(c.b);
+                }
+                QE eval{0, 0}, prod{1, 0};
+                int lo = 0, hi = deg;
+                for (int seg = 0; seg <= ni; ++seg) {
+                    for (int k = lo; k < hi; ++k) {      // eval <- eval (z - x_k) + w_k v_k prod;  prod <- prod (z - x_k)
+                        const QE term{f_sub(shifted.a, P.bary_x[k]), shifted.b};
+                        const QE wv = qe_scale(QE{W(1 + 2 * k), W(2 + 2 * k)}, P.bary_w[k]);
+                        eval = qe_add(qe_mul(eval, term), qe_mul(wv, prod));
+                        prod = qe_mul(prod, term);
+                    }
+                    if (seg == ni) break;
+                    const QE ie{W(at_inter + 2 * seg), W(at_inter + 2 * seg + 1)};
+                    const QE ip{W(at_inter + 2 * (ni + seg)), W(at_inter + 2 * (ni + seg) + 1)};
+                    QE c = qe_sub(ie, eval);
+                    add_c(c.a); add_c(c.b);
+                    c = qe_sub(ip, prod);
+                    add_c(c.a); add_c(c.b);
+                    eval = ie; prod = ip;
+                    lo = 1 + (deg - 1) * (seg + 1);
+                    hi = min(lo + deg - 1, np);
+                }
+                const QE c = qe_sub(QE{W(at_value), W(at_value + 1)}, eval);
+                add_c(c.a); add_c(c.b);
+                break;
+            }
+            case TAG_POSEIDON_MDS: {       // 12 F_{p^2} inputs at 2 i, outputs at 24 + 2 i: the MDS matrix acts on each component
+                if (PART != 3) break;
+                u64 sa[12], sb[12];
+#pragma unroll
+                for (int j = 0; j < 12; ++j) { sa[j] = W(2 * j); sb[j] = W(2 * j + 1); }
+                mds_layer(sa);
+                mds_layer(sb);
+#pragma unroll
+                for (int j = 0; j < 12; ++j) {
+                    add_c(f_sub(W(24 + 2 * j), f_canon(sa[j])));
+                    add_c(f_sub(W(25 + 2 * j), f_canon(sb[j])));
+                }
+                break;
+            }
             default: break;   // rejected on the host (ZKB_E_UNSUPPORTED_GATE)
         }
         acc0 = f_add(acc0, f_mul(filter, g0));
@@ -810,6 +954,9 @@ __global__ void __launch_bounds__(128, 8) quotient_kernel(QuotientArgs a) {
     if (PART == 1) {
         a.out[l] = acc0;
         if (nch > 1) a.out[a.out_stride + l] = acc1;
+    } else if (PART == 3) {
+        a.out[l] = f_add(acc0, a.out[l]);
+        if (nch > 1) a.out[a.out_stride + l] = f_add(acc1, a.out[a.out_stride + l]);
     } else {
         u64 zi = P.zh_inv[i & rate_mask];
         a.out[l] = f_mul(f_add(acc0, a.out[l]), zi);
@@ -824,6 +971,10 @@ void launch_quotient(const QuotientParams* params_dev, const QuotientParams& ph,
     size_t N = size_t(1) << (ph.lg_n + ph.rate_bits);
     ZKB_COUNT_LAUNCH();
     quotient_kernel<1><<<(unsigned)((N + 127) / 128), 128, 0, st>>>(a);
+    if (ph.has_recursion_gates) {
+        ZKB_COUNT_LAUNCH();
+        quotient_kernel<3><<<(unsigned)((N + 127) / 128), 128, 0, st>>>(a);
+    }
     ZKB_COUNT_LAUNCH();
     quotient_kernel<2><<<(unsigned)((N + 127) / 128), 128, 0, st>>>(a);
 }

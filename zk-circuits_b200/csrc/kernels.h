@@ -53,7 +53,10 @@ void launch_canonical_check(const u64* v, size_t count, unsigned* flag_dev, cuda
 void launch_salt_fill(u64* out, size_t stride, size_t num_leaves, u64 seed, unsigned batch, cudaStream_t st);
 
 // ---- prover stages ----
-struct GateDesc { u32 tag; u32 param; u32 selector_index; u32 group_lo, group_hi; u32 row; };
+// param / p2 / p3: Constant num_consts; BaseSum num_limbs; Arithmetic, ArithmeticExtension, MulExtension num_ops;
+// Reducing(Extension) num_coeffs; Exponentiation num_power_bits; RandomAccess bits / num_copies / num_extra_constants;
+// CosetInterpolation subgroup_bits / degree
+struct GateDesc { u32 tag; u32 param; u32 selector_index; u32 group_lo, group_hi; u32 row; u32 p2, p3; };
 struct QuotientParams {
     unsigned lg_n, rate_bits;
     int num_wires, num_routed, num_constants, num_selectors, num_challenges, num_partial_products, qdf;
@@ -65,6 +68,8 @@ struct QuotientParams {
     u64 zh_inv[16];      // 1 / Z_H on the coset, index i mod 2^rate_bits
     u64 zh[16];
     u64 n_inv_dummy;
+    u64 bary_w[16], bary_x[16];   // CosetInterpolation: barycentric weights and the subgroup points w^k
+    int has_recursion_gates;      // any gate evaluated by the third quotient launch
 };
 // chunk products + running product -> out columns [Z_0..Z_{c-1}, pp(ch0)..., pp(ch1)...], each n values
 // betas_gammas: HOST array [betas(nch), gammas(nch)]

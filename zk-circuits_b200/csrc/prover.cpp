@@ -277,7 +277,15 @@ void Circuit::run_quotient(const u64* pi_hash, const u64* betas, const u64* gamm
     qp->qdf = (int)cd_.quotient_degree_factor; qp->num_gates = (int)cd_.gates.size(); qp->num_gate_constraints = (int)cd_.num_gate_constraints;
     for (size_t g = 0; g < cd_.gates.size(); ++g) {
         u64 sel = cd_.selector_indices[g];
-        qp->gates[g] = GateDesc{cd_.gates[g].tag, (u32)cd_.gates[g].param, (u32)sel, (u32)cd_.groups[sel].first, (u32)cd_.groups[sel].second, (u32)g};
+        const GateInfo& gi = cd_.gates[g];
+        qp->gates[g] = GateDesc{gi.tag, (u32)gi.param, (u32)sel, (u32)cd_.groups[sel].first, (u32)cd_.groups[sel].second, (u32)g,
+                                (u32)gi.p2, (u32)gi.p3};
+        if (gi.is_recursion_gate()) qp->has_recursion_gates = 1;
+        if (gi.tag == GT_COSET_INTERP) {      // one parameter set per circuit (checked at create)
+            const u64 w = gl_root_of_unity((unsigned)gi.param);
+            u64 x = 1;
+            for (size_t k = 0; k < gi.weights.size(); ++k) { qp->bary_w[k] = gi.weights[k]; qp->bary_x[k] = x; x = gl_mul(x, w); }
+        }
     }
     for (size_t j = 0; j < cd_.k_is.size(); ++j) qp->k_is[j] = cd_.k_is[j];
     for (int c = 0; c < nch; ++c) { qp->betas[c] = betas[c]; qp->gammas[c] = gammas[c]; qp->alphas[c] = alphas[c]; }

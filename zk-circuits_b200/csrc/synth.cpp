@@ -27,7 +27,23 @@ struct Rng {
     u64 felt() { return gl_canon(next()); }
     u64 below(u64 m) { return next() % m; }
 };
-constexpr int G_NOOP = 0, G_CONST = 1, G_PI = 2, G_BASESUM = 3, G_ARITH = 4, G_POSEIDON = 5;
+// row kinds; a circuit's gate table maps them to gate indices
+enum Kind { G_NOOP = 0, G_CONST, G_PI, G_BASESUM, G_ARITH, G_POSEIDON,
+            G_ARITH_EXT, G_MUL_EXT, G_REDUCING, G_REDUCING_EXT, G_RANDOM_ACCESS, G_EXP, G_COSET, G_MDS, NUM_KINDS };
+// one entry of the serialized gate list: DefaultGateSerializer tag, parameters, constraint degree
+struct GateRow { Kind kind; u32 tag; std::vector<u64> params; unsigned degree; };
+// sorted by (degree, id) as upstream's CircuitBuilder::build leaves them
+std::vector<GateRow> gate_table(bool recursion, const std::vector<u64>& bary_weights) {
+    if (!recursion)
+        return {{G_NOOP, 9, {}, 0}, {G_CONST, 3, {2}, 1}, {G_PI, 12, {}, 1}, {G_BASESUM, 2, {63}, 2}, {G_ARITH, 0, {20}, 3},
+                {G_POSEIDON, 11, {}, 7}};
+    std::vector<u64> coset = {4, 6, 16};      // subgroup_bits, degree, weights.len, weights...
+    coset.insert(coset.end(), bary_weights.begin(), bary_weights.end());
+    return {{G_NOOP, 9, {}, 0}, {G_CONST, 3, {2}, 1}, {G_MDS, 10, {}, 1}, {G_PI, 12, {}, 1}, {G_BASESUM, 2, {63}, 2},
+            {G_REDUCING_EXT, 14, {32}, 2}, {G_REDUCING, 15, {43}, 2}, {G_ARITH_EXT, 1, {10}, 3}, {G_ARITH, 0, {20}, 3},
+            {G_MUL_EXT, 8, {13}, 3}, {G_EXP, 5, {66}, 4}, {G_RANDOM_ACCESS, 13, {4, 4, 2}, 5}, {G_COSET, 4, coset, 6},
+            {G_POSEIDON, 11, {}, 7}};
+}
 constexpr int W_SWAP = 24, W_DELTA = 25, W_FULL0 = 29, W_PARTIAL = 65, W_FULL1 = 87;
 constexpr u64 UNUSED_SEL = 0xFFFFFFFFULL;
 constexpr u64 NUM_QUERY_ROUNDS = 28, RATE_BITS = 3, CAP_HEIGHT = 4, ARITY_BITS = 4, FINAL_POLY_BITS = 5;
@@ -70,7 +86,9 @@ struct Bytes {
 }  // namespace
 
 // CommonCircuitData::to_bytes layout
-static std::vector<uint8_t> serialize_common(const SynthCircuit& s, const std::vector<u64>& k_is, bool zk) {
+static std::vector<uint8_t> serialize_common(const SynthCircuit& s, const std::vector<u64>& k_is, bool zk,
+                                             const std::vector<GateRow>& gates, const std::vector<u64>& selector_indices,
+                                             const std::vector<std::pair<u64, u64>>& groups, u64 num_gate_constraints) {
     Bytes o;
     o.w64(135); o.w64(80); o.w64(2); o.w64(100); o.w64(2); o.w64(8);
     o.w8(1); o.w8(zk ? 1 : 0);
@@ -81,18 +99,17 @@ static std::vector<uint8_t> serialize_common(const SynthCircuit& s, const std::v
     o.vec(s.reduction_arity_bits);
     o.w64(s.degree_bits);
     o.w8(zk ? 1 : 0);                       // hiding
-    o.vec({0, 0, 0, 0, 0, 1});              // selector_indices
-    o.w64(2); o.w64(0); o.w64(5); o.w64(5); o.w64(6);   // groups
-    o.w64(8); o.w64(123); o.w64(4); o.w64(s.public_inputs.size());
+    o.vec(selector_indices);
+    o.w64(groups.size());
+    for (auto& g : groups) { o.w64(g.first); o.w64(g.second); }
+    o.w64(8); o.w64(num_gate_constraints); o.w64(groups.size() + 2); o.w64(s.public_inputs.size());
     o.vec(k_is);
     o.w64(9); o.w64(0); o.w64(0); o.w64(0);
-    o.w64(6);                               // gates, sorted by (degree, id) as upstream
-    o.w32(9);                               // Noop
-    o.w32(3); o.w64(2);                     // Constant { num_consts: 2 }
-    o.w32(12);                              // PublicInput
-    o.w32(2); o.w64(63);                    // BaseSum<2> { num_limbs: 63 }
-    o.w32(0); o.w64(20);                    // Arithmetic { num_ops: 20 }
-    o.w32(11);                              // Poseidon
+    o.w64(gates.size());
+    for (auto& g : gates) {
+        o.w32(g.tag);
+        for (u64 p : g.params) o.w64(p);
+    }
     return o.b;
 }
 
@@ -102,6 +119,35 @@ SynthCircuit make_synth_circuit(const SynthSpec& spec) {
     std::vector<u64> k_is(80);
     k_is[0] = 1;
     for (int j = 1; j < 80; ++j) k_is[j] = gl_mul(k_is[j - 1], GL_GEN);
+
+    // gate table, selector groups by upstream's greedy rule (extend a group while size + degree < 9)
+    const bool recursion = spec.recursion();
+    if (recursion && spec.zk) throw std::runtime_error("recursion-shaped circuits are not zero-knowledge");
+    std::vector<u64> bary(16);
+    {
+        u64 xs[16], w16 = gl_root_of_unity(4);
+        xs[0] = 1;
+        for (int i = 1; i < 16; ++i) xs[i] = gl_mul(xs[i - 1], w16);
+        for (int i = 0; i < 16; ++i) {
+            u64 d = 1;
+            for (int j = 0; j < 16; ++j) if (j != i) d = gl_mul(d, gl_sub(xs[i], xs[j]));
+            bary[i] = gl_inv(d);
+        }
+    }
+    const std::vector<GateRow> gates = gate_table(recursion, bary);
+    int gate_index[NUM_KINDS];
+    std::fill(gate_index, gate_index + NUM_KINDS, -1);
+    for (size_t i = 0; i < gates.size(); ++i) gate_index[gates[i].kind] = (int)i;
+    std::vector<u64> selector_indices(gates.size());
+    std::vector<std::pair<u64, u64>> groups;
+    for (size_t start = 0; start < gates.size();) {
+        size_t size = 0;
+        while (start + size < gates.size() && size + gates[start + size].degree < 9) ++size;
+        for (size_t i = start; i < start + size; ++i) selector_indices[i] = groups.size();
+        groups.push_back({start, start + size});
+        start += size;
+    }
+    const size_t nsel = groups.size();
 
     std::vector<Row> rows;
     std::vector<std::pair<Cell, Cell>> copies;
@@ -120,6 +166,16 @@ SynthCircuit make_synth_circuit(const SynthSpec& spec) {
         }
         rows[row].w[col] = v;
         return v;
+    };
+    auto take_ext = [&](u32 row, u32 col) {     // an F_{p^2} value on two consecutive routed wires
+        u64 a = take_input(row, col);
+        u64 b = take_input(row, col + 1);
+        return e_make(a, b);
+    };
+    auto put_ext = [&](u32 row, u32 col, ext2 v, bool to_pool) {
+        rows[row].w[col] = v.a;
+        rows[row].w[col + 1] = v.b;
+        if (to_pool) { pool.push_back({v.a, {row, col}}); pool.push_back({v.b, {row, col + 1}}); }
     };
     auto copy_from = [&](u32 row, u32 col, const Pooled& p) {
         rows[row].w[col] = p.value;
@@ -206,6 +262,12 @@ SynthCircuit make_synth_circuit(const SynthSpec& spec) {
     for (size_t i = 1; i < spec.n_const; ++i) todo.push_back(G_CONST);
     for (size_t i = 0; i < spec.n_base_sum; ++i) todo.push_back(G_BASESUM);
     for (size_t i = 0; i < spec.n_arith; ++i) todo.push_back(G_ARITH);
+    {
+        const std::pair<Kind, size_t> extra[] = {{G_ARITH_EXT, spec.n_arith_ext}, {G_MUL_EXT, spec.n_mul_ext}, {G_REDUCING, spec.n_reducing},
+                                                 {G_REDUCING_EXT, spec.n_reducing_ext}, {G_RANDOM_ACCESS, spec.n_random_access},
+                                                 {G_EXP, spec.n_exp}, {G_COSET, spec.n_coset}, {G_MDS, spec.n_mds}};
+        for (auto& e : extra) todo.insert(todo.end(), e.second, (int)e.first);
+    }
     // Poseidon rows come in sponge chains (storage-proof-like, 24 rows) and single compressions
     size_t pos_left = spec.n_poseidon > poseidon_used ? spec.n_poseidon - poseidon_used : 0;
     const int CHAIN = -1;
@@ -255,6 +317,96 @@ SynthCircuit make_synth_circuit(const SynthSpec& spec) {
                 rows[r].w[4 * i + 3] = out;
                 pool.push_back({out, {r, 4 * i + 3}});
             }
+        } else if (t == G_ARITH_EXT || t == G_MUL_EXT) {
+            // out = c0 a b (+ c1 addend) in F_{p^2}; 10 ops of 8 wires, or 13 ops of 6 wires without the addend
+            const u32 stride = t == G_ARITH_EXT ? 8 : 6, ops = t == G_ARITH_EXT ? 10 : 13;
+            u32 r = new_row(t);
+            rows[r].consts[0] = rng.below(2) ? 1 : rng.felt();
+            if (t == G_ARITH_EXT) rows[r].consts[1] = rng.below(2) ? 1 : rng.felt();
+            for (u32 i = 0; i < ops; ++i) {
+                ext2 a = take_ext(r, stride * i);
+                ext2 b = take_ext(r, stride * i + 2);
+                ext2 o = e_mul_base(e_mul(a, b), rows[r].consts[0]);
+                if (t == G_ARITH_EXT) o = e_add(o, e_mul_base(take_ext(r, stride * i + 4), rows[r].consts[1]));
+                put_ext(r, stride * i + stride - 2, o, true);
+            }
+        } else if (t == G_REDUCING || t == G_REDUCING_EXT) {
+            // Horner chain acc <- acc alpha + coeff over 43 base / 32 extension coefficients; the last value lands on wires 0..1
+            const u32 nc = t == G_REDUCING ? 43 : 32, cw = t == G_REDUCING ? 1 : 2, accs_at = 6 + cw * nc;
+            u32 r = new_row(t);
+            ext2 alpha = take_ext(r, 2);
+            ext2 acc = take_ext(r, 4);
+            for (u32 i = 0; i < nc; ++i) {
+                ext2 coeff = cw == 2 ? take_ext(r, 6 + 2 * i) : e_from(take_input(r, 6 + i));
+                acc = e_add(e_mul(acc, alpha), coeff);
+                if (i + 1 == nc) put_ext(r, 0, acc, true);
+                else put_ext(r, accs_at + 2 * i, acc, false);
+            }
+        } else if (t == G_RANDOM_ACCESS) {
+            // four 16-way selections (index bits on the unrouted wires 74..89) and two constants on wires 72, 73
+            u32 r = new_row(t);
+            for (u32 cpy = 0; cpy < 4; ++cpy) {
+                const u32 at = 18 * cpy;
+                const u64 idx = rng.below(16);
+                rows[r].w[at] = idx;
+                for (u32 i = 0; i < 16; ++i) take_input(r, at + 2 + i);
+                rows[r].w[at + 1] = rows[r].w[at + 2 + idx];
+                pool.push_back({rows[r].w[at + 1], {r, at + 1}});
+                for (u32 i = 0; i < 4; ++i) rows[r].w[74 + 4 * cpy + i] = (idx >> i) & 1;
+            }
+            for (u32 k = 0; k < 2; ++k) {
+                const u64 v = rng.below(2) ? rng.felt() : rng.below(256);
+                rows[r].consts[k] = v;
+                rows[r].w[72 + k] = v;
+                pool.push_back({v, {r, 72 + k}});
+            }
+        } else if (t == G_EXP) {
+            // square-and-multiply over 66 exponent bits (most significant first), every partial power on its own wire
+            u32 r = new_row(t);
+            const u64 base = take_input(r, 0);
+            for (u32 i = 0; i < 66; ++i) rows[r].w[1 + i] = rng.below(2);
+            u64 power = 1;
+            for (u32 i = 0; i < 66; ++i) {
+                if (i) power = gl_mul(power, power);
+                if (rows[r].w[66 - i]) power = gl_mul(power, base);
+                rows[r].w[68 + i] = power;
+            }
+            rows[r].w[67] = power;
+            pool.push_back({power, {r, 67}});
+            for (u32 k = 0; k < 2; ++k) { u32 b = (u32)rng.below(66); bools.push_back({rows[r].w[1 + b], {r, 1 + b}}); }
+        } else if (t == G_COSET) {
+            // 16 F_{p^2} values on shift * <w_16>, interpolated at an F_{p^2} point: barycentric sums in three runs of
+            // 6 + 5 + 5 points, the two intermediate (sum, product) pairs on wires 37..44, point / shift on 45..46
+            u32 r = new_row(t);
+            u64 shift;
+            do shift = rng.felt(); while (shift == 0);
+            rows[r].w[0] = shift;
+            for (u32 i = 0; i < 32; ++i) take_input(r, 1 + i);
+            const ext2 z = e_mul_base(take_ext(r, 33), gl_inv(shift));
+            put_ext(r, 45, z, false);
+            ext2 sum = e_from(0), prod = e_from(1);
+            u64 x = 1;
+            const u64 w16 = gl_root_of_unity(4);
+            for (u32 k = 0; k < 16; ++k, x = gl_mul(x, w16)) {
+                if (k == 6 || k == 11) {
+                    const u32 i = k == 6 ? 0 : 1;
+                    put_ext(r, 37 + 2 * i, sum, false);
+                    put_ext(r, 41 + 2 * i, prod, false);
+                }
+                const ext2 term = e_sub(z, e_from(x));
+                const ext2 wv = e_mul_base(e_make(rows[r].w[1 + 2 * k], rows[r].w[2 + 2 * k]), bary[k]);
+                sum = e_add(e_mul(sum, term), e_mul(wv, prod));
+                prod = e_mul(prod, term);
+            }
+            put_ext(r, 35, sum, true);
+        } else if (t == G_MDS) {
+            // Poseidon's MDS matrix on 12 F_{p^2} values: it acts on the two components separately
+            u32 r = new_row(t);
+            u64 lo[12], hi[12];
+            for (u32 i = 0; i < 12; ++i) { ext2 v = take_ext(r, 2 * i); lo[i] = v.a; hi[i] = v.b; }
+            h_mds_layer(lo);
+            h_mds_layer(hi);
+            for (u32 k = 0; k < 12; ++k) put_ext(r, 24 + 2 * k, e_make(lo[k], hi[k]), true);
         } else if (t == G_POSEIDON) {
             u32 r = new_row(G_POSEIDON);
             for (u32 i = 0; i < 8; ++i) take_input(r, i);
@@ -319,14 +471,14 @@ SynthCircuit make_synth_circuit(const SynthSpec& spec) {
 
     // wires, constants
     out.wires.assign(135, std::vector<u64>(n));
-    out.const_sigma_values.assign(84, std::vector<u64>(n));
+    out.const_sigma_values.assign(nsel + 2 + 80, std::vector<u64>(n));
     for (size_t r = 0; r < n; ++r) {
         for (int j = 0; j < 135; ++j) out.wires[j][r] = rows[r].w[j];
-        int g = rows[r].gate;
-        out.const_sigma_values[0][r] = g < 5 ? (u64)g : UNUSED_SEL;
-        out.const_sigma_values[1][r] = g == 5 ? 5 : UNUSED_SEL;
-        out.const_sigma_values[2][r] = rows[r].consts[0];
-        out.const_sigma_values[3][r] = rows[r].consts[1];
+        const int g = gate_index[rows[r].gate];
+        if (g < 0) throw std::runtime_error("row kind outside the circuit's gate set");
+        for (size_t k = 0; k < nsel; ++k) out.const_sigma_values[k][r] = selector_indices[g] == k ? (u64)g : UNUSED_SEL;
+        out.const_sigma_values[nsel][r] = rows[r].consts[0];
+        out.const_sigma_values[nsel + 1][r] = rows[r].consts[1];
     }
     // sigma from the copy-constraint classes (cycle through each class)
     std::vector<u32> parent(80 * n);
@@ -356,9 +508,9 @@ SynthCircuit make_synth_circuit(const SynthSpec& spec) {
     for (u32 col = 0; col < 80; ++col)
         for (size_t r = 0; r < n; ++r) {
             u32 t = sigma[col * n + r];
-            out.const_sigma_values[4 + col][r] = gl_mul(k_is[t / n], subgroup[t % n]);
+            out.const_sigma_values[nsel + 2 + col][r] = gl_mul(k_is[t / n], subgroup[t % n]);
         }
-    out.common = serialize_common(out, k_is, spec.zk);
+    out.common = serialize_common(out, k_is, spec.zk, gates, selector_indices, groups, 123);
     return out;
 }
 

@@ -162,6 +162,7 @@ def main():
                          "threads than cores costs throughput (measured at 8 GPUs / 32 cores: 4 streams 1477 proofs/s, 8 streams 1410)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-sweep", action="store_true", help="skip the LDE/Merkle microbench points (config #3)")
+    ap.add_argument("--no-aggregation", action="store_true", help="skip the aggregation-tree measurement (config #4)")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -351,6 +352,41 @@ def main():
             sweep.append({"lg_n": lg_n, "cols": cols, "lde_ms": tm["lde_ms"], "lde_gbs": gbs, "lde_frac_hbm": gbs / peak,
                           "merkle_ms": tm["merkle_ms"], "perms_per_sec": pp / (tm["merkle_ms"] * 1e-3)})
         line["lde_merkle_sweep"] = sweep
+    if world == 1 and not args.no_aggregation:
+        # config #4: the aggregator's default tree (branching 2, depth 3: 8 leaf proofs -> 4 + 2 + 1 chunk proofs,
+        # aggregator/src/circuits/tree.rs:17-20,55-77) with recursion-shaped chunk circuits (14-gate set, 4 selector groups,
+        # n = 2^12, non-zk; the real recursive-verifier circuit needs the Rust circuit builder). Chunks of a level run
+        # concurrently on their own prover contexts, levels are sequential. Witness generation (Rust side) is not included.
+        rs = Z.SynthCircuit(seed=4, **Z.SynthCircuit.RECURSION)
+        S = min(4, B)
+        rcircs = [Z.ProverCircuit(rs.common, rs.const_sigma_values, is_values=True, device=local_rank) for _ in range(S)]
+        rpinned = torch.empty(rs.wires.shape, dtype=torch.int64, pin_memory=True)
+        rpinned.numpy().view(np.uint64)[:] = rs.wires
+        raddr = rpinned.data_ptr()
+
+        def prove_chunk(prover, chunk, level, index):
+            return prover.prove(raddr, rs.public_inputs, salt_seed=0)
+
+        leaves = [None] * 8
+        for _ in range(3):
+            zbatch.aggregate_tree(leaves, 2, prove_chunk, rcircs)
+        reps = max(3, K // 2)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            root, widths = zbatch.aggregate_tree(leaves, 2, prove_chunk, rcircs)
+        torch.cuda.synchronize()
+        t_tree = (time.perf_counter() - t0) / reps
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            rcircs[0].prove(raddr, rs.public_inputs, salt_seed=0)
+        t_chunk = (time.perf_counter() - t0) / reps
+        line["aggregation"] = {"workload": "aggregation_tree_8_leaves_recursion_synth_n2^12", "leaf_proofs": 8, "branching": 2,
+                               "chunk_proofs_per_level": widths, "tree_ms": 1000 * t_tree, "chunk_prove_ms": 1000 * t_chunk,
+                               "chunk_stage_ms": rcircs[0].timings(), "chunk_proof_bytes": len(root), "streams": S,
+                               "chunk_degree_bits": int(rs.n).bit_length() - 1, "gates": 14,
+                               "note": "host-buffer zkb_prove() calls (H2D of the 135 x 2^12 wire matrix inside); synthetic "
+                                       "recursion-shaped circuit, recursion gate formulas unpinned against qp-plonky2 (DESIGN.md)"}
     if sharded_line is not None:
         line["sharded_commit"] = sharded_line
     if world == 1 and not args.no_cpu_baseline:

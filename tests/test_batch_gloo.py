@@ -113,3 +113,33 @@ def test_coset_sharded_commit_over_gloo(tmp_path, world_size):
     port = 31500 + (os.getpid() % 2000) + world_size
     mp.spawn(_sharded_rank_main, args=(world_size, port, str(tmp_path)), nprocs=world_size, join=True)
     assert (tmp_path / "ok2").read_text() == "ok"
+
+
+def test_aggregate_tree_mirrors_the_reference_level_order():
+    """zkb200.batch.aggregate_tree = aggregate_to_tree (aggregator/src/circuits/tree.rs:55-77): chunks of `branching`,
+    every chunk of a level before any chunk of the next, children in order, a short last chunk allowed."""
+    sys.path.insert(0, os.path.join(ROOT, "zk-circuits_b200"))
+    import threading
+    from zkb200.batch import aggregate_tree
+
+    lock, log = threading.Lock(), []
+
+    def prove_chunk(prover, chunk, level, index):
+        with lock:
+            log.append((level, index, prover))
+        return "(" + "".join(chunk) + ")"
+
+    root, widths = aggregate_tree(list("abcdefgh"), 2, prove_chunk, ["s0", "s1", "s2"])
+    assert root == "(((ab)(cd))((ef)(gh)))" and widths == [4, 2, 1]          # the default 8-leaf, depth-3 tree
+    levels = [lv for lv, _, _ in log]
+    assert levels == sorted(levels), "a level started before the one below it finished"
+    assert {(lv, i) for lv, i, _ in log} == {(0, 0), (0, 1), (0, 2), (0, 3), (1, 0), (1, 1), (2, 0)}
+    assert all(p == f"s{i % 3}" for _, i, p in log)                          # chunk i of a level runs on stream i mod S
+    root, widths = aggregate_tree(list("abcde"), 3, prove_chunk, ["s0"])
+    assert root == "((abc)(de))" and widths == [2, 1]
+    root, widths = aggregate_tree(["a"], 2, prove_chunk, ["s0"])
+    assert root == "(a)" and widths == [1]
+    with pytest.raises(ValueError):
+        aggregate_tree([], 2, prove_chunk, ["s0"])
+    with pytest.raises(ValueError):
+        aggregate_tree(["a"], 1, prove_chunk, ["s0"])

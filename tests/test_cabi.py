@@ -51,9 +51,9 @@ def test_malformed_common_data_is_a_parse_error(zkb):
         with pytest.raises(zkb.ZkbError) as e:
             zkb.ProverCircuit(bad if bad else b"\0", cs)
         assert e.value.status == "ZKB_E_PARSE"
-    # unsupported gate tag (13 = RandomAccess) -> ZKB_E_UNSUPPORTED_GATE
+    # unsupported gate tag (6 = Lookup; lookup tables are outside the implemented set) -> ZKB_E_UNSUPPORTED_GATE
     tampered = bytearray(good)
-    tampered[997] = 13
+    tampered[997] = 6
     with pytest.raises(zkb.ZkbError) as e:
         zkb.ProverCircuit(bytes(tampered), cs)
     assert e.value.status == "ZKB_E_UNSUPPORTED_GATE"
@@ -95,3 +95,21 @@ def test_header_is_plain_c_and_the_c_example_links(zkb, tmp_path):
         assert out.returncode == 2 and "no CUDA device" in out.stderr and "sm_100a" in out.stderr
     else:
         assert out.returncode == 0, out.stderr
+
+
+@pytest.mark.parametrize("shape", ["tiny", "tiny_zk", "recursion"])
+def test_workload_generator_matches_the_oracles(zkb, oracle, shape):
+    """zkb_synth_* (host code standing in for the Rust circuit builder + witness generation) emits the same circuit,
+    witness and CommonCircuitData bytes as the oracle's generator for the same spec — for the wormhole gate set and for the
+    recursion gate set — and the oracle's checker accepts the witness."""
+    if shape == "recursion":
+        spec = dict(seed=3, **oracle.Synth.RECURSION_TINY)
+    else:
+        spec = dict(seed=6, zk=shape == "tiny_zk", **oracle.Synth.TINY)
+    a = zkb.SynthCircuit(**spec)
+    b = oracle.Synth(**spec)
+    assert b.check() == ""
+    assert a.common == b.common
+    assert np.array_equal(a.const_sigma_values, b.const_sigma_values)
+    assert np.array_equal(a.wires, b.wires)
+    assert np.array_equal(a.public_inputs, b.public_inputs)

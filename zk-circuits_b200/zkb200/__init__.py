@@ -32,7 +32,7 @@ EXPORTS = ["zkb_version", "zkb_last_error", "zkb_device_count", "zkb_kernel_laun
            "zkb_circuit_verifier_only", "zkb_proof_size", "zkb_prove", "zkb_witness_upload", "zkb_prove_resident",
            "zkb_last_timings", "zkb_poseidon_permute_batch", "zkb_lde_batch", "zkb_merkle_commit", "zkb_commit_batch",
            "zkb_commit_cosets",
-           "zkb_partial_products", "zkb_quotient", "zkb_synth_create", "zkb_synth_destroy", "zkb_synth_common_len",
+           "zkb_partial_products", "zkb_quotient", "zkb_synth_create", "zkb_synth_create_recursion", "zkb_synth_num_constants", "zkb_synth_destroy", "zkb_synth_common_len",
            "zkb_synth_degree", "zkb_synth_get"]
 
 
@@ -81,6 +81,10 @@ def lib():
                                         ctypes.c_int, u64p, f32p, ctypes.c_int]
         L.zkb_partial_products.argtypes = [ctypes.c_void_p, u64p, u64p, u64p, u64p]
         L.zkb_quotient.argtypes = [ctypes.c_void_p, u64p, u64p, u64p, ctypes.c_size_t, u64p, u64p, u64p, u64p]
+        L.zkb_synth_create_recursion.argtypes = [ctypes.c_uint] + [ctypes.c_size_t] * 5 + [ctypes.c_uint64, ctypes.c_void_p,
+                                                 ctypes.POINTER(ctypes.c_void_p)]
+        L.zkb_synth_num_constants.restype = ctypes.c_size_t
+        L.zkb_synth_num_constants.argtypes = [ctypes.c_void_p]
         L.zkb_synth_create.argtypes = [ctypes.c_uint, ctypes.c_int] + [ctypes.c_size_t] * 5 + [ctypes.c_uint64, ctypes.POINTER(ctypes.c_void_p)]
         L.zkb_synth_destroy.argtypes = [ctypes.c_void_p]
         L.zkb_synth_common_len.argtypes = [ctypes.c_void_p]
@@ -261,17 +265,29 @@ TINY = dict(n_poseidon=6, n_base_sum=5, n_arith=6, n_const=3, num_public_inputs=
 class SynthCircuit:
     """Synthetic wormhole-/voting-shaped circuit + satisfying witness (csrc/synth.cpp; host code)."""
 
+    RECURSION_KEYS = ("n_arith_ext", "n_mul_ext", "n_reducing", "n_reducing_ext", "n_random_access", "n_exp", "n_coset", "n_mds")
+    # one aggregation chunk's recursive-verifier circuit, n = 2^12 (row mix: an estimate, SURVEY.md App. E item 2)
+    RECURSION = dict(n_poseidon=1600, n_base_sum=260, n_arith=500, n_const=60, num_public_inputs=16, n_arith_ext=800,
+                     n_mul_ext=160, n_reducing=120, n_reducing_ext=120, n_random_access=230, n_exp=60, n_coset=112, n_mds=8)
+
     def __init__(self, zk=False, seed=1, min_degree_bits=0, n_poseidon=488, n_base_sum=3800, n_arith=2520, n_const=100,
-                 num_public_inputs=16):
+                 num_public_inputs=16, **recursion):
         h = ctypes.c_void_p()
-        _check(lib().zkb_synth_create(min_degree_bits, int(zk), n_poseidon, n_base_sum, n_arith, n_const, num_public_inputs,
-                                      seed, ctypes.byref(h)))
+        if recursion:
+            if set(recursion) - set(self.RECURSION_KEYS) or zk:
+                raise ValueError("bad recursion spec (recursion-shaped circuits are not zero-knowledge)")
+            rows = (ctypes.c_size_t * 8)(*[int(recursion.get(k, 0)) for k in self.RECURSION_KEYS])
+            _check(lib().zkb_synth_create_recursion(min_degree_bits, n_poseidon, n_base_sum, n_arith, n_const, num_public_inputs,
+                                                    seed, ctypes.cast(rows, ctypes.c_void_p), ctypes.byref(h)))
+        else:
+            _check(lib().zkb_synth_create(min_degree_bits, int(zk), n_poseidon, n_base_sum, n_arith, n_const, num_public_inputs,
+                                          seed, ctypes.byref(h)))
         try:
             n = lib().zkb_synth_degree(h)
             cb = np.zeros(lib().zkb_synth_common_len(h), dtype=np.uint8)
             self.n = n
             self.zk = bool(zk)
-            self.const_sigma_values = np.zeros((84, n), dtype=np.uint64)
+            self.const_sigma_values = np.zeros((lib().zkb_synth_num_constants(h) + 80, n), dtype=np.uint64)
             self.wires = np.zeros((135, n), dtype=np.uint64)
             self.public_inputs = np.zeros(num_public_inputs, dtype=np.uint64)
             _check(lib().zkb_synth_get(h, cb.ctypes.data_as(u8p), self.const_sigma_values.ctypes.data_as(u64p),

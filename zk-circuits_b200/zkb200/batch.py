@@ -73,6 +73,29 @@ def prove_batch(witnesses, provers, prove_fn, gather=True):
     return [p for part in parts for p in part]
 
 
+def aggregate_tree(leaf_proofs, branching, prove_chunk, provers):
+    """Level-by-level aggregation of `leaf_proofs` into one root proof — the host-side mirror of the reference's
+    `aggregate_to_tree` / `aggregate_level` (/root/reference/wormhole/aggregator/src/circuits/tree.rs:55-103): a level's
+    proofs are cut into chunks of `branching` (the last chunk may be short), every chunk of a level is proved concurrently
+    (the reference maps them over rayon; here over this rank's prover contexts = CUDA streams), and a level starts only when
+    the one below is complete, so the GPU sees 4, 2, 1 concurrent proofs for the default 8-leaf tree.
+
+    prove_chunk(prover, chunk, level, index) -> proof   (level 0 = the chunks made of leaf proofs)
+    Returns (root_proof, [number of chunk proofs per level])."""
+    if branching < 2:
+        raise ValueError("branching factor must be at least 2")
+    if not leaf_proofs:
+        raise ValueError("no leaf proofs")
+    level, depth, widths = list(leaf_proofs), 0, []
+    while len(level) > 1 or depth == 0:
+        chunks = [level[i:i + branching] for i in range(0, len(level), branching)]
+        jobs = [(lambda p, c=c, d=depth, i=i: prove_chunk(p, c, d, i)) for i, c in enumerate(chunks)]
+        level = run_streams(jobs, provers)
+        widths.append(len(chunks))
+        depth += 1
+    return level[0], widths
+
+
 def max_over_ranks(values, device=None):
     """Element-wise max of a list of floats over all ranks (timing rule: a multi-GPU number is the slowest rank's)."""
     rank, ws = world()

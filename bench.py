@@ -198,7 +198,12 @@ def main():
     n, nw = synth.n, synth.wires.shape[0]
     # B independent prover contexts per GPU (one stream each), driven by B host threads: the reference's callers
     # already prove concurrently from rayon workers (aggregator/src/circuits/tree.rs:93-103), one circuit per call.
+    t0 = time.perf_counter()
     circs = [Z.ProverCircuit(synth.common, synth.const_sigma_values, is_values=True, device=local_rank) for _ in range(B)]
+    t_create = (time.perf_counter() - t0) / B      # includes the first context's one-time table setup
+    t0 = time.perf_counter()
+    Z.ProverCircuit(synth.common, synth.const_sigma_values, is_values=True, device=local_rank)
+    t_create_warm = time.perf_counter() - t0
     circ = circs[0]
     # pinned host staging for the e2e arm (the reference-side caller would hand over its witness like this)
     pinned = [torch.empty((nw, n), dtype=torch.int64, pin_memory=True) for _ in range(B)]
@@ -321,6 +326,9 @@ def main():
                    "l2": "no flush: one proof streams ~0.5 GB of LDE/leaf data, far above the 126 MB L2",
                    "timer": "host clock between device synchronisations + rank barrier (a step contains host-side Fiat-Shamir "
                             "work between launches); stage_ms and the roofline numbers are CUDA events on the proving stream"},
+        "circuit_create_ms": {"first_contexts_avg": 1000 * t_create, "warm": 1000 * t_create_warm,
+                              "note": "zkb_circuit_create from host values: upload + constants/sigmas iNTT, LDE and Merkle tree on the "
+                                      "device + every work buffer (SURVEY 8f rank 1; cached per circuit by zkb200.batch.ContextPool)"},
         "prove_ms_single_stream": 1000 * t_single / K, "device_ms_per_proof": stages["total"], "stage_ms": stages,
         "e2e": {"value": world * K * B / t_e2e, "unit": UNIT, "ms_per_step": 1000 * t_e2e / K,
                 "h2d_bytes_per_step": int(B * (nw * n * 8 + pis.size * 8)), "d2h_bytes_per_step": int(B * len(proof))},
@@ -387,6 +395,17 @@ def main():
                                "chunk_degree_bits": int(rs.n).bit_length() - 1, "gates": 14,
                                "note": "host-buffer zkb_prove() calls (H2D of the 135 x 2^12 wire matrix inside); synthetic "
                                        "recursion-shaped circuit, recursion gate formulas unpinned against qp-plonky2 (DESIGN.md)"}
+    if world == 1 and not args.no_aggregation:
+        # config #2: voting-shaped circuit (6-gate set, n = 2^8, non-zk, 13 public inputs): latency of one proof
+        vs = Z.SynthCircuit(zk=False, seed=2, **Z.VOTING)
+        vc = Z.ProverCircuit(vs.common, vs.const_sigma_values, is_values=True, device=local_rank)
+        for i in range(3):
+            vp = vc.prove(vs.wires, vs.public_inputs, salt_seed=i)
+        t0 = time.perf_counter()
+        for i in range(K):
+            vp = vc.prove(vs.wires, vs.public_inputs, salt_seed=i)
+        line["voting"] = {"workload": "voting_synth", "degree_bits": int(vs.n).bit_length() - 1, "prove_ms": 1000 * (time.perf_counter() - t0) / K,
+                          "proof_bytes": len(vp), "stage_ms": vc.timings()}
     if sharded_line is not None:
         line["sharded_commit"] = sharded_line
     if world == 1 and not args.no_cpu_baseline:

@@ -143,3 +143,24 @@ def test_aggregate_tree_mirrors_the_reference_level_order():
         aggregate_tree([], 2, prove_chunk, ["s0"])
     with pytest.raises(ValueError):
         aggregate_tree(["a"], 1, prove_chunk, ["s0"])
+
+
+def test_context_pool_builds_each_circuit_once_per_device():
+    sys.path.insert(0, os.path.join(ROOT, "zk-circuits_b200"))
+    from zkb200.batch import ContextPool
+
+    built = []
+
+    def make(device):
+        built.append(device)
+        return object()
+
+    pool = ContextPool(streams=2)
+    a = pool.get([1, 2, 3, 4], 0, make)
+    assert len(a) == 2 and built == [0, 0]
+    assert pool.get((1, 2, 3, 4), 0, make) is a and built == [0, 0]          # same circuit, same GPU: cached
+    b = pool.get([1, 2, 3, 4], 1, make)                                      # same circuit on another GPU
+    c = pool.get([9, 2, 3, 4], 0, make)                                      # next level of the tree: another circuit
+    assert b is not a and c is not a and len(pool) == 3 and (pool.hits, pool.misses) == (1, 3)
+    with pytest.raises(ValueError):
+        ContextPool(0)

@@ -45,7 +45,7 @@ def test_noncanonical_input_rejected(zkb):
 
 
 @pytest.mark.parametrize("width,lg,cap_h", [(1, 5, 0), (4, 6, 2), (5, 6, 6), (8, 7, 4), (9, 8, 4), (16, 4, 4),
-                                            (24, 10, 4), (135, 11, 4), (139, 9, 4), (84, 12, 0)])
+                                            (24, 10, 4), (135, 11, 4), (139, 9, 4), (84, 12, 0), (135, 13, 4), (20, 14, 3), (7, 13, 13)])
 def test_merkle_commit_matches_oracle(zkb, oracle, width, lg, cap_h):
     rng = np.random.default_rng(width * 100 + lg)
     leaves = rand_felts(rng, (width, 1 << lg))

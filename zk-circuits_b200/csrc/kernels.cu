@@ -151,10 +151,15 @@ __global__ void __launch_bounds__(128) merkle_leaves_kernel(const u64* __restric
     }
     store_digest(digests, l, s);
 }
+__global__ void merkle_leaves_wide_kernel(const u64* __restrict__ leaves, size_t col_stride, int width, size_t num_leaves,
+                                          u64* __restrict__ digests);   // defined with the lane-parallel kernels below
 void launch_merkle_leaves(const u64* leaves, size_t col_stride, int width, size_t num_leaves, u64* digests, cudaStream_t st) {
     if (!num_leaves) return;
     ZKB_COUNT_LAUNCH();
-    merkle_leaves_kernel<<<(unsigned)((num_leaves + 127) / 128), 128, 0, st>>>(leaves, col_stride, width, num_leaves, digests);
+    if (num_leaves <= 4096 && width > 4)   // MERKLE_WIDE_MAX_NODES: a leaf per thread is one chain of ceil(width / 8) permutations
+        merkle_leaves_wide_kernel<<<(unsigned)((num_leaves + 7) / 8), 128, 0, st>>>(leaves, col_stride, width, num_leaves, digests);
+    else
+        merkle_leaves_kernel<<<(unsigned)((num_leaves + 127) / 128), 128, 0, st>>>(leaves, col_stride, width, num_leaves, digests);
 }
 
 __global__ void __launch_bounds__(128) merkle_leaves_ext_kernel(const u64* __restrict__ a, const u64* __restrict__ b, int arity,
@@ -275,6 +280,24 @@ __global__ void __launch_bounds__(128) merkle_leaves_ext_wide_kernel(const u64* 
     for (int c = 0; c < width; c += 8) {
         const int k = c + (int)j;
         if (live && j < 8 && k < width) limb_split(((k & 1) ? b : a)[l * arity + (k >> 1)], x0, x1, x2);
+        wide_permute(x0, x1, x2, s_rc, jj);
+    }
+    if (live && j < 4) digests[l * 4 + j] = gl_canon(limb_to_u64(x0, x1, x2));
+}
+// the same for the row leaves of a polynomial batch (column-major, width > 4): the trees of circuits with n <= 2^9
+// (voting-sized) have at most 4096 leaves, far too few threads for one leaf each
+__global__ void __launch_bounds__(128) merkle_leaves_wide_kernel(const u64* __restrict__ leaves, size_t col_stride, int width,
+                                                                 size_t num_leaves, u64* __restrict__ digests) {
+    __shared__ u32 s_rc[3 * P_WIDTH * P_ROUNDS];
+    wide_load_rc(s_rc);
+    const unsigned lane = threadIdx.x & 31, j = lane & 15, jj = j < 12 ? j : 11;
+    const size_t l = ((size_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * 2 + (lane >> 4);
+    const bool live = l < num_leaves;
+    u32 x0 = 0, x1 = 0, x2 = 0;
+#pragma unroll 1
+    for (int c = 0; c < width; c += 8) {
+        const int k = c + (int)j;
+        if (live && j < 8 && k < width) limb_split(leaves[(size_t)k * col_stride + l], x0, x1, x2);
         wide_permute(x0, x1, x2, s_rc, jj);
     }
     if (live && j < 4) digests[l * 4 + j] = gl_canon(limb_to_u64(x0, x1, x2));
@@ -675,6 +698,9 @@ struct QuotientArgs {
     const u64* w; size_t w_stride;
     const u64* z; size_t z_stride;
     u64* out; size_t out_stride;
+    // sliced mode (small circuits, part != nullptr): the launch's work items are spread over blockIdx.y and every slice
+    // stores its raw sums in its own slot part[(slot_base + blockIdx.y)][ch][N]; quotient_combine_kernel adds the slots
+    u64* part; int slot_base;
 };
 
 // (g0, g1) += c * (p0, p1): deliberately NOT inlined — the quotient kernel has ~150 call sites and its straight-line
@@ -714,12 +740,21 @@ __global__ void __launch_bounds__(128, PART == 3 ? 4 : 8) quotient_kernel(Quotie
         ++term;
     };
     const int nterm_perm = nch * (1 + nchunks);     // L0 terms + partial-product checks come first
+    // sliced mode: PART 1 = one slice per challenge's permutation terms + a last slice for its gates; PART 3 = its gates
+    // round-robin over the slices
+    const int slice = blockIdx.y, nsl = gridDim.y;
     if (PART == 1) {
     // L0(x) (Z - 1)
     u64 l0 = f_mul(P.zh[i & rate_mask], gl_inv(f_mul(gl_canon(u64(1) << P.lg_n), f_sub(x, 1))));
-    for (int ch = 0; ch < nch; ++ch) add_term(f_mul(l0, f_sub(z[(size_t)ch * a.z_stride], 1)));
+    for (int ch = 0; ch < nch; ++ch) {
+        if (nsl > 1 && slice != ch) continue;
+        term = ch;
+        add_term(f_mul(l0, f_sub(z[(size_t)ch * a.z_stride], 1)));
+    }
     // partial product checks
     for (int ch = 0; ch < nch; ++ch) {
+        if (nsl > 1 && slice != ch) continue;
+        term = nch + ch * nchunks;
         u64 beta = P.betas[ch], gamma = P.gammas[ch];
         u64 bx = f_mul(beta, x);
         u64 prev = z[(size_t)ch * a.z_stride];
@@ -740,9 +775,11 @@ __global__ void __launch_bounds__(128, PART == 3 ? 4 : 8) quotient_kernel(Quotie
     // gate constraints, filtered
     const int goff = nterm_perm;
     const int nsel = P.num_selectors;
+    int ordinal = 0;             // index of the gate among this launch's gates
     for (int g = 0; g < P.num_gates; ++g) {
         const GateDesc gd = P.gates[g];
         if ((gd.tag == TAG_POSEIDON ? 2 : tag_is_recursion(gd.tag) ? 3 : 1) != PART) continue;
+        if (nsl > 1 && (PART == 1 ? slice != nsl - 1 : (ordinal++ % nsl) != slice)) continue;
         u64 s = cs[(size_t)gd.selector_index * a.cs_stride];
         u64 filter = 1;
         for (u32 r = gd.group_lo; r < gd.group_hi; ++r)
@@ -951,7 +988,11 @@ __global__ void __launch_bounds__(128, PART == 3 ? 4 : 8) quotient_kernel(Quotie
         acc0 = f_add(acc0, f_mul(filter, g0));
         if (nch > 1) acc1 = f_add(acc1, f_mul(filter, g1));
     }
-    if (PART == 1) {
+    if (a.part) {
+        u64* dst = a.part + ((size_t)(a.slot_base + slice) * nch << lgN) + l;
+        dst[0] = acc0;
+        if (nch > 1) dst[N] = acc1;
+    } else if (PART == 1) {
         a.out[l] = acc0;
         if (nch > 1) a.out[a.out_stride + l] = acc1;
     } else if (PART == 3) {
@@ -964,19 +1005,70 @@ __global__ void __launch_bounds__(128, PART == 3 ? 4 : 8) quotient_kernel(Quotie
     }
 }
 
+// out[ch][l] = (sum over slots of part[slot][ch][l]) / Z_H
+__global__ void quotient_combine_kernel(const QuotientParams* p, const u64* part, int nslots, u64* out, size_t out_stride) {
+    const QuotientParams& P = *p;
+    const unsigned lgN = P.lg_n + P.rate_bits;
+    const size_t N = size_t(1) << lgN, l = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if (l >= N) return;
+    const int ch = blockIdx.y, nch = P.num_challenges;
+    u64 acc = 0;
+    for (int s = 0; s < nslots; ++s) acc = f_add(acc, part[((size_t)(s * nch + ch) << lgN) + l]);
+    const u32 i = bitrev32((u32)l, lgN);
+    out[(size_t)ch * out_stride + l] = f_mul(acc, P.zh_inv[i & ((1u << P.rate_bits) - 1)]);
+}
+
+int quotient_slots(const QuotientParams& ph) {
+    int rec = 0;
+    for (int g = 0; g < ph.num_gates; ++g) rec += tag_is_recursion(ph.gates[g].tag);
+    return (ph.num_challenges + 1) + rec + 1;
+}
+
 void launch_quotient(const QuotientParams* params_dev, const QuotientParams& ph, const u64* apow_dev, int nterms,
                      const u64* cs_lde, size_t cs_stride, const u64* wires_lde, size_t w_stride, const u64* zs_lde,
-                     size_t z_stride, u64* out, size_t out_stride, cudaStream_t st) {
-    QuotientArgs a{params_dev, apow_dev, nterms, cs_lde, cs_stride, wires_lde, w_stride, zs_lde, z_stride, out, out_stride};
+                     size_t z_stride, u64* out, size_t out_stride, cudaStream_t st, const QuotientFork* fork) {
+    QuotientArgs a{params_dev, apow_dev, nterms, cs_lde, cs_stride, wires_lde, w_stride, zs_lde, z_stride, out, out_stride, nullptr, 0};
     size_t N = size_t(1) << (ph.lg_n + ph.rate_bits);
-    ZKB_COUNT_LAUNCH();
-    quotient_kernel<1><<<(unsigned)((N + 127) / 128), 128, 0, st>>>(a);
-    if (ph.has_recursion_gates) {
+    const unsigned gx = (unsigned)((N + 127) / 128);
+    if (fork && fork->part) {
+        // small circuit: one thread per point leaves most of the GPU idle (2^15 points = 7 warps per SM) and a thread's gate
+        // list is one long dependency chain, so the three launches run CONCURRENTLY on the circuit's stream and two helper
+        // streams, their work items spread over blockIdx.y, each slice writing its own slot; one small launch adds the slots
+        a.part = fork->part;
+        int rec = 0;
+        for (int g = 0; g < ph.num_gates; ++g) rec += tag_is_recursion(ph.gates[g].tag);
+        const int s1 = ph.num_challenges + 1;
+        ZKB_CUDA_CHECK(cudaEventRecord(fork->fork, st));
+        for (int k = 0; k < 2; ++k) ZKB_CUDA_CHECK(cudaStreamWaitEvent(fork->aux[k], fork->fork, 0));
+        // launch order = CTA dispatch order: the Poseidon launch (one long chain per thread, 256 CTAs at 2^15 points) and
+        // part 1 become resident together; the recursion slices (most CTAs, 128 registers) fill in behind them
+        a.slot_base = s1 + rec;
         ZKB_COUNT_LAUNCH();
-        quotient_kernel<3><<<(unsigned)((N + 127) / 128), 128, 0, st>>>(a);
+        quotient_kernel<2><<<dim3(gx, 1), 128, 0, st>>>(a);
+        a.slot_base = 0;
+        ZKB_COUNT_LAUNCH();
+        quotient_kernel<1><<<dim3(gx, s1), 128, 0, fork->aux[0]>>>(a);
+        if (rec) {
+            a.slot_base = s1;
+            ZKB_COUNT_LAUNCH();
+            quotient_kernel<3><<<dim3(gx, rec), 128, 0, fork->aux[1]>>>(a);
+        }
+        for (int k = 0; k < 2; ++k) {
+            ZKB_CUDA_CHECK(cudaEventRecord(fork->join[k], fork->aux[k]));
+            ZKB_CUDA_CHECK(cudaStreamWaitEvent(st, fork->join[k], 0));
+        }
+        ZKB_COUNT_LAUNCH();
+        quotient_combine_kernel<<<dim3(gx, ph.num_challenges), 128, 0, st>>>(params_dev, fork->part, s1 + rec + 1, out, out_stride);
+        return;
     }
     ZKB_COUNT_LAUNCH();
-    quotient_kernel<2><<<(unsigned)((N + 127) / 128), 128, 0, st>>>(a);
+    quotient_kernel<1><<<gx, 128, 0, st>>>(a);
+    if (ph.has_recursion_gates) {
+        ZKB_COUNT_LAUNCH();
+        quotient_kernel<3><<<gx, 128, 0, st>>>(a);
+    }
+    ZKB_COUNT_LAUNCH();
+    quotient_kernel<2><<<gx, 128, 0, st>>>(a);
 }
 
 // ---------------------------------------------------------------------------------------------

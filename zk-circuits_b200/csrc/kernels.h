@@ -79,9 +79,13 @@ void launch_partial_products(const u64* wires, size_t wire_stride, const u64* si
 size_t partial_products_scratch_words(int num_routed, int chunk, int num_challenges, unsigned lg_n);
 // quotient values at every LDE point (leaf order): out[ch * out_stride + l]
 // apow_dev: [num_challenges][nterms] powers of alpha, nterms = nch*(2+npp) + num_gate_constraints
+// fork: null for the single-stream form (large circuits); otherwise the three launches run concurrently on st and the two
+// helper streams with their gates spread over blockIdx.y, into `part` = quotient_slots() x num_challenges x N words
+struct QuotientFork { u64* part; cudaStream_t aux[2]; cudaEvent_t fork, join[2]; };
+int quotient_slots(const QuotientParams& params_host);
 void launch_quotient(const QuotientParams* params_dev, const QuotientParams& params_host, const u64* apow_dev, int nterms,
                      const u64* cs_lde, size_t cs_stride, const u64* wires_lde, size_t w_stride, const u64* zs_lde,
-                     size_t z_stride, u64* out, size_t out_stride, cudaStream_t st);
+                     size_t z_stride, u64* out, size_t out_stride, cudaStream_t st, const QuotientFork* fork = nullptr);
 // evaluate ncols coefficient polynomials (n each) at the ext point z: out[2*c], out[2*c+1]
 void launch_eval_polys(const u64* coeffs, size_t stride, int ncols, unsigned lg_n, const u64* zpow_a, const u64* zpow_b,
                        u64* out, cudaStream_t st);

@@ -77,6 +77,16 @@ Circuit::Circuit(const uint8_t* common, size_t len, const u64* const_sigma, bool
     zs_vals_.alloc((size_t)nzp * n_);
     zs_.coeff_ptr = zs_vals_.get(); zs_.coeff_stride = n_;
     q_.alloc((size_t)nch * N_);
+    if (lg_N_ <= 16) {           // fewer than ~3 warps per scheduler in a one-thread-per-point launch: slice + overlap
+        size_t nrec = 0;
+        for (auto& gi : cd_.gates) nrec += gi.is_recursion_gate();
+        qpart_.alloc(((size_t)nch + 1 + nrec + 1) * nch * N_);
+        for (auto& a : qfork_.aux) CK(cudaStreamCreateWithFlags(&a, cudaStreamNonBlocking));
+        CK(cudaEventCreateWithFlags(&qfork_.fork, cudaEventDisableTiming));
+        for (auto& e : qfork_.join) CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        qfork_.part = qpart_.get();
+        q_sliced_ = true;
+    }
     quot_.coeff_ptr = q_.get(); quot_.coeff_stride = n_;     // chunk (ch, m) = q[ch*N + m*n ..]
     pp_scratch_.alloc(partial_products_scratch_words((int)cd_.num_routed_wires, (int)cd_.quotient_degree_factor, nch, lg_n_));
     k_is_dev_.alloc(cd_.k_is.size());
@@ -157,6 +167,9 @@ Circuit::~Circuit() {
     if (st_) cudaStreamSynchronize(st_);
     for (auto& kv : level_graphs_) if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
     for (auto& e : ev_) if (e) cudaEventDestroy(e);
+    for (auto& a : qfork_.aux) if (a) { cudaStreamSynchronize(a); cudaStreamDestroy(a); }
+    if (qfork_.fork) cudaEventDestroy(qfork_.fork);
+    for (auto& e : qfork_.join) if (e) cudaEventDestroy(e);
     if (sync_ev_) { cudaEventDestroy(sync_ev_); --g_live_contexts; }
     if (h_stage_) cudaFreeHost(h_stage_);
     if (st_) cudaStreamDestroy(st_);
@@ -304,7 +317,7 @@ void Circuit::run_quotient(const u64* pi_hash, const u64* betas, const u64* gamm
     CK(cudaMemcpyAsync(qparams_dev_.get(), qp, sizeof(QuotientParams), cudaMemcpyHostToDevice, st_));
     CK(cudaMemcpyAsync(apow_dev_.get(), ap, (size_t)nch * nterms * 8, cudaMemcpyHostToDevice, st_));
     launch_quotient(reinterpret_cast<const QuotientParams*>(qparams_dev_.get()), *qp, apow_dev_.get(), nterms, cs_.lde.get(), N_,
-                    wires_.lde.get(), N_, zs_.lde.get(), N_, q_.get(), N_, st_);
+                    wires_.lde.get(), N_, zs_.lde.get(), N_, q_.get(), N_, st_, q_sliced_ ? &qfork_ : nullptr);
     // values on the coset (leaf order) -> coefficients; chunks of n are the committed quotient polynomials
     launch_coset_intt_bitrev(q_.get(), N_, nch, lg_N_, GL_GEN, st_);
 }

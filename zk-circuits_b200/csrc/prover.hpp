@@ -95,6 +95,10 @@ private:
     DevBuf apow_dev_;            // quotient alpha powers [nch][nterms]
     DevBuf fri_apow_;            // 2 * total columns (SoA)
     DevBuf qparams_dev_;         // QuotientParams
+    // small circuits (N <= 2^16): the quotient launches run concurrently, sliced over their gates (kernels.h QuotientFork)
+    DevBuf qpart_;               // [slots][nch][N]
+    QuotientFork qfork_{};
+    bool q_sliced_ = false;
     // FRI
     std::vector<DevBuf> fri_coeffs_;   // per layer (+ final): 2 * m_i (SoA a then b)
     std::vector<DevBuf> fri_values_;   // per layer: 2 * 8 * m_i

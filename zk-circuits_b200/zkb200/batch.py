@@ -73,6 +73,41 @@ def prove_batch(witnesses, provers, prove_fn, gather=True):
     return [p for part in parts for p in part]
 
 
+class ContextPool:
+    """Prover contexts cached by (circuit digest, device): SURVEY.md §8f rank 1. The reference builds its circuit inside every
+    bench iteration (/root/reference/wormhole/prover/benches/prover.rs:14-19) and once per chunk in `aggregate_chunk`
+    (aggregator/src/circuits/tree.rs:111-127) although every chunk of a level shares one CommonCircuitData (tree.rs:64-70);
+    a GPU context costs a constants/sigmas commitment plus ~0.6 GB of buffers, so it is built once per distinct circuit and
+    handed out again. `make(device)` builds one context; `streams` contexts are kept per key."""
+
+    def __init__(self, streams=1):
+        if streams < 1:
+            raise ValueError("streams must be positive")
+        self.streams = streams
+        self._lock = threading.Lock()
+        self._ctx = {}
+        self.hits = self.misses = 0
+
+    def get(self, circuit_digest, device, make):
+        key = (tuple(int(x) for x in circuit_digest), int(device))
+        with self._lock:
+            got = self._ctx.get(key)
+            if got is not None:
+                self.hits += 1
+                return got
+            self.misses += 1
+        made = [make(device) for _ in range(self.streams)]
+        with self._lock:
+            return self._ctx.setdefault(key, made)
+
+    def __len__(self):
+        return len(self._ctx)
+
+    def clear(self):
+        with self._lock:
+            self._ctx.clear()
+
+
 def aggregate_tree(leaf_proofs, branching, prove_chunk, provers):
     """Level-by-level aggregation of `leaf_proofs` into one root proof — the host-side mirror of the reference's
     `aggregate_to_tree` / `aggregate_level` (/root/reference/wormhole/aggregator/src/circuits/tree.rs:55-103): a level's

@@ -157,7 +157,7 @@ void eval_gate_unfiltered(const Gate& g, const typename Ops::T* consts, const ty
             for (size_t i = 0; i < nc; ++i) {
                 A coeff = ext ? A::read(w, 6 + 2 * i) : A::from_base(w[6 + i]);
                 A next = i + 1 == nc ? A::read(w, 0) : A::read(w, start_accs + 2 * i);
-                (next - (acc * alpha + coeff)).push(out);
+                ((acc * alpha + coeff) - next).push(out);      // upstream: acc * alpha + coeff - accs[i]
                 acc = next;
             }
             break;

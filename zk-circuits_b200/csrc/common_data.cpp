@@ -101,7 +101,7 @@ CommonData parse_common_data(const uint8_t* p, size_t len) {
         throw UnsupportedError("quotient_degree_factor must equal 2^rate_bits");
     if (d.selector_indices.size() != d.gates.size()) throw ParseError("selector / gate count mismatch");
     for (u64 s : d.selector_indices) if (s >= d.groups.size()) throw ParseError("selector index out of range");
-    if (d.gates.size() > 16 || d.num_routed_wires > 128 || d.k_is.size() != d.num_routed_wires)
+    if (d.gates.size() > 32 || d.num_routed_wires > 128 || d.k_is.size() != d.num_routed_wires)
         throw UnsupportedError("circuit exceeds the supported gate / routed-wire count");
     if (d.num_routed_wires > d.num_wires || d.num_wires > 1024) throw ParseError("bad wire counts");
     if ((d.num_routed_wires + d.quotient_degree_factor - 1) / d.quotient_degree_factor != d.num_partial_products + 1)

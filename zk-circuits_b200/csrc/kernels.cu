@@ -892,7 +892,7 @@ __global__ void __launch_bounds__(128, PART == 3 ? 4 : 8) quotient_kernel(Quotie
                     else t.a = f_add(t.a, W(6 + j));
                     const int at = j + 1 == nc ? 0 : start_accs + 2 * j;
                     acc = QE{W(at), W(at + 1)};
-                    const QE c = qe_sub(acc, t);
+                    const QE c = qe_sub(t, acc);          // upstream: acc * alpha + coeff - accs[i]
                     add_c(c.a); add_c(c.b);
                 }
                 break;

@@ -61,7 +61,7 @@ struct QuotientParams {
     unsigned lg_n, rate_bits;
     int num_wires, num_routed, num_constants, num_selectors, num_challenges, num_partial_products, qdf;
     int num_gates, num_gate_constraints;
-    GateDesc gates[16];
+    GateDesc gates[32];
     u64 k_is[128];
     u64 betas[4], gammas[4], alphas[4];
     u64 pi_hash[4];

@@ -5,7 +5,7 @@
     python bench.py --gpus N --steps K --warmup W            # CUDA prover (one process per GPU under torchrun)
     python bench.py --impl reference --gpus N --steps K ...  # CPU arm: the oracle's restated Plonky2 prover
 
-A step = `--streams` (default: min(8, host cores per rank)) independent proofs per GPU of the synthetic wormhole-shaped zk circuit (config #1:
+A step = `--streams` (default 8) independent proofs per GPU of the synthetic wormhole-shaped zk circuit (config #1:
 n = 2^14, 135 wires, 6-gate set, 28 FRI queries, 16 PoW bits; proof = 148 932 bytes), each on its own prover context
 and CUDA stream, driven by one host thread each — the way the reference's rayon callers invoke prove(). `value` is
 measured with the witnesses resident in HBM, `e2e` through the host-buffer C-ABI call zkb_prove() (H2D of the wire
@@ -25,7 +25,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, os.path.join(ROOT, "zk-circuits_b200"))
 
 WORKLOAD = "wormhole_zk_synth_n2^14"
-NCU_LDE_TRAFFIC_BYTES = 18952192 + 84903424   # dram__bytes_read.sum + dram__bytes_write.sum, one lde_block_kernel launch
+NCU_LDE_TRAFFIC_BYTES = 18886912 + 82320640   # dram__bytes_read.sum + dram__bytes_write.sum, one lde_block_kernel_t<3, 1024> launch
 METRIC = "wormhole_proofs_per_sec"
 UNIT = "proofs/s"
 
@@ -157,9 +157,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="zkb200", choices=["zkb200", "reference"])
     ap.add_argument("--streams", type=int, default=0,
-                    help="proofs in flight per GPU (independent prover contexts, one host thread each); 0 = auto: "
-                         "min(8, host cores per rank) — every context's host thread spin-waits on its stream, so more "
-                         "threads than cores costs throughput (measured at 8 GPUs / 32 cores: 4 streams 1477 proofs/s, 8 streams 1410)")
+                    help="proofs in flight per GPU (independent prover contexts, one host thread each); 0 = 8. With more proofs "
+                         "in flight than host cores per rank the stream waits sleep-poll instead of spinning (8 GPUs / 32 cores: "
+                         "1622 proofs/s with 8 streams sleep-polling, 1419 with 4 streams spinning)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-sweep", action="store_true", help="skip the LDE/Merkle microbench points (config #3)")
     ap.add_argument("--no-aggregation", action="store_true", help="skip the aggregation-tree measurement (config #4)")
@@ -193,7 +193,7 @@ def main():
 
     W = max(3, args.warmup)
     K = max(1, args.steps)
-    B = args.streams if args.streams > 0 else max(2, min(8, (os.cpu_count() or 8) // max(1, world)))
+    B = args.streams if args.streams > 0 else 8
     synth = Z.SynthCircuit(zk=True, seed=1, **Z.WORMHOLE)
     n, nw = synth.n, synth.wires.shape[0]
     # B independent prover contexts per GPU (one stream each), driven by B host threads: the reference's callers
@@ -254,12 +254,31 @@ def main():
     for i in range(W):
         run_parallel(lambda b: circs[b].prove_resident(pis, salt_seed=5000 + 100 * b + i, out=outs[b]))
     barrier()
+
+    class DeviceTimer:
+        """CUDA events on torch's current stream bracketing the timed region: the start event is recorded after a device
+        synchronise (nothing in flight), the end event after every proving stream has drained, so the elapsed time is the
+        device-timeline time of the K steps, host-side Fiat-Shamir gaps included. The host clock is kept as a cross-check."""
+
+        def __enter__(self):
+            torch.cuda.synchronize()
+            self.e0, self.e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            self.t0 = time.perf_counter()
+            self.e0.record()
+            return self
+
+        def __exit__(self, *a):
+            torch.cuda.synchronize()
+            self.e1.record()
+            self.e1.synchronize()
+            self.host_s = time.perf_counter() - self.t0
+            self.seconds = self.e0.elapsed_time(self.e1) * 1e-3
+
     with ClockSampler(local_rank) as clk:
-        t0 = time.perf_counter()
-        for i in range(K):
-            run_parallel(lambda b: circs[b].prove_resident(pis, salt_seed=2000 * (rank + 1) + 100 * b + i, out=outs[b]))
-        torch.cuda.synchronize()
-        t_res = time.perf_counter() - t0
+        with DeviceTimer() as tm_res:
+            for i in range(K):
+                run_parallel(lambda b: circs[b].prove_resident(pis, salt_seed=2000 * (rank + 1) + 100 * b + i, out=outs[b]))
+        t_res = tm_res.seconds
         barrier()
         # ---- end-to-end arm through zkb_prove() with host buffers ----
         proofs = [None] * B
@@ -270,11 +289,10 @@ def main():
         for i in range(2):
             run_parallel(lambda b: e2e_step(b, i))
         barrier()
-        t0 = time.perf_counter()
-        for i in range(K):
-            run_parallel(lambda b: e2e_step(b, 3000 * (rank + 1) + i))
-        torch.cuda.synchronize()
-        t_e2e = time.perf_counter() - t0
+        with DeviceTimer() as tm_e2e:
+            for i in range(K):
+                run_parallel(lambda b: e2e_step(b, 3000 * (rank + 1) + i))
+        t_e2e = tm_e2e.seconds
     proof = proofs[0]
     barrier()
 
@@ -324,8 +342,10 @@ def main():
         "config": {"workload": WORKLOAD, "degree_bits": 14, "zero_knowledge": True, "num_wires": nw, "proof_bytes": len(proof),
                    "proofs_per_step_per_gpu": B, "parallelism": f"replica x{world} (no collective), {B} proof streams per GPU",
                    "l2": "no flush: one proof streams ~0.5 GB of LDE/leaf data, far above the 126 MB L2",
-                   "timer": "host clock between device synchronisations + rank barrier (a step contains host-side Fiat-Shamir "
-                            "work between launches); stage_ms and the roofline numbers are CUDA events on the proving stream"},
+                   "timer": "CUDA events bracketing the K steps (recorded after a device synchronise on both sides, rank barrier "
+                            "before; a step contains host-side Fiat-Shamir work between launches, which the events include), max "
+                            "over ranks; stage_ms and the roofline numbers are CUDA events on the proving stream",
+                   "host_clock_ms_per_step": 1000 * tm_res.host_s / K},
         "circuit_create_ms": {"first_contexts_avg": 1000 * t_create, "warm": 1000 * t_create_warm,
                               "note": "zkb_circuit_create from host values: upload + constants/sigmas iNTT, LDE and Merkle tree on the "
                                       "device + every work buffer (SURVEY 8f rank 1; cached per circuit by zkb200.batch.ContextPool)"},
@@ -333,11 +353,11 @@ def main():
         "e2e": {"value": world * K * B / t_e2e, "unit": UNIT, "ms_per_step": 1000 * t_e2e / K,
                 "h2d_bytes_per_step": int(B * (nw * n * 8 + pis.size * 8)), "d2h_bytes_per_step": int(B * len(proof))},
         "gpu_launches": int(launches) * B,
-        "roofline": {"kernel": "lde_block_kernel: coset pre-scale + 8 x NTT of the 135 wire columns, n = 2^14 (one launch)",
+        "roofline": {"kernel": "lde_block_kernel_t<3, 1024>: coset pre-scale + 8 x NTT of the 135 wire columns, n = 2^14 (one launch)",
                      "bound": "hbm", "achieved": lde_gbs, "peak": peak, "unit": "GB/s", "frac": lde_gbs / peak,
                      "traffic": NCU_LDE_TRAFFIC_BYTES,
                      "note": "integer-issue bound in practice (47 instr/byte vs 5.7 the chip can issue per HBM byte; DESIGN.md 4.2); "
-                             "traffic = dram read + write of one launch from profiles/r01_ncu_lde_block_v2.md (output partly still in L2)",
+                             "traffic = dram read + write of one launch from profiles/r01_ncu_lde_block_v3.md (output partly still in L2)",
                      "from_values_gbs": 80 * n * nw / ((stages["wires_intt"] + lde_ms) * 1e-3) / 1e9,
                      "peak_source": peak_src, "algorithmic_bytes_per_launch": lde_bytes, "avg_ms": lde_ms},
         "poseidon": {"kernel": "wires Merkle commit (merkle_leaves_kernel + 13 level launches)", "perms_per_launch": perms,

@@ -176,9 +176,16 @@ Circuit::~Circuit() {
 }
 
 // Host waits on the stream ~10 times per proof. Spinning (the runtime's default) gives the lowest latency. With more
-// prover contexts in a process than host cores available to it (8 ranks x 8 streams on a 32-core box) the wait polls
-// and yields instead, so that runnable threads are not starved by spinners. A blocking (interrupt) wait was measured
-// and is much worse here (708 vs 1355 proofs/s at 8 GPUs). ZKB_SYNC=spin|yield|block overrides the choice.
+// proofs in flight in a process than host cores available to it (8 ranks x 8 streams on a 32-core box) the wait polls
+// every ~20 us and sleeps in between instead, so that the threads doing Fiat-Shamir work are not starved by spinners:
+// measured at 8 GPUs / 32 cores, 8 streams per GPU sleep-polling 1622 proofs/s (98 % of 8 x one GPU), 4 streams per GPU
+// spinning 1419, 8 streams yielding 1410 (profiles/r01_bench_n8_sync_modes.json). A blocking (interrupt) wait is much
+// worse (708). ZKB_SYNC=spin|yield|block|sleep overrides the choice.
+static std::atomic<int> g_proofs_in_flight{0};
+struct InFlight {
+    InFlight() { ++g_proofs_in_flight; }
+    ~InFlight() { --g_proofs_in_flight; }
+};
 static int sync_mode() {      // 0 spin, 1 yield, 2 block, 3 sleep-poll
     if (const char* e = std::getenv("ZKB_SYNC")) {
         if (!std::strcmp(e, "sleep")) return 3;
@@ -190,7 +197,7 @@ static int sync_mode() {      // 0 spin, 1 yield, 2 block, 3 sleep-poll
     int local_world = 1;
     if (const char* w = std::getenv("LOCAL_WORLD_SIZE")) local_world = std::atoi(w) > 0 ? std::atoi(w) : 1;
     const unsigned share = cores / (unsigned)local_world;
-    return (share != 0 && (unsigned)g_live_contexts.load() > share) ? 1 : 0;
+    return (share != 0 && (unsigned)g_proofs_in_flight.load() >= share) ? 3 : 0;
 }
 void Circuit::sync() {
     const int mode = sync_mode();
@@ -368,6 +375,7 @@ size_t Circuit::prove_resident(const u64* public_inputs, size_t n_pi, const u64*
     if (!out || cap < psize) throw BufferError(psize);
     check_canonical(public_inputs, n_pi, "public_inputs");
     DeviceGuard g(device_);
+    InFlight in_flight;
 
     const int ncs = cs_.ncols, nw = wires_.ncols, nzp = zs_.ncols, nq = quot_.ncols, nch = (int)cd_.num_challenges;
     const int nall = ncs + nw + nzp + nq;

@@ -383,9 +383,10 @@ def main():
     if world == 1 and not args.no_aggregation:
         # config #4: the aggregator's default tree (branching 2, depth 3: 8 leaf proofs -> 4 + 2 + 1 chunk proofs,
         # aggregator/src/circuits/tree.rs:17-20,55-77) with recursion-shaped chunk circuits (14-gate set, 4 selector groups,
-        # n = 2^12, non-zk; the real recursive-verifier circuit needs the Rust circuit builder). Chunks of a level run
-        # concurrently on their own prover contexts, levels are sequential. Witness generation (Rust side) is not included.
-        rs = Z.SynthCircuit(seed=4, **Z.SynthCircuit.RECURSION)
+        # zero-knowledge like the aggregator's own config — aggregator.rs:21 — so n = 2^14 with the blinding rows; the real
+        # recursive-verifier circuit needs the Rust circuit builder). Chunks of a level run concurrently on their own prover
+        # contexts, levels are sequential. Witness generation (Rust side) is not included.
+        rs = Z.SynthCircuit(zk=True, seed=4, **Z.SynthCircuit.RECURSION)
         S = min(4, B)
         rcircs = [Z.ProverCircuit(rs.common, rs.const_sigma_values, is_values=True, device=local_rank) for _ in range(S)]
         rpinned = torch.empty(rs.wires.shape, dtype=torch.int64, pin_memory=True)
@@ -393,7 +394,7 @@ def main():
         raddr = rpinned.data_ptr()
 
         def prove_chunk(prover, chunk, level, index):
-            return prover.prove(raddr, rs.public_inputs, salt_seed=0)
+            return prover.prove(raddr, rs.public_inputs, salt_seed=1000 * level + index)
 
         leaves = [None] * 8
         for _ in range(3):
@@ -409,10 +410,10 @@ def main():
         for _ in range(reps):
             rcircs[0].prove(raddr, rs.public_inputs, salt_seed=0)
         t_chunk = (time.perf_counter() - t0) / reps
-        line["aggregation"] = {"workload": "aggregation_tree_8_leaves_recursion_synth_n2^12", "leaf_proofs": 8, "branching": 2,
+        line["aggregation"] = {"workload": "aggregation_tree_8_leaves_recursion_zk_synth_n2^14", "leaf_proofs": 8, "branching": 2,
                                "chunk_proofs_per_level": widths, "tree_ms": 1000 * t_tree, "chunk_prove_ms": 1000 * t_chunk,
                                "chunk_stage_ms": rcircs[0].timings(), "chunk_proof_bytes": len(root), "streams": S,
-                               "chunk_degree_bits": int(rs.n).bit_length() - 1, "gates": 14,
+                               "chunk_degree_bits": int(rs.n).bit_length() - 1, "gates": 14, "zero_knowledge": True,
                                "note": "host-buffer zkb_prove() calls (H2D of the 135 x 2^12 wire matrix inside); synthetic "
                                        "recursion-shaped circuit, recursion gate formulas unpinned against qp-plonky2 (DESIGN.md)"}
     if world == 1 and not args.no_aggregation:

@@ -126,10 +126,11 @@ typedef struct zkb_synth zkb_synth;
 int zkb_synth_create(unsigned min_degree_bits, int zk, size_t n_poseidon, size_t n_base_sum, size_t n_arith, size_t n_const,
                      size_t num_public_inputs, uint64_t seed, zkb_synth** out);
 /* recursion-shaped circuit (configs #4/#5: the gate set a recursive-verifier circuit instantiates at
- * wormhole/aggregator/src/circuits/tree.rs:119 — SURVEY.md App. C.2 — with four selector groups, non-zk):
+ * wormhole/aggregator/src/circuits/tree.rs:119 — SURVEY.md App. C.2 — with four selector groups; zk as the aggregator's
+ * chunk circuits are, which inherit the leaf circuit's standard_recursion_zk_config, aggregator.rs:21 / tree.rs:111):
  * recursion_rows[8] = rows of ArithmeticExtension, MulExtension, Reducing, ReducingExtension, RandomAccess,
  * Exponentiation, CosetInterpolation, PoseidonMds on top of the base counts; const_sigma_values is then [6 + 80][n] */
-int zkb_synth_create_recursion(unsigned min_degree_bits, size_t n_poseidon, size_t n_base_sum, size_t n_arith, size_t n_const,
+int zkb_synth_create_recursion(unsigned min_degree_bits, int zk, size_t n_poseidon, size_t n_base_sum, size_t n_arith, size_t n_const,
                                size_t num_public_inputs, uint64_t seed, const size_t recursion_rows[8], zkb_synth** out);
 int zkb_synth_destroy(zkb_synth* s);
 /* number of constant columns (selectors + gate constants) of the synthetic circuit: const_sigma_values has this + 80 columns */

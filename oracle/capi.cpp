@@ -210,11 +210,11 @@ OrcSynth* orc_synth_make(unsigned min_degree_bits, int zk, size_t n_poseidon, si
 }
 // recursion-shaped circuit: counts[8] = rows of ArithmeticExtension, MulExtension, Reducing, ReducingExtension,
 // RandomAccess, Exponentiation, CosetInterpolation, PoseidonMds
-OrcSynth* orc_synth_make_recursion(unsigned min_degree_bits, size_t n_poseidon, size_t n_base_sum, size_t n_arith, size_t n_const,
+OrcSynth* orc_synth_make_recursion(unsigned min_degree_bits, int zk, size_t n_poseidon, size_t n_base_sum, size_t n_arith, size_t n_const,
                                    size_t num_public_inputs, u64 seed, const size_t* counts) {
     try {
         SynthSpec sp;
-        sp.min_degree_bits = min_degree_bits; sp.zk = false;
+        sp.min_degree_bits = min_degree_bits; sp.zk = zk != 0;
         sp.n_poseidon = n_poseidon; sp.n_base_sum = n_base_sum; sp.n_arith = n_arith; sp.n_const = n_const;
         sp.num_public_inputs = num_public_inputs; sp.seed = seed;
         sp.n_arith_ext = counts[0]; sp.n_mul_ext = counts[1]; sp.n_reducing = counts[2]; sp.n_reducing_ext = counts[3];

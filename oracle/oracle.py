@@ -246,12 +246,12 @@ class Synth:
         L = lib()
         if recursion:
             unknown = set(recursion) - set(self.RECURSION_KEYS)
-            if unknown or zk:
-                raise ValueError(f"bad recursion spec {unknown} (recursion circuits are not zero-knowledge)")
+            if unknown:
+                raise ValueError(f"bad recursion spec {unknown}")
             counts = (ctypes.c_size_t * 8)(*[int(recursion.get(k, 0)) for k in self.RECURSION_KEYS])
             L.orc_synth_make_recursion.restype = ctypes.c_void_p
-            L.orc_synth_make_recursion.argtypes = [ctypes.c_uint] + [ctypes.c_size_t] * 5 + [ctypes.c_uint64, ctypes.c_void_p]
-            self._h = L.orc_synth_make_recursion(min_degree_bits, n_poseidon, n_base_sum, n_arith, n_const, num_public_inputs, seed,
+            L.orc_synth_make_recursion.argtypes = [ctypes.c_uint, ctypes.c_int] + [ctypes.c_size_t] * 5 + [ctypes.c_uint64, ctypes.c_void_p]
+            self._h = L.orc_synth_make_recursion(min_degree_bits, int(zk), n_poseidon, n_base_sum, n_arith, n_const, num_public_inputs, seed,
                                                  ctypes.cast(counts, ctypes.c_void_p))
         else:
             L.orc_synth_make.argtypes = [ctypes.c_uint, ctypes.c_int] + [ctypes.c_size_t] * 5 + [ctypes.c_uint64]

@@ -89,7 +89,9 @@ struct SynthSpec {
     size_t num_public_inputs = 16;
     u64 seed = 1;
     // rows of the recursion gate set; any non-zero count switches the circuit to the 14-gate set that
-    // `verify_proof` (aggregator/src/circuits/tree.rs:119) instantiates, with 4 selector groups
+    // `verify_proof` (aggregator/src/circuits/tree.rs:119) instantiates, with 4 selector groups. The aggregator builds its
+    // chunk circuits with the config of the proofs it verifies (tree.rs:111, aggregator.rs:21: standard_recursion_zk_config),
+    // so they are zero-knowledge like the leaf circuit; the tests at tree.rs:165 use the non-zk config
     size_t n_arith_ext = 0, n_mul_ext = 0, n_reducing = 0, n_reducing_ext = 0, n_random_access = 0, n_exp = 0, n_coset = 0,
            n_mds = 0;
 };

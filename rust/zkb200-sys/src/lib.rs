@@ -58,7 +58,7 @@ extern "C" {
     pub fn zkb_quotient(c: *mut zkb_circuit, wires: *const u64, zs_pp: *const u64, public_inputs: *const u64, n_pi: usize,
                         betas: *const u64, gammas: *const u64, alphas: *const u64, out: *mut u64) -> c_int;
 
-    pub fn zkb_synth_create_recursion(min_degree_bits: c_uint, n_poseidon: usize, n_base_sum: usize, n_arith: usize, n_const: usize,
+    pub fn zkb_synth_create_recursion(min_degree_bits: c_uint, zk: c_int, n_poseidon: usize, n_base_sum: usize, n_arith: usize, n_const: usize,
                                       num_public_inputs: usize, seed: u64, recursion_rows: *const usize, out: *mut *mut zkb_synth) -> c_int;
     pub fn zkb_synth_num_constants(s: *const zkb_synth) -> usize;
     pub fn zkb_synth_create(min_degree_bits: c_uint, zk: c_int, n_poseidon: usize, n_base_sum: usize, n_arith: usize,

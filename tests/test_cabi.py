@@ -97,13 +97,13 @@ def test_header_is_plain_c_and_the_c_example_links(zkb, tmp_path):
         assert out.returncode == 0, out.stderr
 
 
-@pytest.mark.parametrize("shape", ["tiny", "tiny_zk", "recursion"])
+@pytest.mark.parametrize("shape", ["tiny", "tiny_zk", "recursion", "recursion_zk"])
 def test_workload_generator_matches_the_oracles(zkb, oracle, shape):
     """zkb_synth_* (host code standing in for the Rust circuit builder + witness generation) emits the same circuit,
     witness and CommonCircuitData bytes as the oracle's generator for the same spec — for the wormhole gate set and for the
     recursion gate set — and the oracle's checker accepts the witness."""
-    if shape == "recursion":
-        spec = dict(seed=3, **oracle.Synth.RECURSION_TINY)
+    if shape.startswith("recursion"):
+        spec = dict(seed=3, zk=shape.endswith("_zk"), **oracle.Synth.RECURSION_TINY)
     else:
         spec = dict(seed=6, zk=shape == "tiny_zk", **oracle.Synth.TINY)
     a = zkb.SynthCircuit(**spec)

@@ -56,9 +56,16 @@ def test_recursion_gate_set_proof_bytes(zkb, oracle):
 
 
 def test_recursion_shaped_circuit_proof_bytes(zkb, oracle):
-    """A recursion-shaped circuit at the size class of one aggregation chunk (n = 2^12, non-zk)."""
+    """A recursion-shaped circuit at the size class of one aggregation chunk (n = 2^12, non-zk as in tree.rs:165)."""
     s, oc, gc, proof = run_case(zkb, oracle, oracle.Synth.RECURSION, False, seed=4)
     assert s.info["degree_bits"] == 12 and len(proof) == gc.proof_size
+
+
+def test_zero_knowledge_recursion_circuit_proof_bytes(zkb, oracle):
+    """The aggregator's chunk circuits inherit the leaf circuit's zk config (aggregator.rs:21, tree.rs:111): 14-gate set,
+    salted batches, n = 2^14."""
+    s, oc, gc, proof = run_case(zkb, oracle, oracle.Synth.RECURSION_TINY, True, seed=3)
+    assert s.info["degree_bits"] == 14 and s.info["num_gates"] == 14
 
 
 def test_explicit_salts(zkb, oracle):

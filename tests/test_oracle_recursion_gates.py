@@ -67,6 +67,17 @@ def test_each_recursion_gate_rejects_a_tampered_wire(oracle, rec, gate):
     assert c.verify(c.prove(w, s.public_inputs)) != ""
 
 
+def test_zero_knowledge_recursion_circuit(oracle):
+    """The aggregator builds its chunk circuits with the leaf circuit's zk config (aggregator.rs:21, tree.rs:111): blinding
+    rows push the degree to 2^14 and every batch is salted."""
+    s = oracle.Synth(zk=True, seed=3, **oracle.Synth.RECURSION_TINY)
+    assert s.check() == "" and s.info["degree_bits"] == 14 and s.info["zero_knowledge"] == 1
+    c = oracle.Circuit(s.common, s.const_sigma_values)
+    proof = c.prove(s.wires, s.public_inputs, salt_seed=9)
+    assert c.verify(proof) == "" and len(proof) == 149324
+    assert oracle.proof_roundtrip(s.common, proof) == proof
+
+
 def test_larger_recursion_circuit(oracle):
     s = oracle.Synth(seed=11, n_poseidon=60, n_base_sum=10, n_arith=20, n_const=6, num_public_inputs=16, n_arith_ext=40,
                      n_mul_ext=10, n_reducing=8, n_reducing_ext=8, n_random_access=12, n_exp=6, n_coset=8, n_mds=3)

@@ -303,14 +303,14 @@ int zkb_synth_create(unsigned min_degree_bits, int zk, size_t n_poseidon, size_t
         return (int)ZKB_OK;
     });
 }
-int zkb_synth_create_recursion(unsigned min_degree_bits, size_t n_poseidon, size_t n_base_sum, size_t n_arith, size_t n_const,
+int zkb_synth_create_recursion(unsigned min_degree_bits, int zk, size_t n_poseidon, size_t n_base_sum, size_t n_arith, size_t n_const,
                                size_t num_public_inputs, uint64_t seed, const size_t recursion_rows[8], zkb_synth** out) {
     return guarded([&] {
         if (!out || !recursion_rows) throw ArgError("null argument");
         *out = nullptr;
         if (min_degree_bits > 20 || num_public_inputs > 1024) throw ArgError("bad synthetic circuit shape");
         SynthSpec sp;
-        sp.min_degree_bits = min_degree_bits; sp.zk = false;
+        sp.min_degree_bits = min_degree_bits; sp.zk = zk != 0;
         sp.n_poseidon = n_poseidon; sp.n_base_sum = n_base_sum; sp.n_arith = n_arith; sp.n_const = n_const;
         sp.num_public_inputs = num_public_inputs; sp.seed = seed;
         sp.n_arith_ext = recursion_rows[0]; sp.n_mul_ext = recursion_rows[1]; sp.n_reducing = recursion_rows[2];

@@ -122,7 +122,6 @@ SynthCircuit make_synth_circuit(const SynthSpec& spec) {
 
     // gate table, selector groups by upstream's greedy rule (extend a group while size + degree < 9)
     const bool recursion = spec.recursion();
-    if (recursion && spec.zk) throw std::runtime_error("recursion-shaped circuits are not zero-knowledge");
     std::vector<u64> bary(16);
     {
         u64 xs[16], w16 = gl_root_of_unity(4);

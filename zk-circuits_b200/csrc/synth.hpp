@@ -13,7 +13,8 @@ struct SynthSpec {
     size_t num_public_inputs = 16;
     u64 seed = 1;
     // rows of the recursion gate set: any non-zero count selects the 14-gate set a recursive-verifier
-    // circuit has (aggregator/src/circuits/tree.rs:119) with its four selector groups; such circuits are not zero-knowledge
+    // circuit has (aggregator/src/circuits/tree.rs:119) with its four selector groups; zk as configured (the aggregator
+    // inherits the leaf circuit's standard_recursion_zk_config, aggregator.rs:21 / tree.rs:111)
     size_t n_arith_ext = 0, n_mul_ext = 0, n_reducing = 0, n_reducing_ext = 0, n_random_access = 0, n_exp = 0, n_coset = 0,
            n_mds = 0;
     bool recursion() const {

@@ -81,7 +81,7 @@ def lib():
                                         ctypes.c_int, u64p, f32p, ctypes.c_int]
         L.zkb_partial_products.argtypes = [ctypes.c_void_p, u64p, u64p, u64p, u64p]
         L.zkb_quotient.argtypes = [ctypes.c_void_p, u64p, u64p, u64p, ctypes.c_size_t, u64p, u64p, u64p, u64p]
-        L.zkb_synth_create_recursion.argtypes = [ctypes.c_uint] + [ctypes.c_size_t] * 5 + [ctypes.c_uint64, ctypes.c_void_p,
+        L.zkb_synth_create_recursion.argtypes = [ctypes.c_uint, ctypes.c_int] + [ctypes.c_size_t] * 5 + [ctypes.c_uint64, ctypes.c_void_p,
                                                  ctypes.POINTER(ctypes.c_void_p)]
         L.zkb_synth_num_constants.restype = ctypes.c_size_t
         L.zkb_synth_num_constants.argtypes = [ctypes.c_void_p]
@@ -266,7 +266,8 @@ class SynthCircuit:
     """Synthetic wormhole-/voting-shaped circuit + satisfying witness (csrc/synth.cpp; host code)."""
 
     RECURSION_KEYS = ("n_arith_ext", "n_mul_ext", "n_reducing", "n_reducing_ext", "n_random_access", "n_exp", "n_coset", "n_mds")
-    # one aggregation chunk's recursive-verifier circuit, n = 2^12 (row mix: an estimate, SURVEY.md App. E item 2)
+    # one aggregation chunk's recursive-verifier circuit: 2^12 rows before blinding, n = 2^14 with zk=True as the aggregator
+    # configures it (row mix: an estimate, SURVEY.md App. E item 2)
     RECURSION = dict(n_poseidon=1600, n_base_sum=260, n_arith=500, n_const=60, num_public_inputs=16, n_arith_ext=800,
                      n_mul_ext=160, n_reducing=120, n_reducing_ext=120, n_random_access=230, n_exp=60, n_coset=112, n_mds=8)
 
@@ -274,10 +275,10 @@ class SynthCircuit:
                  num_public_inputs=16, **recursion):
         h = ctypes.c_void_p()
         if recursion:
-            if set(recursion) - set(self.RECURSION_KEYS) or zk:
-                raise ValueError("bad recursion spec (recursion-shaped circuits are not zero-knowledge)")
+            if set(recursion) - set(self.RECURSION_KEYS):
+                raise ValueError("bad recursion spec")
             rows = (ctypes.c_size_t * 8)(*[int(recursion.get(k, 0)) for k in self.RECURSION_KEYS])
-            _check(lib().zkb_synth_create_recursion(min_degree_bits, n_poseidon, n_base_sum, n_arith, n_const, num_public_inputs,
+            _check(lib().zkb_synth_create_recursion(min_degree_bits, int(zk), n_poseidon, n_base_sum, n_arith, n_const, num_public_inputs,
                                                     seed, ctypes.cast(rows, ctypes.c_void_p), ctypes.byref(h)))
         else:
             _check(lib().zkb_synth_create(min_degree_bits, int(zk), n_poseidon, n_base_sum, n_arith, n_const, num_public_inputs,

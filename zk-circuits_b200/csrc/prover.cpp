@@ -4,6 +4,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <chrono>
+#include <cstdio>
 #include <thread>
 
 namespace zkb {
@@ -20,11 +21,13 @@ void DevBuf::alloc(size_t words) {
     if (words == 0) return;
     CK(cudaMalloc(&p_, words * sizeof(u64)));
     words_ = words;
+    owned_ = true;
 }
 void DevBuf::release() {
-    if (p_) cudaFree(p_);
+    if (p_ && owned_) cudaFree(p_);
     p_ = nullptr;
     words_ = 0;
+    owned_ = true;
 }
 
 namespace {
@@ -42,6 +45,13 @@ void check_canonical(const u64* v, size_t n, const char* what) {
 Circuit::Circuit(const uint8_t* common, size_t len, const u64* const_sigma, bool is_values, const u64* digest, int device)
     : cd_(parse_common_data(common, len)), device_(device) {
     if (!const_sigma) throw ArgError("const_sigma is null");
+    // ZKB_TRACE=1: wall-clock checkpoints of the context build on stderr (which part of zkb_circuit_create costs what)
+    const bool trace = std::getenv("ZKB_TRACE") != nullptr;
+    const auto t_begin = std::chrono::steady_clock::now();
+    auto mark = [&](const char* what) {
+        if (trace) std::fprintf(stderr, "[zkb create] %-28s %8.3f ms\n", what,
+                                std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_begin).count());
+    };
     int ndev = 0;
     CK(cudaGetDeviceCount(&ndev));
     if (device < 0 || device >= ndev) throw ArgError("bad device index");
@@ -59,62 +69,67 @@ Circuit::Circuit(const uint8_t* common, size_t len, const u64* const_sigma, bool
     const int nzp = (int)cd_.num_zs_pp(), nq = (int)cd_.num_quotient_polys(), nch = (int)cd_.num_challenges;
     const int salt = (int)cd_.salt_size();
     const unsigned cap_h = (unsigned)cd_.cap_height;
+    mark("stream, events, tables");
     check_canonical(const_sigma, (size_t)ncs * n_, "const_sigma");
+    mark("host canonical check");
 
+    // plan every device buffer, then carve them out of one allocation (256-byte aligned slices)
+    std::vector<std::pair<DevBuf*, size_t>> plan;
+    auto want = [&](DevBuf& b, size_t words) { plan.push_back({&b, words}); };
     auto init_batch = [&](BatchDev& b, int ncols, int s, bool own_coeffs) {
         b.ncols = ncols;
         b.salt = s;
-        if (own_coeffs) { b.coeffs.alloc((size_t)ncols * n_); b.coeff_ptr = b.coeffs.get(); b.coeff_stride = n_; }
-        b.lde.alloc((size_t)(ncols + s) * N_);
-        b.digests.alloc(merkle_digest_count(N_, cap_h) * 4);
+        if (own_coeffs) want(b.coeffs, (size_t)ncols * n_);
+        want(b.lde, (size_t)(ncols + s) * N_);
+        want(b.digests, merkle_digest_count(N_, cap_h) * 4);
     };
     init_batch(cs_, ncs, 0, true);
     init_batch(wires_, nw, salt, true);
     init_batch(zs_, nzp, salt, false);
     init_batch(quot_, nq, salt, false);
-    sigma_vals_.alloc((size_t)cd_.num_routed_wires * n_);
-    wires_vals_.alloc((size_t)nw * n_);
-    zs_vals_.alloc((size_t)nzp * n_);
-    zs_.coeff_ptr = zs_vals_.get(); zs_.coeff_stride = n_;
-    q_.alloc((size_t)nch * N_);
+    want(sigma_vals_, (size_t)cd_.num_routed_wires * n_);
+    want(wires_vals_, (size_t)nw * n_);
+    want(zs_vals_, (size_t)nzp * n_);
+    want(q_, (size_t)nch * N_);
     if (lg_N_ <= 16) {           // fewer than ~3 warps per scheduler in a one-thread-per-point launch: slice + overlap
         size_t nrec = 0;
         for (auto& gi : cd_.gates) nrec += gi.is_recursion_gate();
-        qpart_.alloc(((size_t)nch + 1 + nrec + 1) * nch * N_);
+        want(qpart_, ((size_t)nch + 1 + nrec + 1) * nch * N_);
         for (auto& a : qfork_.aux) CK(cudaStreamCreateWithFlags(&a, cudaStreamNonBlocking));
         CK(cudaEventCreateWithFlags(&qfork_.fork, cudaEventDisableTiming));
         for (auto& e : qfork_.join) CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
-        qfork_.part = qpart_.get();
         q_sliced_ = true;
     }
-    quot_.coeff_ptr = q_.get(); quot_.coeff_stride = n_;     // chunk (ch, m) = q[ch*N + m*n ..]
-    pp_scratch_.alloc(partial_products_scratch_words((int)cd_.num_routed_wires, (int)cd_.quotient_degree_factor, nch, lg_n_));
-    k_is_dev_.alloc(cd_.k_is.size());
-    zpow_.alloc(4 * n_);
+    want(pp_scratch_, partial_products_scratch_words((int)cd_.num_routed_wires, (int)cd_.quotient_degree_factor, nch, lg_n_));
+    want(k_is_dev_, cd_.k_is.size());
+    want(zpow_, 4 * n_);
     const int nall = ncs + nw + nzp + nq;
-    openings_dev_.alloc(2 * (size_t)(nall + nch));
+    want(openings_dev_, 2 * (size_t)(nall + nch));
     const int nterms = nch * (2 + (int)cd_.num_partial_products) + (int)cd_.num_gate_constraints;
-    apow_dev_.alloc((size_t)nch * nterms);
-    fri_apow_.alloc(2 * (size_t)nall);
-    qparams_dev_.alloc((sizeof(QuotientParams) + 7) / 8);
+    want(apow_dev_, (size_t)nch * nterms);
+    want(fri_apow_, 2 * (size_t)nall);
+    want(qparams_dev_, (sizeof(QuotientParams) + 7) / 8);
     // FRI layers
     size_t m = n_;
     const size_t L = cd_.reduction_arity_bits.size();
+    fri_coeffs_.resize(L + 1);
+    fri_values_.resize(L);
+    fri_digests_.resize(L);
     for (size_t i = 0; i <= L; ++i) {
-        fri_coeffs_.emplace_back(2 * m);
+        want(fri_coeffs_[i], 2 * m);
         if (i < L) {
             size_t M = m << cd_.rate_bits;
-            fri_values_.emplace_back(2 * M);
+            want(fri_values_[i], 2 * M);
             size_t leaves = M >> cd_.reduction_arity_bits[i];
-            fri_digests_.emplace_back(merkle_digest_count(leaves, cap_h) * 4);
+            want(fri_digests_[i], merkle_digest_count(leaves, cap_h) * 4);
             fri_cap_off_.push_back(0);
             m >>= cd_.reduction_arity_bits[i];
         }
     }
-    pow_dev_.alloc(16);
-    flag_dev_.alloc(1);
+    want(pow_dev_, 16);
+    want(flag_dev_, 1);
     const size_t nqr = cd_.num_query_rounds;
-    query_idx_dev_.alloc(((1 + L) * nqr + 1) / 2 + 1);
+    want(query_idx_dev_, ((1 + L) * nqr + 1) / 2 + 1);
     // query gather buffer
     size_t qwords = 0;
     {
@@ -126,11 +141,28 @@ Circuit::Circuit(const uint8_t* common, size_t len, const u64* const_sigma, bool
             qwords += nqr * ((size_t(2) << ab) + 4 * (bits >= cap_h ? bits - cap_h : 0));
         }
     }
-    query_out_dev_.alloc(qwords);
+    want(query_out_dev_, qwords);
+    {
+        auto round32 = [](size_t w) { return (w + 31) & ~size_t(31); };
+        size_t total = 0;
+        for (auto& pw : plan) total += round32(pw.second);
+        arena_.alloc(total);
+        size_t off = 0;
+        for (auto& pw : plan) {
+            if (pw.second) pw.first->view(arena_.get() + off, pw.second);
+            off += round32(pw.second);
+        }
+    }
+    for (BatchDev* b : {&cs_, &wires_}) { b->coeff_ptr = b->coeffs.get(); b->coeff_stride = n_; }
+    zs_.coeff_ptr = zs_vals_.get(); zs_.coeff_stride = n_;
+    quot_.coeff_ptr = q_.get(); quot_.coeff_stride = n_;     // chunk (ch, m) = q[ch*N + m*n ..]
+    if (q_sliced_) qfork_.part = qpart_.get();
     h_stage_words_ = qwords + 4096 + 2 * (size_t)(nall + nch) + 2 * cd_.final_poly_len() + 2 * nall;
     h_qp_off_ = h_stage_words_;     // separate region for the quotient parameters + alpha powers
     h_stage_words_ += (sizeof(QuotientParams) + 7) / 8 + (size_t)nch * nterms + 8;
+    mark("device buffers");
     CK(cudaMallocHost(&h_stage_, h_stage_words_ * sizeof(u64)));
+    mark("pinned staging");
 
     CK(cudaMemcpyAsync(k_is_dev_.get(), cd_.k_is.data(), cd_.k_is.size() * 8, cudaMemcpyHostToDevice, st_));
     // ---- constants/sigmas commitment (the part of CircuitBuilder::build the prover needs) ----
@@ -147,7 +179,9 @@ Circuit::Circuit(const uint8_t* common, size_t len, const u64* const_sigma, bool
     }
     cs_cap_.resize((size_t(4)) << cap_h);
     commit_batch(cs_, 0, nullptr, 0, h_stage_);
+    mark("uploads and launches queued");
     sync();
+    mark("constants/sigmas commitment");
     std::memcpy(cs_cap_.data(), h_stage_, cs_cap_.size() * 8);
     // circuit_digest = hash_no_pad(cap ‖ hash_pad([]) ‖ [degree_bits])   
     std::vector<u64> parts(cs_cap_);

@@ -31,14 +31,16 @@ public:
     ~DevBuf() { release(); }
     DevBuf(const DevBuf&) = delete;
     DevBuf& operator=(const DevBuf&) = delete;
-    DevBuf(DevBuf&& o) noexcept : p_(o.p_), words_(o.words_) { o.p_ = nullptr; o.words_ = 0; }
+    DevBuf(DevBuf&& o) noexcept : p_(o.p_), words_(o.words_), owned_(o.owned_) { o.p_ = nullptr; o.words_ = 0; }
     void alloc(size_t words);
+    void view(u64* p, size_t words) { release(); p_ = p; words_ = words; owned_ = false; }   // a slice of someone else's allocation
     void release();
     u64* get() const { return p_; }
     size_t words() const { return words_; }
 private:
     u64* p_ = nullptr;
     size_t words_ = 0;
+    bool owned_ = true;
 };
 
 // one committed polynomial batch on the device (PolynomialBatch): coefficients + LDE (leaf order) + tree
@@ -84,6 +86,9 @@ private:
     size_t n_ = 0, N_ = 0;
     unsigned lg_n_ = 0, lg_N_ = 0;
 
+    // every device buffer of a context is a slice of ONE allocation: cudaMalloc / cudaFree cost 3-15 ms per call on the
+    // B200 boxes (35 separate buffers made zkb_circuit_create 100-500 ms and the destructor 300 ms; one arena: a few ms)
+    DevBuf arena_;
     BatchDev cs_, wires_, zs_, quot_;
     DevBuf sigma_vals_;          // [num_routed][n] values over H, natural order
     DevBuf wires_vals_;          // [num_wires][n]

@@ -68,6 +68,16 @@ def test_zero_knowledge_recursion_circuit_proof_bytes(zkb, oracle):
     assert s.info["degree_bits"] == 14 and s.info["num_gates"] == 14
 
 
+@pytest.mark.parametrize("npi", [0, 1, 8, 9, 17])
+def test_minimal_degree_and_public_input_counts(zkb, oracle, npi):
+    """Edge shapes: the smallest circuits the generator makes (n = 8: 64 LDE points, no FRI reduction layer, a 16-digest cap
+    two levels above the leaves) with 0 / 1 / a full sponge block / one more / two blocks and one more public inputs
+    (hash_no_pad([]) is the zero digest: no permutation)."""
+    spec = dict(n_poseidon=3, n_base_sum=1, n_arith=1, n_const=2, num_public_inputs=npi)
+    s, oc, gc, proof = run_case(zkb, oracle, spec, False, seed=2)
+    assert s.info["degree_bits"] == 3 and s.info["reduction_arity_bits"] == []
+
+
 def test_explicit_salts(zkb, oracle):
     s = oracle.Synth(zk=True, seed=8, **oracle.Synth.TINY)
     oc = oracle.Circuit(s.common, s.const_sigma_values)

@@ -231,7 +231,7 @@ SynthCircuit make_synth_circuit(const SynthSpec& spec) {
     size_t poseidon_used = 0;
     {
         size_t npi = spec.num_public_inputs;
-        size_t nchunks = std::max<size_t>(1, (npi + 7) / 8);
+        size_t nchunks = (npi + 7) / 8;      // no public inputs: hash_no_pad([]) is the zero digest, no permutation
         u32 prev = 0;
         u64 state[12] = {0};
         for (size_t k = 0; k < nchunks; ++k) {
@@ -252,7 +252,8 @@ SynthCircuit make_synth_circuit(const SynthSpec& spec) {
         u64 h[4]; h_hash_no_pad(out.public_inputs.data(), out.public_inputs.size(), h);
         for (int i = 0; i < 4; ++i) {
             if (state[i] != h[i]) throw std::runtime_error("synthetic PI sponge mismatch");
-            copy_from(pi_row, (u32)i, Pooled{state[i], {prev, (u32)(12 + i)}});
+            if (nchunks == 0) copy_from(pi_row, (u32)i, ZERO);
+            else copy_from(pi_row, (u32)i, Pooled{state[i], {prev, (u32)(12 + i)}});
         }
     }
 

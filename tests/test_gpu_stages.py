@@ -170,6 +170,32 @@ def test_recursion_gate_quotient_matches_oracle(zkb, oracle):
     assert np.array_equal(q, tr.quotient_chunks)
 
 
+@pytest.mark.parametrize("recursion,min_bits", [(False, 0), (True, 0), (True, 14)])
+def test_quotient_on_edge_values(zkb, oracle, recursion, min_bits):
+    """Carry / borrow corners of the device field arithmetic through every gate evaluator: wires, Z / partial-product
+    columns, public inputs and challenges drawn from {0, 1, 2, p-1, p-2, 2^32-1, 2^32, 2^32+1, 2^63, p - 2^32, ...}. The
+    witness does not satisfy the circuit — compute_quotient_polys is a pointwise computation on the coset followed by an
+    inverse transform, defined for any input — and every chunk must still equal the oracle's bit for bit."""
+    P = oracle.P
+    edge = np.array([0, 1, 2, 7, P - 1, P - 2, P - 7, 2**32 - 1, 2**32, 2**32 + 1, 2**63, 2**63 - 1, P - 2**32, P - 2**32 + 1,
+                     2**64 - 2**33, 0xFFFFFFFE00000002, 0x00000001FFFFFFFF], dtype=np.uint64)
+    spec = oracle.Synth.RECURSION_TINY if recursion else oracle.Synth.TINY
+    s = oracle.Synth(seed=21, min_degree_bits=min_bits, **spec)     # 2^14: the single-stream (unsliced) launch sequence
+    oc = oracle.Circuit(s.common, s.const_sigma_values)
+    gc = zkb.ProverCircuit(s.common, s.const_sigma_values, is_values=True)
+    rng = np.random.default_rng(5)
+    for trial in range(3 if min_bits == 0 else 1):
+        wires = edge[rng.integers(0, len(edge), size=s.wires.shape)]
+        zs = edge[rng.integers(0, len(edge), size=(20, s.n))]
+        pis = edge[rng.integers(0, len(edge), size=s.public_inputs.shape)]
+        ch = [int(x) for x in edge[rng.integers(0, len(edge), size=6)]]
+        if trial == 0:
+            ch = [P - 1, 2**32 - 1, 1, P - 2**32, 2**32, P - 2]
+        want = oc.quotient(wires, zs, pis, ch[0:2], ch[2:4], ch[4:6])
+        got = gc.quotient(wires, zs, pis, ch[0:2], ch[2:4], ch[4:6], 16, s.n)
+        assert np.array_equal(got, want)
+
+
 @pytest.mark.parametrize("lg_n,ncols", [(9, 7), (14, 3), (16, 2)])
 def test_coset_sharded_commit_parts_concatenate_to_the_full_cap(zkb, oracle, lg_n, ncols):
     """zkb_commit_cosets (one GPU's share of a coset-sharded commitment) for G = 1, 2, 4, 8 emulated ranks on one GPU:

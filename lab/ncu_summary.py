@@ -1,12 +1,13 @@
 #!/usr/bin/env python3
-"""Markdown summary of an `ncu --set full` report (first captured launch): python lab/ncu_summary.py rep.ncu-rep [units] > profiles/x.md
+"""Markdown summary of an `ncu --set full` report: python lab/ncu_summary.py rep.ncu-rep [units] [launch index, default 0] > profiles/x.md
 `units` = work units the launch processed (permutations, field elements ...) for the per-unit instruction count."""
 import csv, io, subprocess, sys, collections
 rep = sys.argv[1]
 units = float(sys.argv[2]) if len(sys.argv) > 2 else None
 raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(raw)))
-h, unit_row, d = rows[0], dict(zip(rows[0], rows[1])), dict(zip(rows[0], rows[2]))
+which = int(sys.argv[3]) if len(sys.argv) > 3 else 0
+h, unit_row, d = rows[0], dict(zip(rows[0], rows[1])), dict(zip(rows[0], rows[2 + which]))
 def g(k):
     v = d.get(k, "")
     try: return float(v.replace(",", ""))
@@ -45,10 +46,12 @@ src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_ou
 rows = list(csv.reader(io.StringIO(src)))
 hi = [i for i, r in enumerate(rows) if r and r[0] == "Address"]
 if hi:
-    hh = rows[hi[0]]
+    lo = hi[min(which, len(hi) - 1)]                       # one "Address" header per captured launch
+    end = hi[which + 1] if which + 1 < len(hi) else len(rows)
+    hh = rows[lo]
     isrc, iex = hh.index("Source"), hh.index("Thread Instructions Executed")
     mix = collections.Counter()
-    for r in rows[hi[0] + 1:]:
+    for r in rows[lo + 1:end]:
         if len(r) <= iex or not r[isrc].split(): continue
         t = r[isrc].split()
         mix[t[1] if t[0].startswith("@") else t[0]] += float(r[iex] or 0)

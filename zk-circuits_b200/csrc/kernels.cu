@@ -752,6 +752,35 @@ __global__ void __launch_bounds__(128, PART == 3 ? 4 : 8) quotient_kernel(Quotie
         add_term(f_mul(l0, f_sub(z[(size_t)ch * a.z_stride], 1)));
     }
     // partial product checks
+    if (nsl == 1 && nch == 2) {
+        // both challenges in one pass over the routed wires: every wire and sigma value is loaded once and the four
+        // running products are independent multiply chains. (Measured: the same 0.33 ms as the per-challenge form below —
+        // this loop is 54 % of the launch's instructions, 640 modular multiplies per point, and runs at the ~55 % issue
+        // ceiling of IMAD.WIDE + carry-chain code, so the saved loads do not show; profiles/r01_ncu_quotient_v3.md)
+        const u64 b0 = P.betas[0], b1 = P.betas[1], gm0 = P.gammas[0], gm1 = P.gammas[1];
+        const u64 bx0 = f_mul(b0, x), bx1 = f_mul(b1, x);
+        u64 prev0 = z[0], prev1 = z[a.z_stride];
+        for (int k = 0; k < nchunks; ++k) {
+            const u64 next0 = k < npp ? z[(size_t)(nch + k) * a.z_stride] : a.z[l_next];
+            const u64 next1 = k < npp ? z[(size_t)(nch + npp + k) * a.z_stride] : a.z[a.z_stride + l_next];
+            u64 num0 = 1, den0 = 1, num1 = 1, den1 = 1;
+            const int j1 = min(P.num_routed, (k + 1) * chunk);
+#pragma unroll 2
+            for (int j = k * chunk; j < j1; ++j) {
+                const u64 wj = w[(size_t)j * a.w_stride], sj = cs[(size_t)(P.num_constants + j) * a.cs_stride], kj = P.k_is[j];
+                const u64 wg0 = f_add(wj, gm0), wg1 = f_add(wj, gm1);
+                num0 = f_mul(num0, f_add(wg0, f_mul(bx0, kj)));
+                den0 = f_mul(den0, f_add(wg0, f_mul(b0, sj)));
+                num1 = f_mul(num1, f_add(wg1, f_mul(bx1, kj)));
+                den1 = f_mul(den1, f_add(wg1, f_mul(b1, sj)));
+            }
+            term = nch + k;
+            add_term(f_sub(f_mul(prev0, num0), f_mul(next0, den0)));
+            term = nch + nchunks + k;
+            add_term(f_sub(f_mul(prev1, num1), f_mul(next1, den1)));
+            prev0 = next0; prev1 = next1;
+        }
+    } else {
     for (int ch = 0; ch < nch; ++ch) {
         if (nsl > 1 && slice != ch) continue;
         term = nch + ch * nchunks;
@@ -770,6 +799,7 @@ __global__ void __launch_bounds__(128, PART == 3 ? 4 : 8) quotient_kernel(Quotie
             add_term(f_sub(f_mul(prev, num), f_mul(next, den)));
             prev = next;
         }
+    }
     }
     }
     // gate constraints, filtered

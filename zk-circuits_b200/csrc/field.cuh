@@ -72,10 +72,7 @@ ZKB_HD void mul128(u64 a, u64 b, u64& lo, u64& hi) {
 #endif
 }
 
-#if defined(__CUDA_ARCH__)
-// ---- device fast paths: 32-bit limbs, carry flags through add.cc/addc (IADD3/IADD3.X/IMAD.X in SASS), no
-// compare+select sequences. The limb algorithms were checked exhaustively on edge values on the host. ----
-
+#if defined(__CUDACC__)
 // 64-bit <-> 2 x 32-bit through mov.b64: a C-level (u32)(v >> 32) makes ptxas emit a stray "VIADD hi, hi, 0" per use
 __device__ __forceinline__ void gl_unpack(u64 v, u32& lo, u32& hi) { asm("mov.b64 {%0, %1}, %2;" : "=r"(lo), "=r"(hi) : "l"(v)); }
 __device__ __forceinline__ u64 gl_pack(u32 lo, u32 hi) { u64 v; asm("mov.b64 %0, {%1, %2};" : "=l"(v) : "r"(lo), "r"(hi)); return v; }
@@ -84,6 +81,11 @@ __device__ __forceinline__ void gl_wide(u32 a, u32 b, u32& lo, u32& hi) {
     asm("mul.wide.u32 %0, %1, %2;" : "=l"(v) : "r"(a), "r"(b));
     gl_unpack(v, lo, hi);
 }
+#endif
+#if defined(__CUDA_ARCH__)
+// ---- device fast paths: 32-bit limbs, carry flags through add.cc/addc (IADD3/IADD3.X/IMAD.X in SASS), no
+// compare+select sequences. The limb algorithms were checked exhaustively on edge values on the host. ----
+
 // (a1:a0) * (b1:b0) -> 128-bit product limbs r0..r3: 4 x IMAD.WIDE.U32 + two 3-limb carry chains
 __device__ __forceinline__ void gl_mul128_limbs(u32 a0, u32 a1, u32 b0, u32 b1, u32& r0, u32& r1, u32& r2, u32& r3) {
     u32 p00h, p01l, p01h, p10l, p10h, p11l, p11h;
@@ -251,30 +253,35 @@ inline u64 gl_root_of_unity(unsigned k) {
 #if defined(__CUDACC__)
 // ---- device-only canonical arithmetic on carry flags (5 / 7 / ~25 instructions; the portable gl_add / gl_sub / gl_mul
 // compile to compare + select sequences of 9-12 on top) ----
-// canonical in, canonical out
+// Pipe balance (lab/pipe_balance.cu, measured on B200): alu-pipe instructions (IADD3, IADD3.X, SEL, ISETP, LOP3) and 32-bit
+// IMADs issue on alternate cycles, so code made of carry chains is bound by its alu count while the FMA pipe idles. Every step
+// of these forms that only CONSUMES a carry is therefore written as madc.lo (IMAD.X on the FMA pipe): butterflies 1.22x,
+// butterfly + multiply 1.16x against the all-IADD3.X forms. They rely on the carry flag's polarity after sub.cc / subc.cc as
+// seen by a following madc: it is the hardware carry of a + ~b + 1, i.e. 1 = NO borrow (subc compensates by itself, madc does
+// not). lab/pipe_balance.cu checks the forms against the plain ones on 2 M cases; the parity tests would catch a toolchain that
+// changed it.
+// canonical in, canonical out: 3 alu + 2 fma
 ZKB_D u64 f_sub(u64 a, u64 b) {
-    u32 o0, o1;
+    u32 a0, a1, b0, b1, o0, o1;
+    gl_unpack(a, a0, a1);
+    gl_unpack(b, b0, b1);
     asm("{\n\t.reg .u32 m;\n\t"
         "sub.cc.u32 %0, %2, %4;\n\t"
         "subc.cc.u32 %1, %3, %5;\n\t"
         "subc.u32 m, 0, 0;\n\t"              // borrow ? 0xffffffff : 0
         "sub.cc.u32 %0, %0, m;\n\t"          // + p  ==  - (2^32 - 1)  (mod 2^64)
-        "subc.u32 %1, %1, 0;\n\t}"
-        : "=&r"(o0), "=&r"(o1) : "r"((u32)a), "r"((u32)(a >> 32)), "r"((u32)b), "r"((u32)(b >> 32)));
-    return ((u64)o1 << 32) | o0;
+        "madc.lo.u32 %1, %6, 1, %1;\n\t"     // hi + 0xffffffff + (no second borrow)  ==  hi - second borrow
+        "}" : "=&r"(o0), "=&r"(o1) : "r"(a0), "r"(a1), "r"(b0), "r"(b1), "r"(0xffffffffu));
+    return gl_pack(o0, o1);
 }
 ZKB_D u64 f_add(u64 a, u64 b) {               // a - (p - b); p - b in (0, p], and a < p, so one borrow fix is exact
-    u32 o0, o1;
-    asm("{\n\t.reg .u32 m, n0, n1;\n\t"
-        "sub.cc.u32 n0, 1, %4;\n\t"
-        "subc.u32 n1, 0xffffffff, %5;\n\t"
-        "sub.cc.u32 %0, %2, n0;\n\t"
-        "subc.cc.u32 %1, %3, n1;\n\t"
-        "subc.u32 m, 0, 0;\n\t"
-        "sub.cc.u32 %0, %0, m;\n\t"
-        "subc.u32 %1, %1, 0;\n\t}"
-        : "=&r"(o0), "=&r"(o1) : "r"((u32)a), "r"((u32)(a >> 32)), "r"((u32)b), "r"((u32)(b >> 32)));
-    return ((u64)o1 << 32) | o0;
+    u32 b0, b1, n0, n1;
+    gl_unpack(b, b0, b1);
+    asm("{\n\t"
+        "sub.cc.u32 %0, 1, %2;\n\t"
+        "subc.u32 %1, 0xffffffff, %3;\n\t"
+        "}" : "=&r"(n0), "=&r"(n1) : "r"(b0), "r"(b1));
+    return f_sub(a, gl_pack(n0, n1));
 }
 
 // r >= p  <=>  high word all ones and low word >= 1; then r - p = low - 1
@@ -283,7 +290,44 @@ ZKB_D u64 f_canon(u64 r) {
     if (hi == 0xFFFFFFFFu && lo != 0) { lo -= 1; hi = 0; }
     return ((u64)hi << 32) | lo;
 }
-ZKB_D u64 f_mul(u64 a, u64 b) { return f_canon(gl_mul_lazy(a, b)); }
+// canonical product of any two u64: the same product limbs and fold as gl_mul_lazy / gl_reduce_limbs (which the Poseidon code,
+// FMA-pipe bound, keeps), with the carry-consuming steps on the FMA pipe: 5 alu + 5 fma in the fold instead of 9 + 2
+ZKB_D u64 f_mul(u64 a, u64 b) {
+    u32 a0, a1, b0, b1, r0, p00h, p01l, p01h, p10l, p10h, p11l, p11h, r1, r2, r3;
+    gl_unpack(a, a0, a1);
+    gl_unpack(b, b0, b1);
+    gl_wide(a0, b0, r0, p00h);
+    gl_wide(a0, b1, p01l, p01h);
+    gl_wide(a1, b0, p10l, p10h);
+    gl_wide(a1, b1, p11l, p11h);
+    const u32 zero = 0, ones = 0xffffffffu;
+    asm("{\n\t"
+        "add.cc.u32 %0, %3, %4;\n\t"        // r1 = p00.hi + p01.lo
+        "addc.cc.u32 %1, %5, %7;\n\t"       // r2 = p01.hi + p10.hi + c
+        "madc.lo.u32 %2, %9, 1, %10;\n\t"   // r3 = p11.hi + c
+        "add.cc.u32 %0, %0, %6;\n\t"        // r1 += p10.lo
+        "addc.cc.u32 %1, %1, %8;\n\t"       // r2 += p11.lo + c
+        "madc.lo.u32 %2, %2, 1, %10;\n\t"
+        "}" : "=&r"(r1), "=&r"(r2), "=&r"(r3)
+            : "r"(p00h), "r"(p01l), "r"(p01h), "r"(p10l), "r"(p10h), "r"(p11l), "r"(p11h), "r"(zero));
+    u64 A;
+    asm("mad.wide.u32 %0, %1, 0xffffffff, %2;" : "=l"(A) : "r"(r2), "l"(gl_pack(r0, 0)));
+    u32 A0, A1, o0, o1;
+    gl_unpack(A, A0, A1);
+    asm("{\n\t.reg .u32 mb, mc;\n\t"
+        "add.cc.u32 %1, %3, %4;\n\t"        // high limb + r1 -> carry
+        "madc.lo.u32 mc, %6, 0, %6;\n\t"    // carry (0 / 1)
+        "sub.cc.u32 %0, %2, %5;\n\t"        // - r3 -> borrow
+        "subc.cc.u32 %1, %1, 0;\n\t"
+        "subc.u32 mb, 0, 0;\n\t"            // borrow ? 0xffffffff : 0
+        "mul.lo.u32 mc, mc, 0xffffffff;\n\t" // carry  ? 0xffffffff : 0
+        "add.cc.u32 %0, %0, mc;\n\t"        // + EPS on carry
+        "madc.lo.u32 %1, %1, 1, %6;\n\t"
+        "sub.cc.u32 %0, %0, mb;\n\t"        // - EPS on borrow
+        "madc.lo.u32 %1, %7, 1, %1;\n\t"    // hi + 0xffffffff + (no borrow)
+        "}" : "=&r"(o0), "=&r"(o1) : "r"(A0), "r"(A1), "r"(r1), "r"(r3), "r"(zero), "r"(ones));
+    return f_canon(gl_pack(o0, o1));
+}
 
 #endif
 

@@ -9,72 +9,41 @@ using namespace zkb;
 #define ITERS 512
 #define CH 8
 
-#if !defined(__CUDA_ARCH__)   // host pass: the device helpers of field.cuh do not exist
-namespace zkb { inline void gl_unpack(u64, u32&, u32&) {} inline u64 gl_pack(u32, u32) { return 0; } inline void gl_wide(u32, u32, u32&, u32&) {} }
-#endif
-// Carry-flag polarity: after sub.cc / subc.cc the flag the next carry-consuming instruction sees is the HARDWARE carry of
-// a + ~b + 1, i.e. 1 = NO borrow (subc undoes that itself; a madc after a sub.cc does not). The forms below rely on it and are
-// checked against the reference forms by check_kernel.
-// a - b mod p, canonical in/out: IADD3, IADD3.X, IMAD.X (mask), IADD3, IMAD.X  = 3 alu + 2 fma (reference form: 4 + 1)
-__device__ __forceinline__ u64 f_sub_v2(u64 a, u64 b) {
-    u32 a0, a1, b0, b1, o0, o1;
-    gl_unpack(a, a0, a1); gl_unpack(b, b0, b1);
+// Reference forms: every carry step as add.cc / addc / sub.cc / subc (ptxas: IADD3 / IADD3.X on the alu pipe) and a compare +
+// select canonicalisation — what field.cuh used before. f_sub / f_add / f_mul / f_canon of field.cuh are the FMA-pipe forms.
+__device__ __forceinline__ u64 ref_sub(u64 a, u64 b) {
+    u32 o0, o1;
     asm("{\n\t.reg .u32 m;\n\t"
         "sub.cc.u32 %0, %2, %4;\n\t"
         "subc.cc.u32 %1, %3, %5;\n\t"
-        "subc.u32 m, 0, 0;\n\t"                  // borrow ? 0xffffffff : 0
-        "sub.cc.u32 %0, %0, m;\n\t"              // - (2^32 - 1) on borrow
-        "madc.lo.u32 %1, %6, 1, %1;\n\t"         // hi + 0xffffffff + (no second borrow) = hi - second borrow
-        "}" : "=&r"(o0), "=&r"(o1) : "r"(a0), "r"(a1), "r"(b0), "r"(b1), "r"(0xffffffffu));
-    return gl_pack(o0, o1);
+        "subc.u32 m, 0, 0;\n\t"
+        "sub.cc.u32 %0, %0, m;\n\t"
+        "subc.u32 %1, %1, 0;\n\t}"
+        : "=&r"(o0), "=&r"(o1) : "r"((u32)a), "r"((u32)(a >> 32)), "r"((u32)b), "r"((u32)(b >> 32)));
+    return ((u64)o1 << 32) | o0;
 }
-// p - b for canonical b (result in (0, p])
-__device__ __forceinline__ u64 f_negp(u64 b) {
-    u32 b0, b1, n0, n1;
-    gl_unpack(b, b0, b1);
-    asm("{\n\t"
-        "sub.cc.u32 %0, 1, %2;\n\t"
-        "subc.u32 %1, 0xffffffff, %3;\n\t"
-        "}" : "=&r"(n0), "=&r"(n1) : "r"(b0), "r"(b1));
-    return gl_pack(n0, n1);
+__device__ __forceinline__ u64 ref_add(u64 a, u64 b) {
+    u32 o0, o1;
+    asm("{\n\t.reg .u32 m, n0, n1;\n\t"
+        "sub.cc.u32 n0, 1, %4;\n\t"
+        "subc.u32 n1, 0xffffffff, %5;\n\t"
+        "sub.cc.u32 %0, %2, n0;\n\t"
+        "subc.cc.u32 %1, %3, n1;\n\t"
+        "subc.u32 m, 0, 0;\n\t"
+        "sub.cc.u32 %0, %0, m;\n\t"
+        "subc.u32 %1, %1, 0;\n\t}"
+        : "=&r"(o0), "=&r"(o1) : "r"((u32)a), "r"((u32)(a >> 32)), "r"((u32)b), "r"((u32)(b >> 32)));
+    return ((u64)o1 << 32) | o0;
 }
-__device__ __forceinline__ u64 f_add_v2(u64 a, u64 b) { return f_sub_v2(a, f_negp(b)); }
-
-// product + reduction with the carry-in-only steps as madc / IMAD, canonical out
-__device__ __forceinline__ u64 f_mul_v2(u64 a, u64 b) {
-    u32 a0, a1, b0, b1;
-    gl_unpack(a, a0, a1); gl_unpack(b, b0, b1);
-    u32 r0, p00h, p01l, p01h, p10l, p10h, p11l, p11h;
-    gl_wide(a0, b0, r0, p00h); gl_wide(a0, b1, p01l, p01h); gl_wide(a1, b0, p10l, p10h); gl_wide(a1, b1, p11l, p11h);
-    u32 r1, r2, r3;
-    const u32 zero = 0, ones = 0xffffffffu;
-    asm("{\n\t"
-        "add.cc.u32 %0, %3, %4;\n\t"
-        "addc.cc.u32 %1, %5, %7;\n\t"
-        "madc.lo.u32 %2, %9, 1, %10;\n\t"       // r3 = p11.hi + c
-        "add.cc.u32 %0, %0, %6;\n\t"
-        "addc.cc.u32 %1, %1, %8;\n\t"
-        "madc.lo.u32 %2, %2, 1, %10;\n\t"
-        "}" : "=&r"(r1), "=&r"(r2), "=&r"(r3) : "r"(p00h), "r"(p01l), "r"(p01h), "r"(p10l), "r"(p10h), "r"(p11l), "r"(p11h), "r"(zero));
-    u64 A;
-    asm("mad.wide.u32 %0, %1, 0xffffffff, %2;" : "=l"(A) : "r"(r2), "l"(gl_pack(r0, 0)));
-    u32 A0, A1, o0, o1;
-    gl_unpack(A, A0, A1);
-    asm("{\n\t.reg .u32 mb, mc;\n\t"
-        "add.cc.u32 %1, %3, %4;\n\t"              // hi + r1 -> carry
-        "madc.lo.u32 mc, %6, 0, %6;\n\t"          // mc = carry (0 / 1)
-        "sub.cc.u32 %0, %2, %5;\n\t"              // lo - r3 -> borrow
-        "subc.cc.u32 %1, %1, 0;\n\t"
-        "subc.u32 mb, 0, 0;\n\t"                  // borrow ? 0xffffffff : 0
-        "mul.lo.u32 mc, mc, 0xffffffff;\n\t"      // carry  ? 0xffffffff : 0   (IMAD)
-        "add.cc.u32 %0, %0, mc;\n\t"              // + EPS on carry
-        "madc.lo.u32 %1, %1, 1, %6;\n\t"
-        "sub.cc.u32 %0, %0, mb;\n\t"              // - EPS on borrow
-        "madc.lo.u32 %1, %7, 1, %1;\n\t"          // hi + 0xffffffff + (no borrow)
-        "}" : "=&r"(o0), "=&r"(o1) : "r"(A0), "r"(A1), "r"(r1), "r"(r3), "r"(zero), "r"(ones));
-    u64 r = gl_pack(o0, o1);
-    return f_canon(r);
+__device__ __forceinline__ u64 ref_mul(u64 a, u64 b) {
+    u64 r = gl_mul_lazy(a, b);            // gl_mul128_limbs + gl_reduce_limbs: all carry steps on the alu pipe
+    u32 lo = (u32)r, hi = (u32)(r >> 32);
+    if (hi == 0xFFFFFFFFu && lo != 0) { lo -= 1; hi = 0; }
+    return ((u64)hi << 32) | lo;
 }
+#define f_sub_v2 f_sub
+#define f_add_v2 f_add
+#define f_mul_v2 f_mul
 
 // every variant against the reference forms on edge values and a pseudo-random stream; *bad counts mismatches
 __global__ void check_kernel(unsigned long long* bad) {
@@ -85,7 +54,7 @@ __global__ void check_kernel(unsigned long long* bad) {
     for (int i = 0; i < 256; ++i) {
         z = (z ^ (z >> 30)) * 0xbf58476d1ce4e5b9ull; z = (z ^ (z >> 27)) * 0x94d049bb133111ebull; z ^= z >> 31;
         u64 a = (i < 144) ? edge[i % 12] : gl_canon(z), b = (i < 144) ? edge[(i / 12) % 12] : gl_canon(z * 0x2545f4914f6cdd1dull + t);
-        if (f_sub_v2(a, b) != f_sub(a, b) || f_add_v2(a, b) != f_add(a, b) || f_mul_v2(a, b) != f_mul(a, b)) atomicAdd(bad, 1ull);
+        if (f_sub(a, b) != ref_sub(a, b) || f_add(a, b) != ref_add(a, b) || f_mul(a, b) != ref_mul(a, b)) atomicAdd(bad, 1ull);
     }
 }
 
@@ -99,13 +68,13 @@ __global__ void __launch_bounds__(256) bench(u64* out, u64 seed) {
     for (int it = 0; it < ITERS; ++it) {
 #pragma unroll
         for (int k = 0; k < CH; ++k) {
-            if (V == 0) { u64 s = f_add(a[k], b[k]), d = f_sub(a[k], b[k]); a[k] = s; b[k] = d; }                       // butterflies only, current
-            if (V == 1) { u64 s = f_add_v2(a[k], b[k]), d = f_sub_v2(a[k], b[k]); a[k] = s; b[k] = d; }                 // butterflies only, rebalanced
-            if (V == 2) { u64 s = f_add(a[k], b[k]), d = f_sub(a[k], b[k]); a[k] = s; b[k] = f_mul(d, w[k]); }          // + one multiply, current
-            if (V == 3) { u64 s = f_add_v2(a[k], b[k]), d = f_sub_v2(a[k], b[k]); a[k] = s; b[k] = f_mul(d, w[k]); }    // rebalanced add/sub, current mul
-            if (V == 4) { u64 s = f_add_v2(a[k], b[k]), d = f_sub_v2(a[k], b[k]); a[k] = s; b[k] = f_mul_v2(d, w[k]); } // all rebalanced
-            if (V == 5) { a[k] = f_mul(a[k], w[k]); }                                                                  // multiplies only, current
-            if (V == 6) { a[k] = f_mul_v2(a[k], w[k]); }                                                               // multiplies only, rebalanced
+            if (V == 0) { u64 s = ref_add(a[k], b[k]), d = ref_sub(a[k], b[k]); a[k] = s; b[k] = d; }                   // butterflies only, alu forms
+            if (V == 1) { u64 s = f_add(a[k], b[k]), d = f_sub(a[k], b[k]); a[k] = s; b[k] = d; }                       // butterflies only, FMA-pipe forms
+            if (V == 2) { u64 s = ref_add(a[k], b[k]), d = ref_sub(a[k], b[k]); a[k] = s; b[k] = ref_mul(d, w[k]); }    // + one multiply, alu forms
+            if (V == 3) { u64 s = f_add(a[k], b[k]), d = f_sub(a[k], b[k]); a[k] = s; b[k] = ref_mul(d, w[k]); }        // FMA-pipe add/sub, alu multiply
+            if (V == 4) { u64 s = f_add(a[k], b[k]), d = f_sub(a[k], b[k]); a[k] = s; b[k] = f_mul(d, w[k]); }          // all FMA-pipe forms
+            if (V == 5) { a[k] = ref_mul(a[k], w[k]); }                                                                // multiplies only, alu forms
+            if (V == 6) { a[k] = f_mul(a[k], w[k]); }                                                                  // multiplies only, FMA-pipe forms
         }
     }
     u64 s = 0;
@@ -142,16 +111,16 @@ int main() {
         cudaMalloc(&bad, 8); cudaMemset(bad, 0, 8);
         check_kernel<<<64, 128>>>(bad);
         cudaMemcpy(&h, bad, 8, cudaMemcpyDeviceToHost);
-        std::printf("IMAD.X forms vs reference forms: %llu mismatches in %d cases\n", h, 64 * 128 * 256);
+        std::printf("FMA-pipe forms (field.cuh) vs alu forms: %llu mismatches in %d cases\n", h, 64 * 128 * 256);
     }
     u64 c[7];
-    run<0>("butterfly (add + sub), current", out, &c[0]);
-    run<1>("butterfly (add + sub), IMAD.X forms", out, &c[1]);
-    run<2>("butterfly + multiply, current", out, &c[2]);
-    run<3>("butterfly IMAD.X forms + current multiply", out, &c[3]);
-    run<4>("butterfly + multiply, IMAD.X forms", out, &c[4]);
-    run<5>("multiply only, current", out, &c[5]);
-    run<6>("multiply only, IMAD.X forms", out, &c[6]);
+    run<0>("butterfly (add + sub), alu forms", out, &c[0]);
+    run<1>("butterfly (add + sub), FMA-pipe forms", out, &c[1]);
+    run<2>("butterfly + multiply, alu forms", out, &c[2]);
+    run<3>("FMA-pipe butterfly + alu multiply", out, &c[3]);
+    run<4>("butterfly + multiply, FMA-pipe forms", out, &c[4]);
+    run<5>("multiply only, alu forms", out, &c[5]);
+    run<6>("multiply only, FMA-pipe forms", out, &c[6]);
     std::printf("results agree: %s\n", (c[0] == c[1] && c[2] == c[3] && c[3] == c[4] && c[5] == c[6]) ? "yes" : "NO");
     return 0;
 }

@@ -284,12 +284,23 @@ ZKB_D u64 f_add(u64 a, u64 b) {               // a - (p - b); p - b in (0, p], a
     return f_sub(a, gl_pack(n0, n1));
 }
 
-// r >= p  <=>  high word all ones and low word >= 1; then r - p = low - 1
+// r >= p  <=>  r + (2^32 - 1) carries out of 64 bits (high word all ones and low word >= 1); then r - p = (low - 1, 0).
+// With c = that carry (0 / 1): low' = low + c * 0xffffffff, high' = high + c (0xffffffff + 1 wraps to 0) — the two carry adds on
+// the alu pipe, everything else on the FMA pipe (the compare + select form is 4-5 alu instructions).
 ZKB_D u64 f_canon(u64 r) {
-    u32 lo = (u32)r, hi = (u32)(r >> 32);
-    if (hi == 0xFFFFFFFFu && lo != 0) { lo -= 1; hi = 0; }
-    return ((u64)hi << 32) | lo;
+    u32 lo, hi, c;
+    gl_unpack(r, lo, hi);
+    asm("{\n\t.reg .u32 t;\n\t"
+        "add.cc.u32 t, %1, 0xffffffff;\n\t"
+        "addc.cc.u32 t, %2, 0;\n\t"
+        "madc.lo.u32 %0, %3, 0, %3;\n\t"
+        "}" : "=r"(c) : "r"(lo), "r"(hi), "r"(0u));
+    u32 lo2, hi2;
+    asm("mad.lo.u32 %0, %1, 0xffffffff, %2;" : "=r"(lo2) : "r"(c), "r"(lo));
+    asm("mad.lo.u32 %0, %1, 1, %2;" : "=r"(hi2) : "r"(c), "r"(hi));
+    return gl_pack(lo2, hi2);
 }
+
 // canonical product of any two u64: the same product limbs and fold as gl_mul_lazy / gl_reduce_limbs (which the Poseidon code,
 // FMA-pipe bound, keeps), with the carry-consuming steps on the FMA pipe: 5 alu + 5 fma in the fold instead of 9 + 2
 ZKB_D u64 f_mul(u64 a, u64 b) {

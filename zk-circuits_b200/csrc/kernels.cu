@@ -865,33 +865,65 @@ __global__ void __launch_bounds__(128, PART == 3 ? 4 : 8) quotient_kernel(Quotie
                 }
 #pragma unroll
                 for (int j = 8; j < 12; ++j) st[j] = W(j);
-                // ONE loop over the 30 rounds (warp-uniform branches) and a non-inlined S-box keep this gate at ~1 k
-                // instructions; wires: full rounds 1..3 -> 29 + 12 (r - 1) + j, partial r' -> 65 + r', last four -> 87 + 12 r'' + j
+                // The state lives in limb form as in the hash kernels (poseidon.cuh): the MDS layer is the shift/add circulant
+                // on three 22-bit limb vectors with the NEXT round's constants folded into its output adds, so after it the
+                // limbs hold exactly "state + round constants" — the value every constraint of the next round compares with its
+                // S-box-input wire. Only the words a constraint needs are folded to a 64-bit value (limb_to_u64_biased); in
+                // the 22 partial rounds that is one word, the other 11 are just carry-normalised. (The first version ran a
+                // 64-bit-word MDS, 288 IMAD.WIDE per round, and was bound by the FMA pipe.) One loop over the 30 rounds,
+                // full rounds in 3 passes of 4 words with a register rotation, non-inlined S-box: small code.
+                // wires: full rounds 1..3 -> 29 + 12 (r - 1) + j, partial r' -> 65 + r', last four -> 87 + 12 r'' + j
+                u32 o0[12], o1[12], o2[12];
+#pragma unroll
+                for (int j = 0; j < 12; ++j) {
+                    limb_split(f_canon(st[j]), o0[j], o1[j], o2[j]);
+                    o0[j] += c_rc3[3 * j]; o1[j] += c_rc3[3 * j + 1]; o2[j] += c_rc3[3 * j + 2];
+                }
+                auto rotate4 = [&]() {
+                    u32 t;
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        t = o0[i]; o0[i] = o0[i + 4]; o0[i + 4] = o0[i + 8]; o0[i + 8] = t;
+                        t = o1[i]; o1[i] = o1[i + 4]; o1[i + 4] = o1[i + 8]; o1[i + 8] = t;
+                        t = o2[i]; o2[i] = o2[i + 4]; o2[i + 4] = o2[i + 8]; o2[i + 8] = t;
+                    }
+                };
 #pragma unroll 1
                 for (int r = 0; r < P_ROUNDS; ++r) {
-#pragma unroll
-                    for (int j = 0; j < 12; ++j) st[j] = gl_add_lazy_c(st[j], c_rc[12 * r + j]);
                     if (r < P_HALF_FULL || r >= P_HALF_FULL + P_PARTIAL) {
-                        if (r != 0) {
-                            const int base = r < P_HALF_FULL ? 29 + 12 * (r - 1) : 87 + 12 * (r - P_HALF_FULL - P_PARTIAL);
+                        const int base = r < P_HALF_FULL ? 29 + 12 * (r - 1) : 87 + 12 * (r - P_HALF_FULL - P_PARTIAL);
+#pragma unroll 1
+                        for (int pass = 0; pass < 3; ++pass) {
 #pragma unroll
-                            for (int j = 0; j < 12; ++j) {
-                                u64 sin = W(base + j);
-                                add_c(gl_sub_lazy_c(st[j], sin));
-                                st[j] = sin;
+                            for (int i = 0; i < 4; ++i) {
+                                u64 v = limb_to_u64_biased(o0[i], o1[i], o2[i]);
+                                if (r != 0) {
+                                    const u64 sin = W(base + 4 * pass + i);
+                                    add_c(gl_sub_lazy_c(v, sin));
+                                    v = sin;
+                                }
+                                limb_split(q_sbox7(v), o0[i], o1[i], o2[i]);
                             }
+                            rotate4();
                         }
-#pragma unroll
-                        for (int j = 0; j < 12; ++j) st[j] = q_sbox7(st[j]);
                     } else {
-                        u64 sin = W(65 + r - P_HALF_FULL);
-                        add_c(gl_sub_lazy_c(st[0], sin));
-                        st[0] = q_sbox7(sin);
-                    }
-                    mds_layer(st);
-                }
+                        const u64 sin = W(65 + r - P_HALF_FULL);
+                        add_c(gl_sub_lazy_c(limb_to_u64_biased(o0[0], o1[0], o2[0]), sin));
+                        limb_split(q_sbox7(sin), o0[0], o1[0], o2[0]);
 #pragma unroll
-                for (int j = 0; j < 12; ++j) add_c(gl_sub_lazy_c(st[j], W(12 + j)));
+                        for (int j = 1; j < 12; ++j) limb_normalize(o0[j], o1[j], o2[j]);
+                    }
+                    const u32* rc = c_rc3 + 36 * (r + 1);
+                    mds_limb12(o0, rc);
+                    mds_limb12(o1, rc + 1);
+                    mds_limb12(o2, rc + 2);
+                }
+#pragma unroll 1
+                for (int pass = 0; pass < 3; ++pass) {
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) add_c(gl_sub_lazy_c(limb_to_u64_biased(o0[i], o1[i], o2[i]), W(12 + 4 * pass + i)));
+                    rotate4();
+                }
                 break;
             }
             case TAG_ARITHMETIC_EXT:       // per op: a[2] b[2] addend[2] out[2];  out - (c0 a b + c1 addend)

@@ -348,7 +348,9 @@ def main():
                    "host_clock_ms_per_step": 1000 * tm_res.host_s / K},
         "circuit_create_ms": {"first_contexts_avg": 1000 * t_create, "warm": 1000 * t_create_warm,
                               "note": "zkb_circuit_create from host values: upload + constants/sigmas iNTT, LDE and Merkle tree on the "
-                                      "device + every work buffer (SURVEY 8f rank 1; cached per circuit by zkb200.batch.ContextPool)"},
+                                      "device + every work buffer (SURVEY 8f rank 1; cached per circuit by zkb200.batch.ContextPool). One "
+                                      "cudaMalloc of ~0.6 GB dominates and varies by box (2 ms to 400 ms, fresh memory being cleared); the "
+                                      "rest is ~5 ms (ZKB_TRACE=1)"},
         "prove_ms_single_stream": 1000 * t_single / K, "device_ms_per_proof": stages["total"], "stage_ms": stages,
         "e2e": {"value": world * K * B / t_e2e, "unit": UNIT, "ms_per_step": 1000 * t_e2e / K,
                 "h2d_bytes_per_step": int(B * (nw * n * 8 + pis.size * 8)), "d2h_bytes_per_step": int(B * len(proof))},

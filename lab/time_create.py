@@ -5,8 +5,8 @@ sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."
 import zkb200 as Z
 s = Z.SynthCircuit(zk=True, seed=1, **Z.WORMHOLE)
 keep = []
-for i in range(4):
+for i in range(10):
     t0 = time.perf_counter()
     keep.append(Z.ProverCircuit(s.common, s.const_sigma_values, is_values=True))
     print("create %d: %.2f ms" % (i, 1e3 * (time.perf_counter() - t0)), flush=True)
-t0 = time.perf_counter(); keep.clear(); print("destroy 4: %.2f ms" % (1e3 * (time.perf_counter() - t0)))
+t0 = time.perf_counter(); keep.clear(); print("destroy all: %.2f ms" % (1e3 * (time.perf_counter() - t0)))

@@ -5,6 +5,7 @@
 #include <cstring>
 #include <chrono>
 #include <cstdio>
+#include <mutex>
 #include <thread>
 
 namespace zkb {
@@ -254,6 +255,10 @@ void Circuit::sync() {
 size_t Circuit::run_merkle_levels(u64* digests, size_t num_leaves, unsigned cap_height) {
     LevelGraph& g = level_graphs_[digests];
     if (!g.exec) {
+        // one capture at a time per process: it happens once per tree and context, keeps the launch count of the captured
+        // chain exact when several contexts warm up together, and profilers (ncu) crash on concurrent stream captures
+        static std::mutex capture_mu;
+        std::lock_guard<std::mutex> lk(capture_mu);
         const unsigned long long before = kernel_launch_count();
         cudaGraph_t graph = nullptr;
         CK(cudaStreamBeginCapture(st_, cudaStreamCaptureModeThreadLocal));

@@ -50,6 +50,41 @@ namespace zkb {
 
 static void ntt_set_func_attributes();   // defined with the NTT kernels below
 
+// The canonical device forms (field.cuh: f_sub, f_add, f_mul, f_canon) put carry-consuming steps on the FMA pipe and rely on the
+// polarity of the carry flag a madc sees after sub.cc (1 = no borrow) — compiler behaviour, not a documented contract. Every
+// device runs this once before its first use: the forms against the portable compare-and-select arithmetic on corner values and
+// a pseudo-random stream. A mismatch makes the library refuse to work on that device instead of producing wrong proofs.
+__global__ void field_selfcheck_kernel(unsigned long long* bad) {
+    const u64 edge[14] = {0, 1, 2, 7, GL_P - 1, GL_P - 2, 0xffffffffull, 0x100000000ull, 0x100000001ull, 0x8000000000000000ull,
+                          GL_P - 0x100000000ull, 0xfffffffe00000002ull, 0x00000001ffffffffull, 0xfffffffeffffffffull};
+    const u32 t = threadIdx.x + blockIdx.x * blockDim.x;
+    u64 z = 0x9e3779b97f4a7c15ull * (t + 1);
+    unsigned long long mism = 0;
+    for (int i = 0; i < 256; ++i) {
+        z = (z ^ (z >> 30)) * 0xbf58476d1ce4e5b9ull; z = (z ^ (z >> 27)) * 0x94d049bb133111ebull; z ^= z >> 31;
+        const u64 a = i < 196 ? edge[i % 14] : gl_canon(z), b = i < 196 ? edge[(i / 14) % 14] : gl_canon(z * 0x2545f4914f6cdd1dull + t);
+        unsigned __int128 pr = (unsigned __int128)a * b;
+        const u64 want_mul = (u64)(pr % GL_P);
+        mism += f_sub(a, b) != gl_sub(a, b);
+        mism += f_add(a, b) != gl_add(a, b);
+        mism += f_mul(a, b) != want_mul;
+        mism += f_mul(z, b) != (u64)(((unsigned __int128)z * b) % GL_P);          // lazy (non-canonical) left operand
+        mism += f_canon(z) != gl_canon(z);
+    }
+    if (mism) atomicAdd(bad, mism);
+}
+static void field_selfcheck() {
+    unsigned long long* bad = nullptr;
+    unsigned long long h = 0;
+    ZKB_CUDA_CHECK(cudaMalloc(&bad, sizeof(h)));
+    ZKB_CUDA_CHECK(cudaMemset(bad, 0, sizeof(h)));
+    field_selfcheck_kernel<<<16, 128>>>(bad);
+    ZKB_CUDA_CHECK(cudaMemcpy(&h, bad, sizeof(h), cudaMemcpyDeviceToHost));
+    cudaFree(bad);
+    if (h) throw std::runtime_error("device field arithmetic self-check failed (" + std::to_string(h) +
+                                    " mismatches): this build's carry-flag forms do not hold on this toolchain / device");
+}
+
 void device_tables_init(int device) {
     static std::mutex mu;
     static std::vector<int> done;
@@ -92,6 +127,7 @@ void device_tables_init(int device) {
         ZKB_CUDA_CHECK(cudaMemcpyToSymbol(c_w16, w16, sizeof(w16)));
     }
     ntt_set_func_attributes();
+    field_selfcheck();
     ZKB_CUDA_CHECK(cudaSetDevice(prev));
     done.push_back(device);
 }

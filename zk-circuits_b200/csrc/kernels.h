@@ -98,8 +98,8 @@ void launch_openings(const OpeningsArgs& a, ext2 z0, ext2 z1, cudaStream_t st);
 void launch_ext_powers(ext2 z, unsigned lg_n, u64* zpow_a, u64* zpow_b, cudaStream_t st);
 
 struct FriCombineParams {
-    const u64* lde[4]; size_t stride[4]; int ncols[4];   // unsalted column counts per oracle
-    int num_zs;                                          // columns of oracle 2 opened at g*zeta
+    const u64* lde[4]; size_t stride[4]; int ncols[4];   // unsalted column counts per committed batch
+    int num_zs;                                          // columns of batch 2 (Z / partial products) opened at g*zeta
     ext2 alpha, zeta, zeta_next, reduced0, reduced1;
     unsigned lg_n;
 };

@@ -1,10 +1,11 @@
 /* Minimal C client of libzkb200.so: builds a synthetic wormhole-shaped circuit, proves it once through the C ABI and writes
  * the proof bytes — what a non-Python host (the Rust shim in rust/zkb200, or any C/C++ caller) does.
- *   gcc -std=c11 -O2 -Iinclude examples/prove_example.c -Lzk-circuits_b200 -lzkb200 -Wl,-rpath,$PWD/zk-circuits_b200 -o prove_example
+ *   gcc -std=c11 -O2 -Iinclude examples/prove_example.c -Lzk-circuits_b200 -lzkb200 -lzkb200_synth -Wl,-rpath,$PWD/zk-circuits_b200 -o prove_example
  *   ./prove_example [zk=1] [out.bin]                                                                                   */
 #include <stdio.h>
 #include <stdlib.h>
 #include "zkb200.h"
+#include "zkb200_synth.h" /* synthetic workload (libzkb200_synth.so): stands in for the Rust circuit builder + witness generator */
 
 #define CHECK(call)                                                                      \
     do {                                                                                 \
@@ -16,18 +17,21 @@ int main(int argc, char** argv) {
     int zk = argc > 1 ? atoi(argv[1]) : 1;
     if (zkb_device_count() == 0) { fprintf(stderr, "no CUDA device (%s)\n", zkb_version()); return 2; }
     zkb_synth* s = NULL;
-    CHECK(zkb_synth_create(0, zk, 6, 5, 6, 3, 5, 42, &s));           /* tiny row mix: 6 Poseidon, 5 BaseSum, 6 Arithmetic rows */
+    if (zkb_synth_create(0, zk, 6, 5, 6, 3, 5, 42, &s)) { fprintf(stderr, "synth: %s\n", zkb_synth_last_error()); return 1; }           /* tiny row mix: 6 Poseidon, 5 BaseSum, 6 Arithmetic rows */
     size_t n = zkb_synth_degree(s), clen = zkb_synth_common_len(s);
     uint8_t* common = malloc(clen);
     uint64_t* cs = malloc(84 * n * sizeof(uint64_t));
     uint64_t* wires = malloc(135 * n * sizeof(uint64_t));
     uint64_t pis[5];
-    CHECK(zkb_synth_get(s, common, cs, wires, pis));
+    if (zkb_synth_get(s, common, cs, wires, pis)) return 1;
     zkb_circuit* c = NULL;
     CHECK(zkb_circuit_create(common, clen, cs, /*is_values=*/1, /*digest=*/NULL, /*device=*/0, &c));
     size_t cap = zkb_proof_size(c), len = 0;
     uint8_t* proof = malloc(cap);
-    CHECK(zkb_prove(c, wires, pis, 5, /*salts=*/NULL, /*salt_seed=*/7, ZKB_POW_MIN, proof, cap, &len));
+    /* ZKB_SALTS_FROM_SEED makes the run reproducible (the test suite compares the bytes); production callers leave it out and
+     * get CSPRNG salts. ZKB_CHECK_WITNESS: refuse to emit a proof for a witness that violates a constraint. */
+    CHECK(zkb_prove(c, wires, pis, 5, /*salts=*/NULL, /*salt_seed=*/7, ZKB_POW_MIN | ZKB_SALTS_FROM_SEED | ZKB_CHECK_WITNESS, proof, cap,
+                    &len));
     float ms[ZKB_NUM_TIMINGS];
     int nt = zkb_last_timings(c, ms, ZKB_NUM_TIMINGS);
     printf("proof %zu bytes, n = %zu, device total %.3f ms, %llu kernels launched\n", len, n, nt > 12 ? ms[12] : 0.f,
@@ -35,7 +39,7 @@ int main(int argc, char** argv) {
     if (argc > 2) { FILE* f = fopen(argv[2], "wb"); if (!f) return 3; fwrite(proof, 1, len, f); fclose(f); }
     /* error path: a buffer that is too small reports the required size */
     size_t need = 0;
-    int rc = zkb_prove(c, wires, pis, 5, NULL, 7, ZKB_POW_MIN, proof, 16, &need);
+    int rc = zkb_prove(c, wires, pis, 5, NULL, 0, ZKB_POW_MIN, proof, 16, &need);
     if (rc != ZKB_E_BUFFER || need != cap) { fprintf(stderr, "expected ZKB_E_BUFFER with the size, got %d / %zu\n", rc, need); return 4; }
     zkb_circuit_destroy(c);
     zkb_synth_destroy(s);

@@ -32,9 +32,10 @@ typedef enum zkb_status {
     ZKB_E_ARG = -1,               /* null pointer, bad size, non-canonical field element            */
     ZKB_E_PARSE = -2,             /* malformed CommonCircuitData bytes                              */
     ZKB_E_UNSUPPORTED_GATE = -3,  /* gate tag / config outside the implemented set                  */
-    ZKB_E_UNSAT = -4,             /* reserved (optional vanishing-identity self-check at zeta); not returned by this
-                                     version: like the CPU prover, a witness that violates a constraint yields a
-                                     proof the verifier rejects (witness generation, which catches it, stays in Rust) */
+    ZKB_E_UNSAT = -4,             /* with ZKB_CHECK_WITNESS: the witness violates a gate or copy constraint (the
+                                     reference surfaces such inputs as Err from witness generation, e.g.
+                                     voting/src/lib.rs:399-403). Without the flag, like the CPU prover, the call
+                                     returns a proof the verifier rejects                                           */
     ZKB_E_ZETA_IN_SUBGROUP = -5,  /* reference: "Opening point is in the subgroup."                 */
     ZKB_E_CUDA = -6,
     ZKB_E_NCCL = -7,
@@ -66,23 +67,63 @@ int zkb_circuit_destroy(zkb_circuit* c);
 int zkb_circuit_verifier_only(const zkb_circuit* c, uint64_t* cap_out, size_t cap_words, uint64_t digest_out[4]);
 size_t zkb_proof_size(const zkb_circuit* c);
 
-/* pow_rule: how the FRI proof-of-work witness is chosen (the CPU prover's rayon find_any is not deterministic) */
+/* ---- `flags` of the prove calls: low byte = proof-of-work rule, then option bits ----
+ * pow rule: how the FRI proof-of-work witness is chosen (the CPU prover's rayon find_any is not deterministic) */
 #define ZKB_POW_MIN 0u /* smallest valid witness = CPU result with RAYON_NUM_THREADS=1 */
+/* Salt source of a zero-knowledge circuit when `salts` is NULL. DEFAULT (flag clear): a CSPRNG — ChaCha20 on the device,
+ * keyed per proof with 256 bits from the OS (getrandom); salt_seed is ignored. This is what production callers use: the
+ * blinding columns hide the witness only if a verifier cannot predict them (the CPU prover draws F::rand_vec from an
+ * OS-seeded RNG). With ZKB_SALTS_FROM_SEED the salts are the documented SplitMix64 stream of salt_seed — a public bijection
+ * of (seed, position), so ONE opened leaf reveals every other salt: for byte-parity tests and benchmarks only. */
+#define ZKB_SALTS_FROM_SEED 0x100u
+/* Evaluate every constraint of the circuit (gates, Z(1) = 1, the partial-product chain = copy constraints) on the subgroup
+ * from the witness values before committing Z, on the device (~2 % of a proof); a violation returns ZKB_E_UNSAT instead of
+ * an unverifiable proof. */
+#define ZKB_CHECK_WITNESS 0x200u
+/* zkb_engine_submit only: prove the witness the context already holds (benchmark's device-resident arm) */
+#define ZKB_WITNESS_RESIDENT 0x400u
 
 /* ---- prove: replaces circuit_data.prove(partial_witness) after witness generation.
  *   wires          [num_wires][n] column-major full witness (partition_witness.full_witness().wire_values)
  *   public_inputs  n_pi field elements
  *   salts          NULL, or [3][4][n << rate_bits]: blinding salt columns for the wires / Z-partial-product /
- *                  quotient batches, indexed by leaf position; ignored unless the circuit is zero-knowledge.
- *                  When NULL a zk circuit draws salts on the device from salt_seed (documented SplitMix64 stream)
+ *                  quotient batches, indexed by leaf position (canonical; checked); ignored unless the circuit is
+ *                  zero-knowledge. When NULL a zk circuit draws its salts on the device from a CSPRNG keyed by the OS
+ *                  (see ZKB_SALTS_FROM_SEED below for the deterministic test mode that uses salt_seed)
+ *   flags          ZKB_POW_MIN | option bits (below)
  *   proof_out      receives ProofWithPublicInputs::to_bytes(); *proof_len = bytes written (or required, on
  *                  ZKB_E_BUFFER) */
 int zkb_prove(zkb_circuit* c, const uint64_t* wires, const uint64_t* public_inputs, size_t n_pi, const uint64_t* salts,
-              uint64_t salt_seed, uint32_t pow_rule, uint8_t* proof_out, size_t proof_cap, size_t* proof_len);
+              uint64_t salt_seed, uint32_t flags, uint8_t* proof_out, size_t proof_cap, size_t* proof_len);
 /* split form used by the benchmark: upload once, prove from HBM-resident wires */
 int zkb_witness_upload(zkb_circuit* c, const uint64_t* wires);
 int zkb_prove_resident(zkb_circuit* c, const uint64_t* public_inputs, size_t n_pi, const uint64_t* salts, uint64_t salt_seed,
-                       uint32_t pow_rule, uint8_t* proof_out, size_t proof_cap, size_t* proof_len);
+                       uint32_t flags, uint8_t* proof_out, size_t proof_cap, size_t* proof_len);
+
+/* ---- proof engine: asynchronous proving with pinned, double-buffered witness hand-off.
+ * The reference fills a PartialWitness (wormhole/prover/src/lib.rs:209-225), runs the generator graph and proves, one
+ * blocking call per proof; its aggregator fans such calls out over rayon (aggregator/src/circuits/tree.rs:93-103). An
+ * engine owns n_contexts prover contexts of one circuit on one GPU, ONE driver thread that steps all of them (a proof is
+ * ~10 GPU stages separated by serial Fiat-Shamir steps; the driver runs whichever context's stage has finished), and
+ * n_slots >= n_contexts pinned witness buffers:
+ *     slot = zkb_engine_acquire(e, &buf);     blocks while every slot is in use
+ *     ... write the wire matrix [num_wires][n] (column-major, canonical) into buf — witness generation for proof k+1
+ *         overlaps the GPU work of proofs k, k-1, ... ...
+ *     zkb_engine_submit(e, slot, public_inputs, n_pi, salts, salt_seed, flags, proof_out, cap);     returns at once
+ *     zkb_engine_wait(e, slot, &len);         blocks until THAT proof is done; returns its status; frees the slot
+ * Any number of caller threads may use one engine. public_inputs are copied at submit; salts (if not NULL) and proof_out
+ * must stay valid until the wait returns. Argument errors are reported by submit, proving errors by wait. */
+typedef struct zkb_engine zkb_engine;
+int zkb_engine_create(const uint8_t* common_bin, size_t common_len, const uint64_t* const_sigma, int is_values,
+                      const uint64_t circuit_digest[4], int device, int n_contexts, int n_slots, zkb_engine** out);
+int zkb_engine_destroy(zkb_engine* e);
+size_t zkb_engine_proof_size(const zkb_engine* e);
+/* returns the slot id (>= 0) or a negative zkb_status */
+int zkb_engine_acquire(zkb_engine* e, uint64_t** wires_buf);
+int zkb_engine_release(zkb_engine* e, int slot);     /* give an acquired slot back without proving */
+int zkb_engine_submit(zkb_engine* e, int slot, const uint64_t* public_inputs, size_t n_pi, const uint64_t* salts,
+                      uint64_t salt_seed, uint32_t flags, uint8_t* proof_out, size_t proof_cap);
+int zkb_engine_wait(zkb_engine* e, int slot, size_t* proof_len);
 /* per-stage device times (ms, CUDA events on the circuit's stream) of the last prove; returns count written.
  * order: wires_intt, wires_lde, wires_merkle, partial_products, zs_commit, quotient, quotient_commit, openings,
  *        fri_combine, fri_commit, pow, queries, total, then two host-side figures: milliseconds spent in the Fiat-Shamir
@@ -117,29 +158,6 @@ int zkb_partial_products(zkb_circuit* c, const uint64_t* wires, const uint64_t* 
 /* compute_quotient_polys from wire / Z-partial-product VALUES (unsalted): out [num_challenges*qdf][n] coefficients */
 int zkb_quotient(zkb_circuit* c, const uint64_t* wires, const uint64_t* zs_pp, const uint64_t* public_inputs, size_t n_pi,
                  const uint64_t* betas, const uint64_t* gammas, const uint64_t* alphas, uint64_t* out);
-
-/* ---- synthetic workload generator (host code; stands in for the Rust side of the boundary, i.e.
- * CircuitBuilder::build_prover + witness generation, which need a Rust toolchain). Produces a circuit with the
- * reference wormhole circuit's configuration, gate set and row mix and a satisfying witness.
- * Used by bench.py / smoke() / tests to obtain workloads; not part of the proving path. ---- */
-typedef struct zkb_synth zkb_synth;
-int zkb_synth_create(unsigned min_degree_bits, int zk, size_t n_poseidon, size_t n_base_sum, size_t n_arith, size_t n_const,
-                     size_t num_public_inputs, uint64_t seed, zkb_synth** out);
-/* recursion-shaped circuit (configs #4/#5: the gate set a recursive-verifier circuit instantiates at
- * wormhole/aggregator/src/circuits/tree.rs:119 — SURVEY.md App. C.2 — with four selector groups; zk as the aggregator's
- * chunk circuits are, which inherit the leaf circuit's standard_recursion_zk_config, aggregator.rs:21 / tree.rs:111):
- * recursion_rows[8] = rows of ArithmeticExtension, MulExtension, Reducing, ReducingExtension, RandomAccess,
- * Exponentiation, CosetInterpolation, PoseidonMds on top of the base counts; const_sigma_values is then [6 + 80][n] */
-int zkb_synth_create_recursion(unsigned min_degree_bits, int zk, size_t n_poseidon, size_t n_base_sum, size_t n_arith, size_t n_const,
-                               size_t num_public_inputs, uint64_t seed, const size_t recursion_rows[8], zkb_synth** out);
-int zkb_synth_destroy(zkb_synth* s);
-/* number of constant columns (selectors + gate constants) of the synthetic circuit: const_sigma_values has this + 80 columns */
-size_t zkb_synth_num_constants(const zkb_synth* s);
-size_t zkb_synth_common_len(const zkb_synth* s);
-size_t zkb_synth_degree(const zkb_synth* s);
-/* any output pointer may be NULL: common [common_len] bytes, const_sigma_values [num_constants + 80][n], wires [135][n],
- * public_inputs [num_public_inputs] */
-int zkb_synth_get(const zkb_synth* s, uint8_t* common, uint64_t* const_sigma_values, uint64_t* wires, uint64_t* public_inputs);
 
 #ifdef __cplusplus
 }

@@ -48,6 +48,23 @@ __global__ void __launch_bounds__(256) bench(u64* out, u32 b) {
                 lo[k] = (u32)acc; hi[k] = (u32)(acc >> 32);
                 asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(x[k]) : "r"(lo[k]), "r"(hi[k]));
             }
+            if (KIND >= 10 && KIND <= 14) {   // FP64 pipe: DFMA alone, and interleaved 1:1 with an integer instruction
+                double dacc = __longlong_as_double(((long long)hi[k] << 32) | lo[k]);
+                asm volatile("fma.rn.f64 %0, %0, %1, %2;" : "+d"(dacc) : "d"(1.0000001), "d"(0.5));
+                long long bits = __double_as_longlong(dacc);
+                lo[k] = (u32)bits; hi[k] = (u32)(bits >> 32);
+                if (KIND == 11) asm volatile("mad.lo.u32 %0, %0, %1, %2;" : "+r"(x[k]) : "r"(x[k]), "r"(b));
+                if (KIND == 12) asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(x[k]) : "r"(x[k]), "r"(b));
+                if (KIND == 13) {
+                    u64 acc = ((u64)b << 32) | x[k];
+                    asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(acc) : "r"(x[k]), "r"(b));
+                    x[k] = (u32)acc ^ (u32)(acc >> 32);
+                }
+                if (KIND == 14) {   // 1 DFMA : 1 IMAD : 1 LOP3
+                    asm volatile("mad.lo.u32 %0, %0, %1, %2;" : "+r"(x[k]) : "r"(x[k]), "r"(b));
+                    asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(x[k]) : "r"(x[k]), "r"(b));
+                }
+            }
             if (KIND == 9) {   // predicated 64-bit fix-up: setp + 2 predicated adds
                 asm volatile("{.reg .pred p;\n\tsetp.lt.u32 p, %0, %2;\n\t@p add.cc.u32 %0, %0, %3;\n\t@p addc.u32 %1, %1, 0;}"
                              : "+r"(lo[k]), "+r"(hi[k]) : "r"(x[k]), "r"(hi[k]));
@@ -86,6 +103,11 @@ int main() {
     run<7>("1 IMAD.WIDE + IADD3 + IADD3.X", 3, d);
     run<8>("1 IMAD.WIDE + 1 LOP3", 2, d);
     run<9>("ISETP + 2 predicated IADD3", 3, d);
+    run<10>("DFMA only", 1, d);
+    run<11>("1 DFMA + 1 IMAD(lo)", 2, d);
+    run<12>("1 DFMA + 1 LOP3", 2, d);
+    run<13>("1 DFMA + 1 IMAD.WIDE (+ LOP3)", 3, d);
+    run<14>("1 DFMA + 1 IMAD(lo) + 1 LOP3", 3, d);
     cudaDeviceSynchronize();
     printf("%s\n", cudaGetErrorString(cudaGetLastError()));
     return 0;

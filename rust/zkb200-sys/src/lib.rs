@@ -8,7 +8,7 @@ pub struct zkb_circuit {
     _private: [u8; 0],
 }
 #[repr(C)]
-pub struct zkb_synth {
+pub struct zkb_engine {
     _private: [u8; 0],
 }
 
@@ -24,6 +24,9 @@ pub const ZKB_E_NCCL: c_int = -7;
 pub const ZKB_E_BUFFER: c_int = -8;
 pub const ZKB_E_DIGEST: c_int = -9;
 pub const ZKB_POW_MIN: u32 = 0;
+pub const ZKB_SALTS_FROM_SEED: u32 = 0x100;
+pub const ZKB_CHECK_WITNESS: u32 = 0x200;
+pub const ZKB_WITNESS_RESIDENT: u32 = 0x400;
 pub const ZKB_NUM_TIMINGS: usize = 15;
 
 extern "C" {
@@ -39,10 +42,20 @@ extern "C" {
     pub fn zkb_proof_size(c: *const zkb_circuit) -> usize;
 
     pub fn zkb_prove(c: *mut zkb_circuit, wires: *const u64, public_inputs: *const u64, n_pi: usize, salts: *const u64,
-                     salt_seed: u64, pow_rule: u32, proof_out: *mut u8, proof_cap: usize, proof_len: *mut usize) -> c_int;
+                     salt_seed: u64, flags: u32, proof_out: *mut u8, proof_cap: usize, proof_len: *mut usize) -> c_int;
     pub fn zkb_witness_upload(c: *mut zkb_circuit, wires: *const u64) -> c_int;
     pub fn zkb_prove_resident(c: *mut zkb_circuit, public_inputs: *const u64, n_pi: usize, salts: *const u64, salt_seed: u64,
-                              pow_rule: u32, proof_out: *mut u8, proof_cap: usize, proof_len: *mut usize) -> c_int;
+                              flags: u32, proof_out: *mut u8, proof_cap: usize, proof_len: *mut usize) -> c_int;
+    pub fn zkb_engine_create(common_bin: *const u8, common_len: usize, const_sigma: *const u64, is_values: c_int,
+                             circuit_digest: *const u64, device: c_int, n_contexts: c_int, n_slots: c_int,
+                             out: *mut *mut zkb_engine) -> c_int;
+    pub fn zkb_engine_destroy(e: *mut zkb_engine) -> c_int;
+    pub fn zkb_engine_proof_size(e: *const zkb_engine) -> usize;
+    pub fn zkb_engine_acquire(e: *mut zkb_engine, wires_buf: *mut *mut u64) -> c_int;
+    pub fn zkb_engine_release(e: *mut zkb_engine, slot: c_int) -> c_int;
+    pub fn zkb_engine_submit(e: *mut zkb_engine, slot: c_int, public_inputs: *const u64, n_pi: usize, salts: *const u64,
+                             salt_seed: u64, flags: u32, proof_out: *mut u8, proof_cap: usize) -> c_int;
+    pub fn zkb_engine_wait(e: *mut zkb_engine, slot: c_int, proof_len: *mut usize) -> c_int;
     pub fn zkb_last_timings(c: *const zkb_circuit, ms_out: *mut c_float, cap: c_int) -> c_int;
 
     pub fn zkb_poseidon_permute_batch(states: *mut u64, count: usize, device: c_int) -> c_int;
@@ -57,15 +70,4 @@ extern "C" {
     pub fn zkb_partial_products(c: *mut zkb_circuit, wires: *const u64, betas: *const u64, gammas: *const u64, out: *mut u64) -> c_int;
     pub fn zkb_quotient(c: *mut zkb_circuit, wires: *const u64, zs_pp: *const u64, public_inputs: *const u64, n_pi: usize,
                         betas: *const u64, gammas: *const u64, alphas: *const u64, out: *mut u64) -> c_int;
-
-    pub fn zkb_synth_create_recursion(min_degree_bits: c_uint, zk: c_int, n_poseidon: usize, n_base_sum: usize, n_arith: usize, n_const: usize,
-                                      num_public_inputs: usize, seed: u64, recursion_rows: *const usize, out: *mut *mut zkb_synth) -> c_int;
-    pub fn zkb_synth_num_constants(s: *const zkb_synth) -> usize;
-    pub fn zkb_synth_create(min_degree_bits: c_uint, zk: c_int, n_poseidon: usize, n_base_sum: usize, n_arith: usize,
-                            n_const: usize, num_public_inputs: usize, seed: u64, out: *mut *mut zkb_synth) -> c_int;
-    pub fn zkb_synth_destroy(s: *mut zkb_synth) -> c_int;
-    pub fn zkb_synth_common_len(s: *const zkb_synth) -> usize;
-    pub fn zkb_synth_degree(s: *const zkb_synth) -> usize;
-    pub fn zkb_synth_get(s: *const zkb_synth, common: *mut u8, const_sigma_values: *mut u64, wires: *mut u64,
-                         public_inputs: *mut u64) -> c_int;
 }

@@ -18,8 +18,8 @@ def zkb():
     return zkb200
 
 
-def declared_symbols():
-    src = open(os.path.join(ROOT, "include", "zkb200.h")).read()
+def declared_symbols(header="zkb200.h"):
+    src = open(os.path.join(ROOT, "include", header)).read()
     src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
     return sorted(set(re.findall(r"\b(zkb_[a-z_0-9]+)\s*\(", src)))
 
@@ -32,6 +32,12 @@ def test_header_symbols_are_exported(zkb):
         assert hasattr(L, s), f"{s} declared in include/zkb200.h but not exported"
     assert sorted(zkb.EXPORTS) == syms
     assert "sm_100a" in zkb.version()
+    # the synthetic workload generator is test / bench tooling: its own header and library, nothing of it in libzkb200.so
+    ssyms = declared_symbols("zkb200_synth.h")
+    S = ctypes.CDLL(zkb.SYNTH_LIB_PATH)
+    for s in ssyms:
+        assert hasattr(S, s) and not hasattr(L, s), s
+    assert sorted(zkb.SYNTH_EXPORTS) == ssyms
 
 
 def test_status_codes_match_header(zkb):
@@ -88,7 +94,7 @@ def test_header_is_plain_c_and_the_c_example_links(zkb, tmp_path):
     exe = tmp_path / "prove_example"
     lib_dir = os.path.dirname(zkb.LIB_PATH)
     subprocess.check_call(["gcc", "-std=c11", "-Wall", "-Werror", "-O2", "-I", os.path.join(ROOT, "include"),
-                           os.path.join(ROOT, "examples", "prove_example.c"), "-L", lib_dir, "-lzkb200",
+                           os.path.join(ROOT, "examples", "prove_example.c"), "-L", lib_dir, "-lzkb200", "-lzkb200_synth",
                            f"-Wl,-rpath,{lib_dir}", "-o", str(exe)])
     out = subprocess.run([str(exe)], capture_output=True, text=True, timeout=120)
     if zkb.device_count() == 0:

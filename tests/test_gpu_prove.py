@@ -167,7 +167,7 @@ def test_c_client_proof_is_accepted_and_byte_identical(zkb, oracle, tmp_path):
     exe, out = tmp_path / "prove_example", tmp_path / "proof.bin"
     lib_dir = os.path.dirname(zkb.LIB_PATH)
     subprocess.check_call(["gcc", "-std=c11", "-O2", "-I", os.path.join(root, "include"), os.path.join(root, "examples", "prove_example.c"),
-                           "-L", lib_dir, "-lzkb200", f"-Wl,-rpath,{lib_dir}", "-o", str(exe)])
+                           "-L", lib_dir, "-lzkb200", "-lzkb200_synth", f"-Wl,-rpath,{lib_dir}", "-o", str(exe)])
     subprocess.check_call([str(exe), "1", str(out)])
     proof = out.read_bytes()
     s = zkb.SynthCircuit(zk=True, seed=42, **zkb.TINY)

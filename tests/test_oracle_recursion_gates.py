@@ -84,3 +84,136 @@ def test_larger_recursion_circuit(oracle):
     assert s.check() == "" and s.info["degree_bits"] == 8
     c = oracle.Circuit(s.common, s.const_sigma_values)
     assert c.verify(c.prove(s.wires, s.public_inputs)) == ""
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Layout-independent SEMANTIC pins. The eight formulas cannot be compared with qp-plonky2 here, but WHAT each gate computes is
+# public knowledge: on rows the constraint checker accepts, the gate's output wires must equal the mathematical function of
+# its input wires, evaluated below by independent big-integer arithmetic (plain Lagrange interpolation, Horner's rule,
+# square-and-multiply, list indexing, the MDS matrix of SURVEY A.2). A wrong barycentric weight, accumulator order, bit order
+# or matrix index in oracle/gates.hpp would satisfy its own constraints and still fail here. What stays unpinned is only the
+# wire ORDER inside a row (which wire is "alpha", which is "old_acc"), which needs the L4 fixture.
+# ---------------------------------------------------------------------------------------------------------------------
+P = 0xFFFFFFFF00000001
+W = 7
+MDS_C = [17, 15, 41, 16, 2, 28, 13, 13, 39, 18, 34, 20]
+MDS_D = [8] + [0] * 11
+
+
+def e_add(x, y): return ((x[0] + y[0]) % P, (x[1] + y[1]) % P)
+def e_sub(x, y): return ((x[0] - y[0]) % P, (x[1] - y[1]) % P)
+def e_mul(x, y): return ((x[0] * y[0] + W * x[1] * y[1]) % P, (x[0] * y[1] + x[1] * y[0]) % P)
+def e_scale(x, s): return (x[0] * s % P, x[1] * s % P)
+def e_inv(x):
+    ninv = pow((x[0] * x[0] - W * x[1] * x[1]) % P, P - 2, P)
+    return (x[0] * ninv % P, (-x[1]) * ninv % P)
+
+
+def rows_of(s, gate):
+    return np.nonzero(gate_of_row(s) == GATE_ORDER.index(gate))[0]
+
+
+def row_wires(s, row):
+    return [int(x) for x in s.wires[:, row]]
+
+
+def row_consts(s, row):
+    nsel = 4
+    return [int(x) for x in s.const_sigma_values[nsel:s.info["num_constants"], row]]
+
+
+@pytest.fixture(scope="module")
+def big(oracle):
+    s = oracle.Synth(seed=17, n_poseidon=20, n_base_sum=4, n_arith=6, n_const=4, num_public_inputs=8, n_arith_ext=12,
+                     n_mul_ext=9, n_reducing=9, n_reducing_ext=9, n_random_access=10, n_exp=9, n_coset=9, n_mds=5)
+    assert s.check() == ""
+    return s
+
+
+def test_semantics_arithmetic_and_mul_extension(big):
+    for gate, per, nops in (("ArithmeticExtension", 8, 10), ("MulExtension", 6, 13)):
+        rows = rows_of(big, gate)
+        assert len(rows) >= 5
+        for r in rows:
+            w, k = row_wires(big, r), row_consts(big, r)
+            for i in range(nops):
+                a, b = (w[per * i], w[per * i + 1]), (w[per * i + 2], w[per * i + 3])
+                want = e_scale(e_mul(a, b), k[0])
+                if gate == "ArithmeticExtension":
+                    want = e_add(want, e_scale((w[per * i + 4], w[per * i + 5]), k[1]))
+                assert (w[per * i + per - 2], w[per * i + per - 1]) == want
+
+
+@pytest.mark.parametrize("gate,nc,ext", [("Reducing", 43, False), ("ReducingExtension", 32, True)])
+def test_semantics_reducing_is_horner(big, gate, nc, ext):
+    rows = rows_of(big, gate)
+    assert len(rows) >= 5
+    for r in rows:
+        w = row_wires(big, r)
+        out, alpha, acc = (w[0], w[1]), (w[2], w[3]), (w[4], w[5])
+        coeffs = [(w[6 + 2 * i], w[7 + 2 * i]) for i in range(nc)] if ext else [(w[6 + i], 0) for i in range(nc)]
+        assert any(c != (0, 0) for c in coeffs) and alpha != (0, 0)
+        for c in coeffs:                                   # Horner: ((old * a + c0) * a + c1) * a + ...
+            acc = e_add(e_mul(acc, alpha), c)
+        assert out == acc
+
+
+def test_semantics_exponentiation(big):
+    rows = rows_of(big, "Exponentiation")
+    assert len(rows) >= 5
+    for r in rows:
+        w = row_wires(big, r)
+        nb = 66
+        bits = w[1:1 + nb]
+        assert set(bits) <= {0, 1} and any(bits)
+        exponent = sum(b << i for i, b in enumerate(bits))          # little-endian power bits
+        assert w[nb + 1] == pow(w[0], exponent, P)
+
+
+def test_semantics_random_access(big):
+    rows = rows_of(big, "RandomAccess")
+    assert len(rows) >= 5
+    seen = set()
+    for r in rows:
+        w, k = row_wires(big, r), row_consts(big, r)
+        for cpy in range(4):
+            base = 18 * cpy
+            index, claimed, items = w[base], w[base + 1], w[base + 2: base + 18]
+            assert index < 16 and claimed == items[index]
+            seen.add(index)
+        for j in range(2):                                         # the two extra constant slots carry the gate constants
+            assert w[72 + j] == k[j]
+    assert len(seen) >= 6
+
+
+def test_semantics_coset_interpolation_is_lagrange(oracle, big):
+    rows = rows_of(big, "CosetInterpolation")
+    assert len(rows) >= 5
+    w16 = oracle.root_of_unity(4)
+    for r in rows:
+        w = row_wires(big, r)
+        shift = w[0]
+        vals = [(w[1 + 2 * k], w[2 + 2 * k]) for k in range(16)]
+        point, value = (w[33], w[34]), (w[35], w[36])
+        xs = [shift * pow(w16, k, P) % P for k in range(16)]
+        acc = (0, 0)
+        for k in range(16):                                        # plain Lagrange over the coset shift * <w16>
+            num, den = (1, 0), 1
+            for m in range(16):
+                if m != k:
+                    num = e_mul(num, e_sub(point, (xs[m], 0)))
+                    den = den * ((xs[k] - xs[m]) % P) % P
+            acc = e_add(acc, e_mul(vals[k], e_scale(num, pow(den, P - 2, P))))
+        assert shift != 0 and value == acc
+
+
+def test_semantics_poseidon_mds(big):
+    rows = rows_of(big, "PoseidonMds")
+    assert len(rows) >= 3
+    for r in rows:
+        w = row_wires(big, r)
+        for comp in range(2):
+            x = [w[2 * i + comp] for i in range(12)]
+            for o in range(12):
+                want = (sum(x[(i + o) % 12] * MDS_C[i] for i in range(12)) + x[o] * MDS_D[o]) % P
+                assert w[24 + 2 * o + comp] == want

@@ -1,7 +1,7 @@
 // C ABI of libzkb200.so (include/zkb200.h). No exception crosses this boundary; errors map to zkb_status.
 #include "../../include/zkb200.h"
 #include "prover.hpp"
-#include "synth.hpp"
+#include "engine.hpp"
 #include <cstring>
 #include <new>
 
@@ -10,8 +10,8 @@ using namespace zkb;
 struct zkb_circuit {
     std::unique_ptr<Circuit> impl;
 };
-struct zkb_synth {
-    SynthCircuit sc;
+struct zkb_engine {
+    std::unique_ptr<Engine> impl;
 };
 
 namespace {
@@ -21,15 +21,9 @@ template <class F>
 int guarded(F&& f) {
     try {
         return f();
-    } catch (const ParseError& e) { g_last_error = e.what(); return ZKB_E_PARSE;
-    } catch (const UnsupportedError& e) { g_last_error = e.what(); return ZKB_E_UNSUPPORTED_GATE;
-    } catch (const ArgError& e) { g_last_error = e.what(); return ZKB_E_ARG;
-    } catch (const DigestError& e) { g_last_error = e.what(); return ZKB_E_DIGEST;
-    } catch (const ZetaError& e) { g_last_error = e.what(); return ZKB_E_ZETA_IN_SUBGROUP;
-    } catch (const BufferError& e) { g_last_error = e.what(); return ZKB_E_BUFFER;
-    } catch (const CudaError& e) { g_last_error = e.what(); return ZKB_E_CUDA;
-    } catch (const std::bad_alloc&) { g_last_error = "out of host memory"; return ZKB_E_ARG;
-    } catch (const std::exception& e) { g_last_error = e.what(); return ZKB_E_CUDA; }
+    } catch (...) {
+        return status_of_current_exception(g_last_error);
+    }
 }
 
 void require_device(int device) {
@@ -99,10 +93,11 @@ int zkb_witness_upload(zkb_circuit* c, const uint64_t* wires) {
     });
 }
 int zkb_prove_resident(zkb_circuit* c, const uint64_t* public_inputs, size_t n_pi, const uint64_t* salts, uint64_t salt_seed,
-                       uint32_t pow_rule, uint8_t* proof_out, size_t proof_cap, size_t* proof_len) {
+                       uint32_t flags, uint8_t* proof_out, size_t proof_cap, size_t* proof_len) {
     int rc = guarded([&] {
         if (!c) throw ArgError("circuit is null");
-        size_t n = c->impl->prove_resident(public_inputs, n_pi, salts, salt_seed, pow_rule, proof_out, proof_cap);
+        if (flags & PF_WITNESS_RESIDENT) throw ArgError("ZKB_WITNESS_RESIDENT is an engine flag");
+        size_t n = c->impl->prove_resident(public_inputs, n_pi, salts, salt_seed, flags, proof_out, proof_cap);
         if (proof_len) *proof_len = n;
         return (int)ZKB_OK;
     });
@@ -110,14 +105,74 @@ int zkb_prove_resident(zkb_circuit* c, const uint64_t* public_inputs, size_t n_p
     return rc;
 }
 int zkb_prove(zkb_circuit* c, const uint64_t* wires, const uint64_t* public_inputs, size_t n_pi, const uint64_t* salts,
-              uint64_t salt_seed, uint32_t pow_rule, uint8_t* proof_out, size_t proof_cap, size_t* proof_len) {
+              uint64_t salt_seed, uint32_t flags, uint8_t* proof_out, size_t proof_cap, size_t* proof_len) {
     int rc = guarded([&] {
         if (!c) throw ArgError("circuit is null");
-        c->impl->upload_witness(wires, /*wait=*/false);      // the copy overlaps nothing here but saves one stream sync
+        if (flags & PF_WITNESS_RESIDENT) throw ArgError("ZKB_WITNESS_RESIDENT is an engine flag");
+        // every argument is validated BEFORE the asynchronous upload reads the caller's buffer: an early error return never
+        // leaves a copy in flight (prove_resident drains the stream on every later error path)
+        c->impl->validate_prove_args(public_inputs, n_pi, flags, proof_out, proof_cap);
+        c->impl->upload_witness(wires, /*wait=*/false);      // queued ahead of the proof's kernels: one stream wait fewer
+        size_t n = c->impl->prove_resident(public_inputs, n_pi, salts, salt_seed, flags, proof_out, proof_cap);
+        if (proof_len) *proof_len = n;
         return (int)ZKB_OK;
     });
-    if (rc != ZKB_OK) return rc;
-    return zkb_prove_resident(c, public_inputs, n_pi, salts, salt_seed, pow_rule, proof_out, proof_cap, proof_len);
+    if (rc == ZKB_E_BUFFER && proof_len && c) *proof_len = c->impl->common().proof_size();
+    return rc;
+}
+
+// ---- proof engine ----
+int zkb_engine_create(const uint8_t* common_bin, size_t common_len, const uint64_t* const_sigma, int is_values,
+                      const uint64_t circuit_digest[4], int device, int n_contexts, int n_slots, zkb_engine** out) {
+    return guarded([&] {
+        if (!out) throw ArgError("out is null");
+        *out = nullptr;
+        if (!common_bin || !const_sigma) throw ArgError("null argument");
+        (void)parse_common_data(common_bin, common_len);
+        require_device(device);
+        auto e = std::make_unique<zkb_engine>();
+        e->impl = std::make_unique<Engine>(common_bin, common_len, const_sigma, is_values != 0, circuit_digest, device, n_contexts, n_slots);
+        *out = e.release();
+        return (int)ZKB_OK;
+    });
+}
+int zkb_engine_destroy(zkb_engine* e) {
+    return guarded([&] { delete e; return (int)ZKB_OK; });
+}
+size_t zkb_engine_proof_size(const zkb_engine* e) { return e ? e->impl->common().proof_size() : 0; }
+int zkb_engine_acquire(zkb_engine* e, uint64_t** wires_buf) {
+    int slot = -1;
+    int rc = guarded([&] {
+        if (!e || !wires_buf) throw ArgError("null argument");
+        slot = e->impl->acquire(wires_buf);
+        return (int)ZKB_OK;
+    });
+    return rc == ZKB_OK ? slot : rc;
+}
+int zkb_engine_release(zkb_engine* e, int slot) {
+    return guarded([&] {
+        if (!e) throw ArgError("engine is null");
+        e->impl->release(slot);
+        return (int)ZKB_OK;
+    });
+}
+int zkb_engine_submit(zkb_engine* e, int slot, const uint64_t* public_inputs, size_t n_pi, const uint64_t* salts, uint64_t salt_seed,
+                      uint32_t flags, uint8_t* proof_out, size_t proof_cap) {
+    return guarded([&] {
+        if (!e) throw ArgError("engine is null");
+        e->impl->submit(slot, public_inputs, n_pi, salts, salt_seed, flags, proof_out, proof_cap);
+        return (int)ZKB_OK;
+    });
+}
+int zkb_engine_wait(zkb_engine* e, int slot, size_t* proof_len) {
+    int rc = guarded([&] {
+        if (!e) throw ArgError("engine is null");
+        std::string err;
+        int st = e->impl->wait(slot, proof_len, &err);
+        if (st != ZKB_OK) g_last_error = err;
+        return st;
+    });
+    return rc;
 }
 int zkb_last_timings(const zkb_circuit* c, float* ms_out, int cap) {
     if (!c || !ms_out) return 0;
@@ -282,62 +337,6 @@ int zkb_commit_cosets(const uint64_t* values, size_t ncols, size_t n, unsigned r
         cudaEventDestroy(e0); cudaEventDestroy(e1); cudaEventDestroy(e2);
         if (times_ms) { times_ms[0] = t_lde / reps; times_ms[1] = t_merkle / reps; }
         cuda_check(cudaMemcpy(cap_part_out, dg.get() + cap_off * 4, (size_t(32)) << cap_local, cudaMemcpyDeviceToHost), "D2H cap");
-        return (int)ZKB_OK;
-    });
-}
-
-// ---- synthetic workloads ----
-int zkb_synth_create(unsigned min_degree_bits, int zk, size_t n_poseidon, size_t n_base_sum, size_t n_arith, size_t n_const,
-                     size_t num_public_inputs, uint64_t seed, zkb_synth** out) {
-    return guarded([&] {
-        if (!out) throw ArgError("out is null");
-        *out = nullptr;
-        if (min_degree_bits > 20 || num_public_inputs > 1024) throw ArgError("bad synthetic circuit shape");
-        SynthSpec sp;
-        sp.min_degree_bits = min_degree_bits; sp.zk = zk != 0;
-        sp.n_poseidon = n_poseidon; sp.n_base_sum = n_base_sum; sp.n_arith = n_arith; sp.n_const = n_const;
-        sp.num_public_inputs = num_public_inputs; sp.seed = seed;
-        auto s = std::make_unique<zkb_synth>();
-        s->sc = make_synth_circuit(sp);
-        *out = s.release();
-        return (int)ZKB_OK;
-    });
-}
-int zkb_synth_create_recursion(unsigned min_degree_bits, int zk, size_t n_poseidon, size_t n_base_sum, size_t n_arith, size_t n_const,
-                               size_t num_public_inputs, uint64_t seed, const size_t recursion_rows[8], zkb_synth** out) {
-    return guarded([&] {
-        if (!out || !recursion_rows) throw ArgError("null argument");
-        *out = nullptr;
-        if (min_degree_bits > 20 || num_public_inputs > 1024) throw ArgError("bad synthetic circuit shape");
-        SynthSpec sp;
-        sp.min_degree_bits = min_degree_bits; sp.zk = zk != 0;
-        sp.n_poseidon = n_poseidon; sp.n_base_sum = n_base_sum; sp.n_arith = n_arith; sp.n_const = n_const;
-        sp.num_public_inputs = num_public_inputs; sp.seed = seed;
-        sp.n_arith_ext = recursion_rows[0]; sp.n_mul_ext = recursion_rows[1]; sp.n_reducing = recursion_rows[2];
-        sp.n_reducing_ext = recursion_rows[3]; sp.n_random_access = recursion_rows[4]; sp.n_exp = recursion_rows[5];
-        sp.n_coset = recursion_rows[6]; sp.n_mds = recursion_rows[7];
-        if (!sp.recursion()) throw ArgError("recursion_rows are all zero: use zkb_synth_create");
-        auto s = std::make_unique<zkb_synth>();
-        s->sc = make_synth_circuit(sp);
-        *out = s.release();
-        return (int)ZKB_OK;
-    });
-}
-int zkb_synth_destroy(zkb_synth* s) { delete s; return ZKB_OK; }
-size_t zkb_synth_num_constants(const zkb_synth* s) { return s ? s->sc.const_sigma_values.size() - 80 : 0; }
-size_t zkb_synth_common_len(const zkb_synth* s) { return s ? s->sc.common.size() : 0; }
-size_t zkb_synth_degree(const zkb_synth* s) { return s ? (size_t(1) << s->sc.degree_bits) : 0; }
-int zkb_synth_get(const zkb_synth* s, uint8_t* common, uint64_t* const_sigma_values, uint64_t* wires, uint64_t* public_inputs) {
-    return guarded([&] {
-        if (!s) throw ArgError("synth is null");
-        const SynthCircuit& sc = s->sc;
-        size_t n = size_t(1) << sc.degree_bits;
-        if (common) std::memcpy(common, sc.common.data(), sc.common.size());
-        if (const_sigma_values)
-            for (size_t c = 0; c < sc.const_sigma_values.size(); ++c) std::memcpy(const_sigma_values + c * n, sc.const_sigma_values[c].data(), n * 8);
-        if (wires)
-            for (size_t c = 0; c < sc.wires.size(); ++c) std::memcpy(wires + c * n, sc.wires[c].data(), n * 8);
-        if (public_inputs) std::memcpy(public_inputs, sc.public_inputs.data(), sc.public_inputs.size() * 8);
         return (int)ZKB_OK;
     });
 }

@@ -393,6 +393,42 @@ void launch_salt_fill(u64* out, size_t stride, size_t num_leaves, u64 seed, unsi
     salt_fill_kernel<<<grid, 256, 0, st>>>(out, stride, num_leaves, seed, batch);
 }
 
+// Production salts: the blinding columns hide the opened leaves' neighbours only if they are unpredictable, so they come from
+// a CSPRNG — ChaCha20 (RFC 8439 block function, 20 rounds) keyed per proof with 256 bits the host reads from the OS
+// (getrandom). Block t of the key stream (64-bit counter t, nonce word = batch) gives 8 consecutive words of the flat
+// [4][stride] salt array; a 64-bit word is mapped to the field by one conditional subtraction of p (statistical distance from
+// uniform 2^-32 per element — qp-plonky2 samples F::rand by rejection; the difference is not observable by a verifier).
+struct ChaChaKey { u32 k[8]; };
+ZKB_D u32 rotl32(u32 x, int r) { return __funnelshift_l(x, x, r); }
+#define ZKB_QR(a, b, c, d) a += b; d = rotl32(d ^ a, 16); c += d; b = rotl32(b ^ c, 12); a += b; d = rotl32(d ^ a, 8); c += d; b = rotl32(b ^ c, 7)
+__global__ void __launch_bounds__(256) salt_chacha_kernel(u64* out, size_t words, ChaChaKey key, u32 batch) {
+    const size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if (t * 8 >= words) return;
+    u32 in[16] = {0x61707865u, 0x3320646eu, 0x79622d32u, 0x6b206574u, key.k[0], key.k[1], key.k[2], key.k[3], key.k[4], key.k[5],
+                  key.k[6], key.k[7], (u32)t, (u32)(t >> 32), batch, 0x7a6b6232u};
+    u32 x[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) x[i] = in[i];
+#pragma unroll 2
+    for (int r = 0; r < 10; ++r) {
+        ZKB_QR(x[0], x[4], x[8], x[12]); ZKB_QR(x[1], x[5], x[9], x[13]); ZKB_QR(x[2], x[6], x[10], x[14]); ZKB_QR(x[3], x[7], x[11], x[15]);
+        ZKB_QR(x[0], x[5], x[10], x[15]); ZKB_QR(x[1], x[6], x[11], x[12]); ZKB_QR(x[2], x[7], x[8], x[13]); ZKB_QR(x[3], x[4], x[9], x[14]);
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const u64 v = gl_pack(x[2 * i] + in[2 * i], x[2 * i + 1] + in[2 * i + 1]);
+        if (t * 8 + i < words) out[t * 8 + i] = gl_canon(v);
+    }
+}
+void launch_salt_fill_csprng(u64* out, size_t words, const u32 key[8], unsigned batch, cudaStream_t st) {
+    if (!words) return;
+    ChaChaKey k;
+    for (int i = 0; i < 8; ++i) k.k[i] = key[i];
+    const size_t blocks = (words / 8 + 255) / 256 + 1;
+    ZKB_COUNT_LAUNCH();
+    salt_chacha_kernel<<<(unsigned)blocks, 256, 0, st>>>(out, words, k, (u32)batch);
+}
+
 // ---------------------------------------------------------------------------------------------
 // NTT family: host side. Kernels are in ntt.cuh. n <= 2^14: one shared-memory kernel per transform; larger n: two steps
 // (n = n1 * n2: n1-point transforms down TB-wide column tiles + twiddle, then contiguous n2-point transforms).
@@ -737,6 +773,10 @@ struct QuotientArgs {
     // sliced mode (small circuits, part != nullptr): the launch's work items are spread over blockIdx.y and every slice
     // stores its raw sums in its own slot part[(slot_base + blockIdx.y)][ch][N]; quotient_combine_kernel adds the slots
     u64* part; int slot_base;
+    // witness self-check (ZKB_CHECK_WITNESS): the same constraint code evaluated on the SUBGROUP H instead of the LDE coset —
+    // cs / w / z are then VALUES over H in natural order (stride n), every filtered constraint sum must be zero, and the last
+    // launch raises bit 1 of *unsat_flag instead of dividing by Z_H (which vanishes on H)
+    int on_h; unsigned* unsat_flag;
 };
 
 // (g0, g1) += c * (p0, p1): deliberately NOT inlined — the quotient kernel has ~150 call sites and its straight-line
@@ -754,14 +794,14 @@ __device__ __noinline__ u64 q_sbox7(u64 x) { return gl_sbox7(x); }
 template <int PART>
 __global__ void __launch_bounds__(128, PART == 3 ? 4 : 8) quotient_kernel(QuotientArgs a) {
     const QuotientParams& P = *a.p;
-    const unsigned lgN = P.lg_n + P.rate_bits;
+    const unsigned lgN = a.on_h ? P.lg_n : P.lg_n + P.rate_bits;
     const size_t N = size_t(1) << lgN;
     size_t l = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
     if (l >= N) return;
-    const u32 i = bitrev32((u32)l, lgN);
+    const u32 i = a.on_h ? (u32)l : bitrev32((u32)l, lgN);
     const u32 rate_mask = (1u << P.rate_bits) - 1;
-    const size_t l_next = bitrev32((u32)((i + (1u << P.rate_bits)) & (N - 1)), lgN);
-    const u64 x = f_mul(GL_GEN, root_pow_lg(lgN, i, false));
+    const size_t l_next = a.on_h ? ((l + 1) & (N - 1)) : bitrev32((u32)((i + (1u << P.rate_bits)) & (N - 1)), lgN);
+    const u64 x = a.on_h ? root_pow_lg(lgN, i, false) : f_mul(GL_GEN, root_pow_lg(lgN, i, false));
     const int nch = P.num_challenges, npp = P.num_partial_products, nchunks = npp + 1, chunk = P.qdf;
     const u64* cs = a.cs + l;
     const u64* w = a.w + l;
@@ -781,7 +821,8 @@ __global__ void __launch_bounds__(128, PART == 3 ? 4 : 8) quotient_kernel(Quotie
     const int slice = blockIdx.y, nsl = gridDim.y;
     if (PART == 1) {
     // L0(x) (Z - 1)
-    u64 l0 = f_mul(P.zh[i & rate_mask], gl_inv(f_mul(gl_canon(u64(1) << P.lg_n), f_sub(x, 1))));
+    // on H: L0 is the indicator of the first row
+    u64 l0 = a.on_h ? (u64)(i == 0) : f_mul(P.zh[i & rate_mask], gl_inv(f_mul(gl_canon(u64(1) << P.lg_n), f_sub(x, 1))));
     for (int ch = 0; ch < nch; ++ch) {
         if (nsl > 1 && slice != ch) continue;
         term = ch;
@@ -1096,6 +1137,9 @@ __global__ void __launch_bounds__(128, PART == 3 ? 4 : 8) quotient_kernel(Quotie
     } else if (PART == 3) {
         a.out[l] = f_add(acc0, a.out[l]);
         if (nch > 1) a.out[a.out_stride + l] = f_add(acc1, a.out[a.out_stride + l]);
+    } else if (a.on_h) {
+        const u64 v0 = f_add(acc0, a.out[l]), v1 = nch > 1 ? f_add(acc1, a.out[a.out_stride + l]) : 0;
+        if (v0 | v1) atomicOr(a.unsat_flag, 2u);
     } else {
         u64 zi = P.zh_inv[i & rate_mask];
         a.out[l] = f_mul(f_add(acc0, a.out[l]), zi);
@@ -1125,7 +1169,8 @@ int quotient_slots(const QuotientParams& ph) {
 void launch_quotient(const QuotientParams* params_dev, const QuotientParams& ph, const u64* apow_dev, int nterms,
                      const u64* cs_lde, size_t cs_stride, const u64* wires_lde, size_t w_stride, const u64* zs_lde,
                      size_t z_stride, u64* out, size_t out_stride, cudaStream_t st, const QuotientFork* fork) {
-    QuotientArgs a{params_dev, apow_dev, nterms, cs_lde, cs_stride, wires_lde, w_stride, zs_lde, z_stride, out, out_stride, nullptr, 0};
+    QuotientArgs a{params_dev, apow_dev, nterms, cs_lde, cs_stride, wires_lde, w_stride, zs_lde, z_stride, out, out_stride, nullptr, 0,
+                   0, nullptr};
     size_t N = size_t(1) << (ph.lg_n + ph.rate_bits);
     const unsigned gx = (unsigned)((N + 127) / 128);
     if (fork && fork->part) {
@@ -1159,6 +1204,24 @@ void launch_quotient(const QuotientParams* params_dev, const QuotientParams& ph,
         quotient_combine_kernel<<<dim3(gx, ph.num_challenges), 128, 0, st>>>(params_dev, fork->part, s1 + rec + 1, out, out_stride);
         return;
     }
+    ZKB_COUNT_LAUNCH();
+    quotient_kernel<1><<<gx, 128, 0, st>>>(a);
+    if (ph.has_recursion_gates) {
+        ZKB_COUNT_LAUNCH();
+        quotient_kernel<3><<<gx, 128, 0, st>>>(a);
+    }
+    ZKB_COUNT_LAUNCH();
+    quotient_kernel<2><<<gx, 128, 0, st>>>(a);
+}
+
+// the witness self-check: all three launches over the n points of H (values, natural order), flag bit 1 on a violation
+void launch_constraint_check(const QuotientParams* params_dev, const QuotientParams& ph, const u64* apow_dev, int nterms,
+                             const u64* cs_vals, size_t cs_stride, const u64* wires_vals, size_t w_stride, const u64* zs_vals,
+                             size_t z_stride, u64* scratch, size_t scratch_stride, unsigned* flag_dev, cudaStream_t st) {
+    QuotientArgs a{params_dev, apow_dev, nterms, cs_vals, cs_stride, wires_vals, w_stride, zs_vals, z_stride, scratch, scratch_stride,
+                   nullptr, 0, 1, flag_dev};
+    const size_t n = size_t(1) << ph.lg_n;
+    const unsigned gx = (unsigned)((n + 127) / 128);
     ZKB_COUNT_LAUNCH();
     quotient_kernel<1><<<gx, 128, 0, st>>>(a);
     if (ph.has_recursion_gates) {

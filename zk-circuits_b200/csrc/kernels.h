@@ -51,6 +51,9 @@ void launch_bitrev_permute(u64* data, size_t stride, int ncols, unsigned lg_n, c
 void launch_canonical_check(const u64* v, size_t count, unsigned* flag_dev, cudaStream_t st);
 // salt columns: out[s * stride + l] = salt_value(seed, batch, s, l)  (documented SplitMix64 generator)
 void launch_salt_fill(u64* out, size_t stride, size_t num_leaves, u64 seed, unsigned batch, cudaStream_t st);
+// production salts: `words` field elements from the ChaCha20 key stream of `key` (256 bits from the OS RNG, per proof),
+// nonce = batch; out is the flat [4][stride] salt block of a batch
+void launch_salt_fill_csprng(u64* out, size_t words, const u32 key[8], unsigned batch, cudaStream_t st);
 
 // ---- prover stages ----
 // param / p2 / p3: Constant num_consts; BaseSum num_limbs; Arithmetic, ArithmeticExtension, MulExtension num_ops;
@@ -86,6 +89,12 @@ int quotient_slots(const QuotientParams& params_host);
 void launch_quotient(const QuotientParams* params_dev, const QuotientParams& params_host, const u64* apow_dev, int nterms,
                      const u64* cs_lde, size_t cs_stride, const u64* wires_lde, size_t w_stride, const u64* zs_lde,
                      size_t z_stride, u64* out, size_t out_stride, cudaStream_t st, const QuotientFork* fork = nullptr);
+// ZKB_CHECK_WITNESS: evaluate every constraint (permutation argument included) at the n points of the subgroup H from VALUES
+// in natural order (cs_vals [num_constants + num_routed][n], wires_vals, zs_vals) with the powers of a check challenge in
+// apow_dev; *flag_dev |= 2 if any point's combination is non-zero. scratch: num_challenges * n words.
+void launch_constraint_check(const QuotientParams* params_dev, const QuotientParams& params_host, const u64* apow_dev, int nterms,
+                             const u64* cs_vals, size_t cs_stride, const u64* wires_vals, size_t w_stride, const u64* zs_vals,
+                             size_t z_stride, u64* scratch, size_t scratch_stride, unsigned* flag_dev, cudaStream_t st);
 // evaluate ncols coefficient polynomials (n each) at the ext point z: out[2*c], out[2*c+1]
 void launch_eval_polys(const u64* coeffs, size_t stride, int ncols, unsigned lg_n, const u64* zpow_a, const u64* zpow_b,
                        u64* out, cudaStream_t st);

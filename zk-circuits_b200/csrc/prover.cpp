@@ -3,14 +3,14 @@
 #include <atomic>
 #include <cstdlib>
 #include <cstring>
+#include <cerrno>
 #include <chrono>
 #include <cstdio>
 #include <mutex>
 #include <thread>
+#include <sys/random.h>
 
 namespace zkb {
-
-static std::atomic<int> g_live_contexts{0};     // prover contexts alive in this process (see Circuit::sync)
 
 void cuda_check(cudaError_t e, const char* what) {
     if (e != cudaSuccess) throw CudaError(std::string(what) + ": " + cudaGetErrorString(e));
@@ -46,6 +46,22 @@ void check_canonical(const u64* v, size_t n, const char* what) {
 Circuit::Circuit(const uint8_t* common, size_t len, const u64* const_sigma, bool is_values, const u64* digest, int device)
     : cd_(parse_common_data(common, len)), device_(device) {
     if (!const_sigma) throw ArgError("const_sigma is null");
+    // host-only checks first: nothing is allocated when they fail
+    check_canonical(const_sigma, (size_t)(cd_.num_constants + cd_.num_routed_wires) << cd_.degree_bits, "const_sigma");
+    if (cd_.num_challenges > 2) throw UnsupportedError("more than two challenges");
+    int ndev = 0;
+    CK(cudaGetDeviceCount(&ndev));
+    if (device < 0 || device >= ndev) throw ArgError("bad device index");
+    // a constructor that throws does not run the destructor: release streams, events, pinned and device memory here
+    try {
+        init(const_sigma, is_values, digest);
+    } catch (...) {
+        cleanup();
+        throw;
+    }
+}
+
+void Circuit::init(const u64* const_sigma, bool is_values, const u64* digest) {
     // ZKB_TRACE=1: wall-clock checkpoints of the context build on stderr (which part of zkb_circuit_create costs what)
     const bool trace = std::getenv("ZKB_TRACE") != nullptr;
     const auto t_begin = std::chrono::steady_clock::now();
@@ -53,15 +69,11 @@ Circuit::Circuit(const uint8_t* common, size_t len, const u64* const_sigma, bool
         if (trace) std::fprintf(stderr, "[zkb create] %-28s %8.3f ms\n", what,
                                 std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_begin).count());
     };
-    int ndev = 0;
-    CK(cudaGetDeviceCount(&ndev));
-    if (device < 0 || device >= ndev) throw ArgError("bad device index");
-    DeviceGuard g(device);
-    device_tables_init(device);
+    DeviceGuard g(device_);
+    device_tables_init(device_);
     CK(cudaStreamCreateWithFlags(&st_, cudaStreamNonBlocking));
     for (auto& e : ev_) CK(cudaEventCreate(&e));
     CK(cudaEventCreateWithFlags(&sync_ev_, cudaEventBlockingSync | cudaEventDisableTiming));
-    ++g_live_contexts;
     lg_n_ = (unsigned)cd_.degree_bits;
     lg_N_ = lg_n_ + (unsigned)cd_.rate_bits;
     n_ = size_t(1) << lg_n_;
@@ -71,8 +83,6 @@ Circuit::Circuit(const uint8_t* common, size_t len, const u64* const_sigma, bool
     const int salt = (int)cd_.salt_size();
     const unsigned cap_h = (unsigned)cd_.cap_height;
     mark("stream, events, tables");
-    check_canonical(const_sigma, (size_t)ncs * n_, "const_sigma");
-    mark("host canonical check");
 
     // plan every device buffer, then carve them out of one allocation (256-byte aligned slices)
     std::vector<std::pair<DevBuf*, size_t>> plan;
@@ -88,7 +98,7 @@ Circuit::Circuit(const uint8_t* common, size_t len, const u64* const_sigma, bool
     init_batch(wires_, nw, salt, true);
     init_batch(zs_, nzp, salt, false);
     init_batch(quot_, nq, salt, false);
-    want(sigma_vals_, (size_t)cd_.num_routed_wires * n_);
+    want(cs_vals_, (size_t)ncs * n_);
     want(wires_vals_, (size_t)nw * n_);
     want(zs_vals_, (size_t)nzp * n_);
     want(q_, (size_t)nch * N_);
@@ -130,7 +140,8 @@ Circuit::Circuit(const uint8_t* common, size_t len, const u64* const_sigma, bool
     want(pow_dev_, 16);
     want(flag_dev_, 1);
     const size_t nqr = cd_.num_query_rounds;
-    want(query_idx_dev_, ((1 + L) * nqr + 1) / 2 + 1);
+    const size_t idx_words = ((1 + L) * nqr + 1) / 2 + 1;
+    want(query_idx_dev_, idx_words);
     // query gather buffer
     size_t qwords = 0;
     {
@@ -142,6 +153,7 @@ Circuit::Circuit(const uint8_t* common, size_t len, const u64* const_sigma, bool
             qwords += nqr * ((size_t(2) << ab) + 4 * (bits >= cap_h ? bits - cap_h : 0));
         }
     }
+    q_words_ = qwords;
     want(query_out_dev_, qwords);
     {
         auto round32 = [](size_t w) { return (w + 31) & ~size_t(31); };
@@ -158,32 +170,44 @@ Circuit::Circuit(const uint8_t* common, size_t len, const u64* const_sigma, bool
     zs_.coeff_ptr = zs_vals_.get(); zs_.coeff_stride = n_;
     quot_.coeff_ptr = q_.get(); quot_.coeff_stride = n_;     // chunk (ch, m) = q[ch*N + m*n ..]
     if (q_sliced_) qfork_.part = qpart_.get();
-    h_stage_words_ = qwords + 4096 + 2 * (size_t)(nall + nch) + 2 * cd_.final_poly_len() + 2 * nall;
-    h_qp_off_ = h_stage_words_;     // separate region for the quotient parameters + alpha powers
-    h_stage_words_ += (sizeof(QuotientParams) + 7) / 8 + (size_t)nch * nterms + 8;
     mark("device buffers");
+    // pinned staging: every region sized from the circuit's own parameters (cap height, layers, query rounds)
+    {
+        const size_t cap_words = size_t(4) << cap_h;
+        size_t off = 0;
+        auto region = [&](size_t words) { size_t at = off; off += (words + 7) & ~size_t(7); return at; };
+        ho_.caps = region((3 + L) * cap_words);
+        ho_.open = region(2 * (size_t)(nall + nch));
+        ho_.apow = region(2 * (size_t)nall);
+        ho_.fin = region(2 * cd_.final_poly_len());
+        ho_.pow = region(16);
+        ho_.flag = region(1);
+        ho_.idx = region(idx_words);
+        ho_.q = region(qwords);
+        ho_.qp = region((sizeof(QuotientParams) + 7) / 8 + (size_t)nch * nterms);
+        h_stage_words_ = off;
+    }
     CK(cudaMallocHost(&h_stage_, h_stage_words_ * sizeof(u64)));
     mark("pinned staging");
 
+    CK(cudaMemsetAsync(flag_dev_.get(), 0, sizeof(u64), st_));
     CK(cudaMemcpyAsync(k_is_dev_.get(), cd_.k_is.data(), cd_.k_is.size() * 8, cudaMemcpyHostToDevice, st_));
     // ---- constants/sigmas commitment (the part of CircuitBuilder::build the prover needs) ----
-    const size_t nconst = cd_.num_constants;
+    CK(cudaMemcpyAsync(cs_.coeff_ptr, const_sigma, (size_t)ncs * n_ * 8, cudaMemcpyHostToDevice, st_));
     if (is_values) {
-        CK(cudaMemcpyAsync(cs_.coeff_ptr, const_sigma, (size_t)ncs * n_ * 8, cudaMemcpyHostToDevice, st_));
-        CK(cudaMemcpyAsync(sigma_vals_.get(), cs_.coeff_ptr + nconst * n_, cd_.num_routed_wires * n_ * 8, cudaMemcpyDeviceToDevice, st_));
+        CK(cudaMemcpyAsync(cs_vals_.get(), cs_.coeff_ptr, (size_t)ncs * n_ * 8, cudaMemcpyDeviceToDevice, st_));
         launch_intt_natural(cs_.coeff_ptr, n_, cs_.coeff_ptr, n_, ncs, lg_n_, nullptr, st_);
     } else {
-        CK(cudaMemcpyAsync(cs_.coeff_ptr, const_sigma, (size_t)ncs * n_ * 8, cudaMemcpyHostToDevice, st_));
-        // sigma values over H: evaluate on <w_n> (rate 0, shift 1) then undo the leaf ordering
-        launch_lde(cs_.coeff_ptr + nconst * n_, n_, sigma_vals_.get(), n_, (int)cd_.num_routed_wires, lg_n_, 0, 1, st_);
-        launch_bitrev_permute(sigma_vals_.get(), n_, (int)cd_.num_routed_wires, lg_n_, st_);
+        // values over H: evaluate on <w_n> (rate 0, shift 1) then undo the leaf ordering
+        launch_lde(cs_.coeff_ptr, n_, cs_vals_.get(), n_, ncs, lg_n_, 0, 1, st_);
+        launch_bitrev_permute(cs_vals_.get(), n_, ncs, lg_n_, st_);
     }
     cs_cap_.resize((size_t(4)) << cap_h);
-    commit_batch(cs_, 0, nullptr, 0, h_stage_);
+    commit_batch(cs_, 0, h_stage_ + ho_.caps);
     mark("uploads and launches queued");
     sync();
     mark("constants/sigmas commitment");
-    std::memcpy(cs_cap_.data(), h_stage_, cs_cap_.size() * 8);
+    std::memcpy(cs_cap_.data(), h_stage_ + ho_.caps, cs_cap_.size() * 8);
     // circuit_digest = hash_no_pad(cap ‖ hash_pad([]) ‖ [degree_bits])   
     std::vector<u64> parts(cs_cap_);
     u64 ds[4];
@@ -197,18 +221,22 @@ Circuit::Circuit(const uint8_t* common, size_t len, const u64* const_sigma, bool
     }
 }
 
-Circuit::~Circuit() {
+void Circuit::cleanup() {
     cudaSetDevice(device_);
     if (st_) cudaStreamSynchronize(st_);
     for (auto& kv : level_graphs_) if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
-    for (auto& e : ev_) if (e) cudaEventDestroy(e);
-    for (auto& a : qfork_.aux) if (a) { cudaStreamSynchronize(a); cudaStreamDestroy(a); }
-    if (qfork_.fork) cudaEventDestroy(qfork_.fork);
-    for (auto& e : qfork_.join) if (e) cudaEventDestroy(e);
-    if (sync_ev_) { cudaEventDestroy(sync_ev_); --g_live_contexts; }
-    if (h_stage_) cudaFreeHost(h_stage_);
-    if (st_) cudaStreamDestroy(st_);
+    level_graphs_.clear();
+    for (auto& e : ev_) if (e) { cudaEventDestroy(e); e = nullptr; }
+    for (auto& a : qfork_.aux) if (a) { cudaStreamSynchronize(a); cudaStreamDestroy(a); a = nullptr; }
+    if (qfork_.fork) { cudaEventDestroy(qfork_.fork); qfork_.fork = nullptr; }
+    for (auto& e : qfork_.join) if (e) { cudaEventDestroy(e); e = nullptr; }
+    if (sync_ev_) { cudaEventDestroy(sync_ev_); sync_ev_ = nullptr; }
+    if (h_stage_) { cudaFreeHost(h_stage_); h_stage_ = nullptr; }
+    if (st_) { cudaStreamDestroy(st_); st_ = nullptr; }
+    arena_.release();
 }
+
+Circuit::~Circuit() { cleanup(); }
 
 // Host waits on the stream ~10 times per proof. Spinning (the runtime's default) gives the lowest latency. With more
 // proofs in flight in a process than host cores available to it (8 ranks x 8 streams on a 32-core box) the wait polls
@@ -217,10 +245,6 @@ Circuit::~Circuit() {
 // spinning 1419, 8 streams yielding 1410 (profiles/r01_bench_n8_sync_modes.json). A blocking (interrupt) wait is much
 // worse (708). ZKB_SYNC=spin|yield|block|sleep overrides the choice.
 static std::atomic<int> g_proofs_in_flight{0};
-struct InFlight {
-    InFlight() { ++g_proofs_in_flight; }
-    ~InFlight() { --g_proofs_in_flight; }
-};
 static int sync_mode() {      // 0 spin, 1 yield, 2 block, 3 sleep-poll
     if (const char* e = std::getenv("ZKB_SYNC")) {
         if (!std::strcmp(e, "sleep")) return 3;
@@ -280,55 +304,77 @@ void Circuit::verifier_only(u64* cap_out, u64 digest_out[4]) const {
     if (digest_out) std::memcpy(digest_out, circuit_digest_, 32);
 }
 
+// salt columns of a blinded batch: the caller's (explicit), the documented seeded stream (ZKB_SALTS_FROM_SEED: parity tests),
+// or — the default — ChaCha20 keyed from the OS RNG for this proof
+void Circuit::fill_salts(BatchDev& b, unsigned batch_id) {
+    if (!b.salt) return;
+    u64* sp = b.lde.get() + (size_t)b.ncols * N_;
+    const size_t words = (size_t)b.salt * N_;
+    if (job_.salt_ptr[batch_id]) {
+        CK(cudaMemcpyAsync(sp, job_.salt_ptr[batch_id], words * 8, cudaMemcpyHostToDevice, st_));
+        launch_canonical_check(sp, words, reinterpret_cast<unsigned*>(flag_dev_.get()), st_);
+    } else if (job_.flags & PF_SALTS_FROM_SEED) {
+        launch_salt_fill(sp, N_, N_, job_.salt_seed, batch_id, st_);
+    } else {
+        launch_salt_fill_csprng(sp, words, job_.salt_key, batch_id, st_);
+    }
+}
+
 // LDE (+ salts) + Merkle for a batch whose coefficients are in place; cap is copied to cap_host (pinned) asynchronously
-void Circuit::commit_batch(BatchDev& b, unsigned batch_id, const u64* salts_host, u64 salt_seed, u64* cap_host) {
+void Circuit::commit_batch(BatchDev& b, unsigned batch_id, u64* cap_host) {
     const unsigned cap_h = (unsigned)cd_.cap_height;
     launch_lde(b.coeff_ptr, b.coeff_stride, b.lde.get(), N_, b.ncols, lg_n_, (unsigned)cd_.rate_bits, GL_GEN, st_);
-    if (b.salt) {
-        u64* sp = b.lde.get() + (size_t)b.ncols * N_;
-        if (salts_host) CK(cudaMemcpyAsync(sp, salts_host, (size_t)b.salt * N_ * 8, cudaMemcpyHostToDevice, st_));
-        else launch_salt_fill(sp, N_, N_, salt_seed, batch_id, st_);
-    }
+    if (&b != &cs_) fill_salts(b, batch_id);
     launch_merkle_leaves(b.lde.get(), N_, b.ncols + b.salt, N_, b.digests.get(), st_);
     b.cap_offset = run_merkle_levels(b.digests.get(), N_, cap_h);
     CK(cudaMemcpyAsync(cap_host, b.digests.get() + b.cap_offset * 4, (size_t(32)) << cap_h, cudaMemcpyDeviceToHost, st_));
 }
 
 // H2D of the wire matrix + canonical check on the device. With wait = false nothing synchronises: the copy and the check
-// are queued ahead of the proof's kernels and the flag is read at the proof's first sync point (zkb_prove path).
+// are queued ahead of the proof's kernels and the flag is read at the proof's first stage boundary (zkb_prove path).
 void Circuit::upload_witness(const u64* wires_host, bool wait) {
     if (!wires_host) throw ArgError("wires is null");
+    if (busy()) throw ArgError("a proof is in flight on this context");
     DeviceGuard g(device_);
     unsigned* flag = reinterpret_cast<unsigned*>(flag_dev_.get());
     CK(cudaMemsetAsync(flag, 0, sizeof(u64), st_));
     CK(cudaMemcpyAsync(wires_vals_.get(), wires_host, cd_.num_wires * n_ * 8, cudaMemcpyHostToDevice, st_));
     launch_canonical_check(wires_vals_.get(), cd_.num_wires * n_, flag, st_);
-    check_pending_ = true;
+    witness_loaded_ = true;
     if (wait) {
+        queue_flag_readback();
         sync();
-        finish_witness_check();
+        try {
+            check_flags();
+        } catch (...) {
+            witness_loaded_ = false;
+            throw;
+        }
     }
 }
-void Circuit::finish_witness_check() {     // stream must be idle
-    if (!check_pending_) return;
-    check_pending_ = false;
-    u64 f = 0;
-    CK(cudaMemcpy(&f, flag_dev_.get(), sizeof(u64), cudaMemcpyDeviceToHost));
-    if (f) throw ArgError("wires: non-canonical field element");
+void Circuit::queue_flag_readback() {
+    CK(cudaMemcpyAsync(h_stage_ + ho_.flag, flag_dev_.get(), sizeof(u64), cudaMemcpyDeviceToHost, st_));
+}
+void Circuit::check_flags() {     // stream must be idle
+    const u64 f = h_stage_[ho_.flag];
+    if (f & 1) throw ArgError("non-canonical field element in the wires or salts");
+    if (f & 2) throw UnsatError("the witness does not satisfy the circuit (a gate or copy constraint fails on the subgroup)");
 }
 
 void Circuit::run_partial_products(const u64* betas, const u64* gammas) {
     u64 bg[8];
     const int nch = (int)cd_.num_challenges;
     for (int c = 0; c < nch; ++c) { bg[c] = betas[c]; bg[nch + c] = gammas[c]; }
-    launch_partial_products(wires_vals_.get(), n_, sigma_vals_.get(), n_, k_is_dev_.get(), (int)cd_.num_routed_wires,
-                            (int)cd_.quotient_degree_factor, nch, bg, lg_n_, zs_vals_.get(), n_, pp_scratch_.get(), st_);
+    launch_partial_products(wires_vals_.get(), n_, cs_vals_.get() + cd_.num_constants * n_, n_, k_is_dev_.get(),
+                            (int)cd_.num_routed_wires, (int)cd_.quotient_degree_factor, nch, bg, lg_n_, zs_vals_.get(), n_,
+                            pp_scratch_.get(), st_);
 }
 
-void Circuit::run_quotient(const u64* pi_hash, const u64* betas, const u64* gammas, const u64* alphas) {
+// QuotientParams + powers of the combination challenges into the pinned staging block, then to the device (stream order)
+void Circuit::fill_quotient_params(const u64* pi_hash, const u64* betas, const u64* gammas, const u64* alphas) {
     const int nch = (int)cd_.num_challenges;
     const int nterms = nch * (2 + (int)cd_.num_partial_products) + (int)cd_.num_gate_constraints;
-    QuotientParams* qp = reinterpret_cast<QuotientParams*>(h_stage_ + h_qp_off_);
+    QuotientParams* qp = reinterpret_cast<QuotientParams*>(h_stage_ + ho_.qp);
     std::memset(qp, 0, sizeof(QuotientParams));
     qp->lg_n = lg_n_; qp->rate_bits = (unsigned)cd_.rate_bits;
     qp->num_wires = (int)cd_.num_wires; qp->num_routed = (int)cd_.num_routed_wires; qp->num_constants = (int)cd_.num_constants;
@@ -355,23 +401,50 @@ void Circuit::run_quotient(const u64* pi_hash, const u64* betas, const u64* gamm
         qp->zh[j] = gl_sub(gl_mul(g_n, gl_pow(w_rate, j)), 1);
         qp->zh_inv[j] = gl_inv(qp->zh[j]);
     }
-    u64* ap = h_stage_ + h_qp_off_ + (sizeof(QuotientParams) + 7) / 8;
+    u64* ap = h_stage_ + ho_.qp + (sizeof(QuotientParams) + 7) / 8;
     for (int c = 0; c < nch; ++c) {
         u64 p = 1;
         for (int k = 0; k < nterms; ++k) { ap[(size_t)c * nterms + k] = p; p = gl_mul(p, alphas[c]); }
     }
     CK(cudaMemcpyAsync(qparams_dev_.get(), qp, sizeof(QuotientParams), cudaMemcpyHostToDevice, st_));
     CK(cudaMemcpyAsync(apow_dev_.get(), ap, (size_t)nch * nterms * 8, cudaMemcpyHostToDevice, st_));
+}
+
+void Circuit::run_quotient(const u64* pi_hash, const u64* betas, const u64* gammas, const u64* alphas) {
+    const int nch = (int)cd_.num_challenges;
+    const int nterms = nch * (2 + (int)cd_.num_partial_products) + (int)cd_.num_gate_constraints;
+    fill_quotient_params(pi_hash, betas, gammas, alphas);
+    const QuotientParams* qp = reinterpret_cast<const QuotientParams*>(h_stage_ + ho_.qp);
     launch_quotient(reinterpret_cast<const QuotientParams*>(qparams_dev_.get()), *qp, apow_dev_.get(), nterms, cs_.lde.get(), N_,
                     wires_.lde.get(), N_, zs_.lde.get(), N_, q_.get(), N_, st_, q_sliced_ ? &qfork_ : nullptr);
     // values on the coset (leaf order) -> coefficients; chunks of n are the committed quotient polynomials
     launch_coset_intt_bitrev(q_.get(), N_, nch, lg_N_, GL_GEN, st_);
 }
 
+// ZKB_CHECK_WITNESS (SURVEY §8b's optional self-check, done where the data already is): every constraint of the vanishing
+// polynomial — gates with their selector filters, Z(1) = 1, the partial-product chain and its wrap-around, i.e. the copy
+// constraints — evaluated at the n points of H from the VALUES of constants/sigmas, wires and Z/partial products, combined
+// with powers of a check challenge drawn after the wires are committed. A proof can verify iff all of them vanish on H, so a
+// non-zero sum anywhere means the reference verifier would reject: the call returns ZKB_E_UNSAT instead of proof bytes
+// (the CPU prover does not notice either — SURVEY §8 a8 — its callers get `Err` from witness generation).
+void Circuit::run_witness_check() {
+    const int nch = (int)cd_.num_challenges;
+    const int nterms = nch * (2 + (int)cd_.num_partial_products) + (int)cd_.num_gate_constraints;
+    u64 seed_in[6] = {job_.betas[0], job_.gammas[0], job_.betas[nch - 1], job_.gammas[nch - 1], 0x5a4b4232u, 0}, chk[4];
+    h_hash_no_pad(seed_in, 6, chk);
+    fill_quotient_params(job_.pi_hash, job_.betas, job_.gammas, chk);
+    const QuotientParams* qp = reinterpret_cast<const QuotientParams*>(h_stage_ + ho_.qp);
+    launch_constraint_check(reinterpret_cast<const QuotientParams*>(qparams_dev_.get()), *qp, apow_dev_.get(), nterms,
+                            cs_vals_.get(), n_, wires_vals_.get(), n_, zs_vals_.get(), n_, q_.get(), N_,
+                            reinterpret_cast<unsigned*>(flag_dev_.get()), st_);
+}
+
 void Circuit::partial_products(const u64* wires_host, const u64* betas, const u64* gammas, u64* out_host) {
     if (!wires_host || !betas || !gammas || !out_host) throw ArgError("null argument");
+    if (busy()) throw ArgError("a proof is in flight on this context");
     DeviceGuard g(device_);
     CK(cudaMemcpyAsync(wires_vals_.get(), wires_host, cd_.num_wires * n_ * 8, cudaMemcpyHostToDevice, st_));
+    witness_loaded_ = false;
     run_partial_products(betas, gammas);
     CK(cudaMemcpyAsync(out_host, zs_vals_.get(), cd_.num_zs_pp() * n_ * 8, cudaMemcpyDeviceToHost, st_));
     sync();
@@ -380,9 +453,11 @@ void Circuit::partial_products(const u64* wires_host, const u64* betas, const u6
 void Circuit::quotient(const u64* wires_host, const u64* zs_pp_host, const u64* pis, size_t n_pi, const u64* betas,
                        const u64* gammas, const u64* alphas, u64* out_host) {
     if (!wires_host || !zs_pp_host || !betas || !gammas || !alphas || !out_host) throw ArgError("null argument");
+    if (busy()) throw ArgError("a proof is in flight on this context");
     DeviceGuard g(device_);
     const int nw = (int)cd_.num_wires, nzp = (int)cd_.num_zs_pp();
     CK(cudaMemcpyAsync(wires_vals_.get(), wires_host, (size_t)nw * n_ * 8, cudaMemcpyHostToDevice, st_));
+    witness_loaded_ = false;
     CK(cudaMemcpyAsync(zs_vals_.get(), zs_pp_host, (size_t)nzp * n_ * 8, cudaMemcpyHostToDevice, st_));
     launch_intt_natural(wires_vals_.get(), n_, wires_.coeff_ptr, n_, nw, lg_n_, nullptr, st_);
     launch_lde(wires_.coeff_ptr, n_, wires_.lde.get(), N_, nw, lg_n_, (unsigned)cd_.rate_bits, GL_GEN, st_);
@@ -403,247 +478,345 @@ struct ByteWriter {
     void words(const u64* v, size_t n) { std::memcpy(p + pos, v, n * 8); pos += n * 8; }
     void byte(uint8_t b) { p[pos++] = b; }
 };
+void os_random(void* buf, size_t len) {
+    uint8_t* p = static_cast<uint8_t*>(buf);
+    while (len) {
+        ssize_t got = getrandom(p, len, 0);
+        if (got < 0) {
+            if (errno == EINTR) continue;
+            throw CudaError("getrandom failed: cannot key the salt generator");
+        }
+        p += got;
+        len -= (size_t)got;
+    }
+}
 }  // namespace
 
-size_t Circuit::prove_resident(const u64* public_inputs, size_t n_pi, const u64* salts, u64 salt_seed, u32 pow_rule,
-                               uint8_t* out, size_t cap) {
+void Circuit::validate_prove_args(const u64* public_inputs, size_t n_pi, u32 flags, const uint8_t* out, size_t cap) const {
     if (n_pi != cd_.num_public_inputs) throw ArgError("wrong number of public inputs");
     if (n_pi && !public_inputs) throw ArgError("public_inputs is null");
-    if (pow_rule != 0) throw ArgError("unknown pow_rule");
+    if ((flags & PF_POW_MASK) != 0) throw ArgError("unknown pow_rule");
+    if (flags & ~PF_KNOWN) throw ArgError("unknown flag bits");
     const size_t psize = cd_.proof_size();
     if (!out || cap < psize) throw BufferError(psize);
     check_canonical(public_inputs, n_pi, "public_inputs");
-    DeviceGuard g(device_);
-    InFlight in_flight;
+}
 
+size_t Circuit::prove_resident(const u64* public_inputs, size_t n_pi, const u64* salts, u64 salt_seed, u32 flags,
+                               uint8_t* out, size_t cap) {
+    try {
+        begin_proof(public_inputs, n_pi, salts, salt_seed, flags, out, cap);
+        for (;;) {
+            sync();
+            if (advance()) break;
+        }
+    } catch (...) {
+        abort_proof();
+        throw;
+    }
+    return job_.len;
+}
+
+bool Circuit::ready() {
+    cudaError_t e = cudaStreamQuery(st_);
+    if (e == cudaErrorNotReady) return false;
+    CK(e);
+    return true;
+}
+void Circuit::abort_proof() {
+    if (st_) {
+        cudaSetDevice(device_);
+        cudaStreamSynchronize(st_);
+        for (auto& a : qfork_.aux) if (a) cudaStreamSynchronize(a);
+    }
+    if (job_.stage != ST_IDLE) --g_proofs_in_flight;
+    job_.stage = ST_IDLE;
+}
+
+// Stage 0 of a proof: transcript start, wires commitment queued.
+void Circuit::begin_proof(const u64* public_inputs, size_t n_pi, const u64* salts, u64 salt_seed, u32 flags, uint8_t* out,
+                          size_t cap) {
+    if (busy()) throw ArgError("a proof is in flight on this context");
+    validate_prove_args(public_inputs, n_pi, flags, out, cap);
+    if (!witness_loaded_) throw ArgError("no witness on the device: call zkb_witness_upload first (or zkb_prove)");
+    DeviceGuard g(device_);
+    Job& j = job_;
+    j = Job();
+    j.pis.assign(public_inputs, public_inputs + n_pi);
+    j.salt_seed = salt_seed; j.flags = flags; j.out = out; j.cap = cap;
+    if (cd_.salt_size()) {
+        if (salts) for (int b = 0; b < 3; ++b) j.salt_ptr[b] = salts + (size_t)b * 4 * N_;
+        else if (!(flags & PF_SALTS_FROM_SEED)) os_random(j.salt_key, sizeof(j.salt_key));
+    }
+    h_hash_no_pad(j.pis.data(), n_pi, j.pi_hash);
+    j.ch.observe_many(circuit_digest_, 4);
+    j.ch.observe_many(j.pi_hash, 4);
+
+    const int nw = wires_.ncols;
+    const unsigned cap_h = (unsigned)cd_.cap_height;
+    const size_t cap_words = size_t(4) << cap_h;
+    CK(cudaEventRecord(ev_[0], st_));
+    launch_intt_natural(wires_vals_.get(), n_, wires_.coeff_ptr, n_, nw, lg_n_, nullptr, st_);
+    CK(cudaEventRecord(ev_[T_WIRES_INTT + 1], st_));
+    launch_lde(wires_.coeff_ptr, n_, wires_.lde.get(), N_, nw, lg_n_, (unsigned)cd_.rate_bits, GL_GEN, st_);
+    CK(cudaEventRecord(ev_[T_WIRES_LDE + 1], st_));      // exactly the coset-LDE launch: bench.py's roofline kernel
+    fill_salts(wires_, 0);
+    launch_merkle_leaves(wires_.lde.get(), N_, nw + wires_.salt, N_, wires_.digests.get(), st_);
+    wires_.cap_offset = run_merkle_levels(wires_.digests.get(), N_, cap_h);
+    CK(cudaMemcpyAsync(h_stage_ + ho_.caps, wires_.digests.get() + wires_.cap_offset * 4, cap_words * 8, cudaMemcpyDeviceToHost, st_));
+    CK(cudaEventRecord(ev_[T_WIRES_MERKLE + 1], st_));
+    queue_flag_readback();
+    ++g_proofs_in_flight;
+    j.stage = ST_WIRES;
+}
+
+// one FRI commit-phase layer: LDE of the current coefficients on the shifted coset, 2^arity_bits values per leaf, tree, cap
+void Circuit::queue_fri_layer() {
+    Job& j = job_;
+    const size_t i = j.fri_i;
+    const unsigned ab = (unsigned)cd_.reduction_arity_bits[i], cap_h = (unsigned)cd_.cap_height, rate_bits = (unsigned)cd_.rate_bits;
+    const size_t M = j.m << rate_bits, cap_words = size_t(4) << cap_h;
+    u64* ca = fri_coeffs_[i].get();
+    u64* va = fri_values_[i].get();
+    launch_lde(ca, j.m, va, M, 2, j.lg_m, rate_bits, j.shift, st_);
+    const size_t leaves = M >> ab;
+    launch_merkle_leaves_ext(va, va + M, 1 << ab, leaves, fri_digests_[i].get(), st_);
+    fri_cap_off_[i] = run_merkle_levels(fri_digests_[i].get(), leaves, cap_h);
+    CK(cudaMemcpyAsync(h_stage_ + ho_.caps + (3 + i) * cap_words, fri_digests_[i].get() + fri_cap_off_[i] * 4, cap_words * 8,
+                       cudaMemcpyDeviceToHost, st_));
+}
+
+// Called with the stream idle: the stage's results are in the pinned block. Absorb them into the transcript, draw the
+// next challenges, queue the next stage. Returns true when the proof is complete.
+bool Circuit::advance() {
+    Job& j = job_;
+    if (j.stage == ST_IDLE) throw ArgError("no proof in flight");
+    DeviceGuard g(device_);
     const int ncs = cs_.ncols, nw = wires_.ncols, nzp = zs_.ncols, nq = quot_.ncols, nch = (int)cd_.num_challenges;
     const int nall = ncs + nw + nzp + nq;
-    const unsigned cap_h = (unsigned)cd_.cap_height, rate_bits = (unsigned)cd_.rate_bits;
+    const unsigned cap_h = (unsigned)cd_.cap_height;
     const size_t cap_words = size_t(4) << cap_h;
     const size_t L = cd_.reduction_arity_bits.size();
     const int nqr = (int)cd_.num_query_rounds;
-    const u64* salt_ptr[3] = {nullptr, nullptr, nullptr};
-    if (salts && cd_.salt_size())
-        for (int b = 0; b < 3; ++b) salt_ptr[b] = salts + (size_t)b * 4 * N_;
+    u64* h_caps = h_stage_ + ho_.caps;
+    u64* h_open = h_stage_ + ho_.open;
+    u64* h_final = h_stage_ + ho_.fin;
+    u64* h_pow = h_stage_ + ho_.pow;
+    check_flags();
 
-    // pinned staging layout
-    u64* h_caps = h_stage_;                         // up to (3 + L) caps
-    u64* h_open = h_caps + (3 + L) * cap_words;     // 2 * (nall + nch)
-    u64* h_misc = h_open + 2 * (size_t)(nall + nch);
-
-    u64 pi_hash[4];
-    h_hash_no_pad(public_inputs, n_pi, pi_hash);
-    Challenger ch;
-    ch.observe_many(circuit_digest_, 4);
-    ch.observe_many(pi_hash, 4);
-
-    CK(cudaEventRecord(ev_[0], st_));
-    // (d) wires commitment
-    launch_intt_natural(wires_vals_.get(), n_, wires_.coeff_ptr, n_, nw, lg_n_, nullptr, st_);
-    CK(cudaEventRecord(ev_[T_WIRES_INTT + 1], st_));
-    launch_lde(wires_.coeff_ptr, n_, wires_.lde.get(), N_, nw, lg_n_, rate_bits, GL_GEN, st_);
-    CK(cudaEventRecord(ev_[T_WIRES_LDE + 1], st_));      // exactly the coset-LDE launch: bench.py's roofline kernel
-    if (wires_.salt) {
-        u64* sp = wires_.lde.get() + (size_t)nw * N_;
-        if (salt_ptr[0]) CK(cudaMemcpyAsync(sp, salt_ptr[0], 4 * N_ * 8, cudaMemcpyHostToDevice, st_));
-        else launch_salt_fill(sp, N_, N_, salt_seed, 0, st_);
+    switch (j.stage) {
+    case ST_WIRES: {
+        j.ch.observe_many(h_caps, cap_words);
+        for (int c = 0; c < nch; ++c) j.betas[c] = j.ch.get();
+        for (int c = 0; c < nch; ++c) j.gammas[c] = j.ch.get();
+        // (f) partial products and Z, (g) commit
+        run_partial_products(j.betas, j.gammas);
+        CK(cudaEventRecord(ev_[T_PP + 1], st_));
+        if (j.flags & PF_CHECK_WITNESS) run_witness_check();
+        launch_intt_natural(zs_vals_.get(), n_, zs_vals_.get(), n_, nzp, lg_n_, nullptr, st_);
+        commit_batch(zs_, 1, h_caps + cap_words);
+        CK(cudaEventRecord(ev_[T_ZS_COMMIT + 1], st_));
+        queue_flag_readback();
+        j.stage = ST_ZS;
+        return false;
     }
-    launch_merkle_leaves(wires_.lde.get(), N_, nw + wires_.salt, N_, wires_.digests.get(), st_);
-    wires_.cap_offset = run_merkle_levels(wires_.digests.get(), N_, cap_h);
-    u64* wires_cap = h_caps;
-    CK(cudaMemcpyAsync(wires_cap, wires_.digests.get() + wires_.cap_offset * 4, cap_words * 8, cudaMemcpyDeviceToHost, st_));
-    CK(cudaEventRecord(ev_[T_WIRES_MERKLE + 1], st_));
-    sync();
-    finish_witness_check();
-    ch.observe_many(wires_cap, cap_words);
-    u64 betas[2], gammas[2], alphas[2];
-    for (int c = 0; c < nch; ++c) betas[c] = ch.get();
-    for (int c = 0; c < nch; ++c) gammas[c] = ch.get();
-
-    // (f) partial products and Z, (g) commit
-    run_partial_products(betas, gammas);
-    CK(cudaEventRecord(ev_[T_PP + 1], st_));
-    launch_intt_natural(zs_vals_.get(), n_, zs_vals_.get(), n_, nzp, lg_n_, nullptr, st_);
-    u64* zs_cap = h_caps + cap_words;
-    commit_batch(zs_, 1, salt_ptr[1], salt_seed, zs_cap);
-    CK(cudaEventRecord(ev_[T_ZS_COMMIT + 1], st_));
-    sync();
-    ch.observe_many(zs_cap, cap_words);
-    for (int c = 0; c < nch; ++c) alphas[c] = ch.get();
-
-    // (h) quotient, (i) commit
-    run_quotient(pi_hash, betas, gammas, alphas);
-    CK(cudaEventRecord(ev_[T_QUOTIENT + 1], st_));
-    u64* quot_cap = h_caps + 2 * cap_words;
-    commit_batch(quot_, 2, salt_ptr[2], salt_seed, quot_cap);
-    CK(cudaEventRecord(ev_[T_QUOTIENT_COMMIT + 1], st_));
-    sync();
-    ch.observe_many(quot_cap, cap_words);
-    ext2 zeta = ch.get_ext();
-    if (e_eq(e_pow2k(zeta, lg_n_), e_from(1))) throw ZetaError("Opening point is in the subgroup.");
-    ext2 zeta_next = e_mul_base(zeta, gl_root_of_unity(lg_n_));
-
-    // (j) openings
-    u64* od = openings_dev_.get();
-    {
+    case ST_ZS: {
+        j.ch.observe_many(h_caps + cap_words, cap_words);
+        for (int c = 0; c < nch; ++c) j.alphas[c] = j.ch.get();
+        // (h) quotient, (i) commit
+        run_quotient(j.pi_hash, j.betas, j.gammas, j.alphas);
+        CK(cudaEventRecord(ev_[T_QUOTIENT + 1], st_));
+        commit_batch(quot_, 2, h_caps + 2 * cap_words);
+        CK(cudaEventRecord(ev_[T_QUOTIENT_COMMIT + 1], st_));
+        queue_flag_readback();
+        j.stage = ST_QUOTIENT;
+        return false;
+    }
+    case ST_QUOTIENT: {
+        j.ch.observe_many(h_caps + 2 * cap_words, cap_words);
+        j.zeta = j.ch.get_ext();
+        if (e_eq(e_pow2k(j.zeta, lg_n_), e_from(1))) throw ZetaError("Opening point is in the subgroup.");
+        j.zeta_next = e_mul_base(j.zeta, gl_root_of_unity(lg_n_));
+        // (j) openings
         OpeningsArgs oa;
         oa.seg[0] = {cs_.coeff_ptr, n_, ncs, 0};
         oa.seg[1] = {wires_.coeff_ptr, n_, nw, 0};
         oa.seg[2] = {zs_.coeff_ptr, n_, nzp, 0};
         oa.seg[3] = {quot_.coeff_ptr, n_, nq, 0};
         oa.seg[4] = {zs_.coeff_ptr, n_, nch, 1};          // Z polynomials again, at g * zeta
-        oa.nseg = 5; oa.lg_n = lg_n_; oa.pw = zpow_.get(); oa.out = od;
-        launch_openings(oa, zeta, zeta_next, st_);
+        oa.nseg = 5; oa.lg_n = lg_n_; oa.pw = zpow_.get(); oa.out = openings_dev_.get();
+        launch_openings(oa, j.zeta, j.zeta_next, st_);
+        CK(cudaMemcpyAsync(h_open, openings_dev_.get(), 2 * (size_t)(nall + nch) * 8, cudaMemcpyDeviceToHost, st_));
+        CK(cudaEventRecord(ev_[T_OPENINGS + 1], st_));
+        j.stage = ST_OPENINGS;
+        return false;
     }
-    CK(cudaMemcpyAsync(h_open, od, 2 * (size_t)(nall + nch) * 8, cudaMemcpyDeviceToHost, st_));
-    CK(cudaEventRecord(ev_[T_OPENINGS + 1], st_));
-    sync();
-    // transcript order: constants, sigmas, wires, zs, partial products, quotient, then zs_next — which is the
-    // device order (cs, wires, zs_pp, quot, zs_next)
-    ch.observe_many(h_open, 2 * (size_t)(nall + nch));
-
-    // (k) prove_openings: batch combination -> final polynomial
-    ext2 alpha = ch.get_ext();
-    u64* h_apow = h_misc;                       // SoA: a[nall], b[nall]
-    ext2 reduced0 = e_make(0, 0), reduced1 = e_make(0, 0);
-    {
+    case ST_OPENINGS: {
+        // transcript order: constants, sigmas, wires, zs, partial products, quotient, then zs_next — which is the
+        // device order (cs, wires, zs_pp, quot, zs_next)
+        j.ch.observe_many(h_open, 2 * (size_t)(nall + nch));
+        // (k) prove_openings: batch combination -> final polynomial
+        const ext2 alpha = j.ch.get_ext();
+        u64* h_apow = h_stage_ + ho_.apow;                       // SoA: a[nall], b[nall]
+        ext2 reduced0 = e_make(0, 0), reduced1 = e_make(0, 0);
         ext2 p = e_from(1);
-        for (int j = 0; j < nall; ++j) {
-            h_apow[j] = p.a;
-            h_apow[nall + j] = p.b;
-            reduced0 = e_add(reduced0, e_mul(p, e_make(h_open[2 * j], h_open[2 * j + 1])));
-            if (j < nch) reduced1 = e_add(reduced1, e_mul(p, e_make(h_open[2 * (nall + j)], h_open[2 * (nall + j) + 1])));
+        for (int k = 0; k < nall; ++k) {
+            h_apow[k] = p.a;
+            h_apow[nall + k] = p.b;
+            reduced0 = e_add(reduced0, e_mul(p, e_make(h_open[2 * k], h_open[2 * k + 1])));
+            if (k < nch) reduced1 = e_add(reduced1, e_mul(p, e_make(h_open[2 * (nall + k)], h_open[2 * (nall + k) + 1])));
             p = e_mul(p, alpha);
         }
+        CK(cudaMemcpyAsync(fri_apow_.get(), h_apow, 2 * (size_t)nall * 8, cudaMemcpyHostToDevice, st_));
+        FriCombineParams fp;
+        fp.lde[0] = cs_.lde.get(); fp.lde[1] = wires_.lde.get(); fp.lde[2] = zs_.lde.get(); fp.lde[3] = quot_.lde.get();
+        for (int t = 0; t < 4; ++t) fp.stride[t] = N_;
+        fp.ncols[0] = ncs; fp.ncols[1] = nw; fp.ncols[2] = nzp; fp.ncols[3] = nq;
+        fp.num_zs = nch;
+        fp.alpha = alpha; fp.zeta = j.zeta; fp.zeta_next = j.zeta_next; fp.reduced0 = reduced0; fp.reduced1 = reduced1;
+        fp.lg_n = lg_n_;
+        u64* fc = fri_coeffs_[0].get();
+        launch_fri_combine(fp, fri_apow_.get(), fri_apow_.get() + nall, fc, fc + n_, st_);
+        launch_coset_intt_bitrev(fc, n_, 2, lg_n_, GL_GEN, st_);
+        CK(cudaEventRecord(ev_[T_FRI_COMBINE + 1], st_));
+        // FRI commit phase
+        j.shift = GL_GEN; j.m = n_; j.lg_m = lg_n_; j.fri_i = 0;
+        if (L > 0) {
+            queue_fri_layer();
+            j.stage = ST_FRI_LAYER;
+        } else {
+            CK(cudaMemcpyAsync(h_final, fri_coeffs_[0].get(), 2 * j.m * 8, cudaMemcpyDeviceToHost, st_));
+            CK(cudaEventRecord(ev_[T_FRI_COMMIT + 1], st_));
+            j.stage = ST_FINAL_POLY;
+        }
+        return false;
     }
-    CK(cudaMemcpyAsync(fri_apow_.get(), h_apow, 2 * (size_t)nall * 8, cudaMemcpyHostToDevice, st_));
-    FriCombineParams fp;
-    fp.lde[0] = cs_.lde.get(); fp.lde[1] = wires_.lde.get(); fp.lde[2] = zs_.lde.get(); fp.lde[3] = quot_.lde.get();
-    for (int t = 0; t < 4; ++t) fp.stride[t] = N_;
-    fp.ncols[0] = ncs; fp.ncols[1] = nw; fp.ncols[2] = nzp; fp.ncols[3] = nq;
-    fp.num_zs = nch;
-    fp.alpha = alpha; fp.zeta = zeta; fp.zeta_next = zeta_next; fp.reduced0 = reduced0; fp.reduced1 = reduced1;
-    fp.lg_n = lg_n_;
-    u64* fc = fri_coeffs_[0].get();
-    launch_fri_combine(fp, fri_apow_.get(), fri_apow_.get() + nall, fc, fc + n_, st_);
-    launch_coset_intt_bitrev(fc, n_, 2, lg_n_, GL_GEN, st_);
-    CK(cudaEventRecord(ev_[T_FRI_COMBINE + 1], st_));
-
-    // FRI commit phase
-    u64 shift = GL_GEN;
-    size_t m = n_;
-    unsigned lg_m = lg_n_;
-    std::vector<ext2> fri_betas;
-    for (size_t i = 0; i < L; ++i) {
+    case ST_FRI_LAYER: {
+        const size_t i = j.fri_i;
         const unsigned ab = (unsigned)cd_.reduction_arity_bits[i];
-        const int arity = 1 << ab;
-        const size_t M = m << rate_bits;
+        j.ch.observe_many(h_caps + (3 + i) * cap_words, cap_words);
+        const ext2 beta = j.ch.get_ext();
         u64* ca = fri_coeffs_[i].get();
-        u64* va = fri_values_[i].get();
-        launch_lde(ca, m, va, M, 2, lg_m, rate_bits, shift, st_);
-        const size_t leaves = M >> ab;
-        launch_merkle_leaves_ext(va, va + M, arity, leaves, fri_digests_[i].get(), st_);
-        fri_cap_off_[i] = run_merkle_levels(fri_digests_[i].get(), leaves, cap_h);
-        u64* lcap = h_caps + (3 + i) * cap_words;
-        CK(cudaMemcpyAsync(lcap, fri_digests_[i].get() + fri_cap_off_[i] * 4, cap_words * 8, cudaMemcpyDeviceToHost, st_));
-        sync();
-        ch.observe_many(lcap, cap_words);
-        ext2 beta = ch.get_ext();
-        fri_betas.push_back(beta);
         u64* na = fri_coeffs_[i + 1].get();
-        launch_fri_fold(ca, ca + m, na, na + (m >> ab), m >> ab, arity, beta, st_);
-        m >>= ab;
-        lg_m -= ab;
-        shift = gl_pow(shift, (u64)arity);
+        launch_fri_fold(ca, ca + j.m, na, na + (j.m >> ab), j.m >> ab, 1 << ab, beta, st_);
+        j.m >>= ab;
+        j.lg_m -= ab;
+        j.shift = gl_pow(j.shift, u64(1) << ab);
+        if (++j.fri_i < L) {
+            queue_fri_layer();
+        } else {
+            CK(cudaMemcpyAsync(h_final, fri_coeffs_[L].get(), 2 * j.m * 8, cudaMemcpyDeviceToHost, st_));
+            CK(cudaEventRecord(ev_[T_FRI_COMMIT + 1], st_));
+            j.stage = ST_FINAL_POLY;
+        }
+        return false;
     }
-    const size_t fin = m;   // == final_poly_len
-    u64* h_final = h_misc + 2 * (size_t)nall;
-    CK(cudaMemcpyAsync(h_final, fri_coeffs_[L].get(), 2 * fin * 8, cudaMemcpyDeviceToHost, st_));
-    CK(cudaEventRecord(ev_[T_FRI_COMMIT + 1], st_));
-    sync();
-    for (size_t k = 0; k < fin; ++k) ch.observe_ext(e_make(h_final[k], h_final[fin + k]));
-
-    // proof of work (MIN rule): smallest witness whose response has >= pow_bits leading zeros
-    u64 pow_witness = 0;
-    {
-        u64* h_pow = h_final + 2 * fin;
-        for (int i = 0; i < 12; ++i) h_pow[i] = ch.sponge[i];
-        const int pos = ch.in_len;
-        for (int i = 0; i < pos; ++i) h_pow[i] = ch.in_buf[i];
+    case ST_FINAL_POLY: {
+        const size_t fin = j.m;   // == final_poly_len
+        for (size_t k = 0; k < fin; ++k) j.ch.observe_ext(e_make(h_final[k], h_final[fin + k]));
+        // proof of work (MIN rule): smallest witness whose response has >= pow_bits leading zeros
+        for (int i = 0; i < 12; ++i) h_pow[i] = j.ch.sponge[i];
+        for (int i = 0; i < j.ch.in_len; ++i) h_pow[i] = j.ch.in_buf[i];
         h_pow[12] = ~u64(0);
         CK(cudaMemcpyAsync(pow_dev_.get(), h_pow, 13 * 8, cudaMemcpyHostToDevice, st_));
-        const u64 batch = u64(1) << 32;   // one persistent launch scans this range in increasing order and stops at the minimum
-        u64 base = 0;
-        for (;;) {
-            launch_pow_search(pow_dev_.get(), pos, base, batch, cd_.proof_of_work_bits,
+        j.pow_base = 0;
+        launch_pow_search(pow_dev_.get(), j.ch.in_len, j.pow_base, u64(1) << 32, cd_.proof_of_work_bits,
+                          reinterpret_cast<unsigned long long*>(pow_dev_.get() + 12), st_);
+        CK(cudaMemcpyAsync(h_pow + 13, pow_dev_.get() + 12, 8, cudaMemcpyDeviceToHost, st_));
+        j.stage = ST_POW;
+        return false;
+    }
+    case ST_POW: {
+        if (h_pow[13] == ~u64(0)) {      // nothing in this 2^32 range (probability ~e^-65536 at 16 bits): scan the next one
+            const u64 batch = u64(1) << 32;
+            j.pow_base += batch;
+            if (j.pow_base >= GL_P - batch) throw CudaError("proof of work search exhausted");
+            launch_pow_search(pow_dev_.get(), j.ch.in_len, j.pow_base, batch, cd_.proof_of_work_bits,
                               reinterpret_cast<unsigned long long*>(pow_dev_.get() + 12), st_);
             CK(cudaMemcpyAsync(h_pow + 13, pow_dev_.get() + 12, 8, cudaMemcpyDeviceToHost, st_));
-            sync();
-            if (h_pow[13] != ~u64(0)) { pow_witness = h_pow[13]; break; }
-            base += batch;
-            if (base >= GL_P - batch) throw CudaError("proof of work search exhausted");
+            return false;
         }
-        ch.observe(pow_witness);
-        u64 resp = ch.get();
+        j.pow_witness = h_pow[13];
+        j.ch.observe(j.pow_witness);
+        const u64 resp = j.ch.get();
         if (cd_.proof_of_work_bits && (resp >> (64 - cd_.proof_of_work_bits)) != 0) throw CudaError("proof of work self-check failed");
-    }
-    CK(cudaEventRecord(ev_[T_POW + 1], st_));
-
-    // query rounds
-    u32* h_idx = reinterpret_cast<u32*>(h_final + 2 * fin + 16);
-    for (int q = 0; q < nqr; ++q) {
-        u32 x = (u32)(ch.get() % N_);
-        h_idx[q] = x;
-        for (size_t i = 0; i < L; ++i) { x >>= cd_.reduction_arity_bits[i]; h_idx[(1 + i) * nqr + q] = x; }
-    }
-    u32* d_idx = reinterpret_cast<u32*>(query_idx_dev_.get());
-    CK(cudaMemcpyAsync(d_idx, h_idx, (1 + L) * nqr * 4, cudaMemcpyHostToDevice, st_));
-    u64* qo = query_out_dev_.get();
-    size_t qpos = 0;
-    const BatchDev* trees[4] = {&cs_, &wires_, &zs_, &quot_};
-    const int plen0 = (int)(lg_N_ - cap_h);
-    size_t row_off[4], path_off[4];
-    for (int t = 0; t < 4; ++t) {
-        const int width = trees[t]->ncols + trees[t]->salt;
-        row_off[t] = qpos;
-        launch_gather_rows(trees[t]->lde.get(), N_, width, d_idx, nqr, qo + qpos, st_);
-        qpos += (size_t)nqr * width;
-        path_off[t] = qpos;
-        launch_gather_paths(trees[t]->digests.get(), N_, plen0, d_idx, nqr, qo + qpos, st_);
-        qpos += (size_t)nqr * plen0 * 4;
-    }
-    std::vector<size_t> leaf_off(L), lpath_off(L);
-    std::vector<int> lplen(L);
-    {
+        CK(cudaEventRecord(ev_[T_POW + 1], st_));
+        // query rounds
+        u32* h_idx = reinterpret_cast<u32*>(h_stage_ + ho_.idx);
+        for (int q = 0; q < nqr; ++q) {
+            u32 x = (u32)(j.ch.get() % N_);
+            h_idx[q] = x;
+            for (size_t i = 0; i < L; ++i) { x >>= cd_.reduction_arity_bits[i]; h_idx[(1 + i) * nqr + q] = x; }
+        }
+        u32* d_idx = reinterpret_cast<u32*>(query_idx_dev_.get());
+        CK(cudaMemcpyAsync(d_idx, h_idx, (1 + L) * nqr * 4, cudaMemcpyHostToDevice, st_));
+        u64* qo = query_out_dev_.get();
+        size_t qpos = 0;
+        const BatchDev* trees[4] = {&cs_, &wires_, &zs_, &quot_};
+        const int plen0 = (int)(lg_N_ - cap_h);
+        for (int t = 0; t < 4; ++t) {
+            const int width = trees[t]->ncols + trees[t]->salt;
+            j.row_off[t] = qpos;
+            launch_gather_rows(trees[t]->lde.get(), N_, width, d_idx, nqr, qo + qpos, st_);
+            qpos += (size_t)nqr * width;
+            j.path_off[t] = qpos;
+            launch_gather_paths(trees[t]->digests.get(), N_, plen0, d_idx, nqr, qo + qpos, st_);
+            qpos += (size_t)nqr * plen0 * 4;
+        }
+        j.leaf_off.assign(L, 0); j.lpath_off.assign(L, 0); j.lplen.assign(L, 0);
         size_t mm = n_;
         unsigned bits = lg_N_;
         for (size_t i = 0; i < L; ++i) {
             const unsigned ab = (unsigned)cd_.reduction_arity_bits[i];
             const int arity = 1 << ab;
-            const size_t M = mm << rate_bits;
+            const size_t M = mm << cd_.rate_bits;
             bits -= ab;
-            lplen[i] = bits >= cap_h ? (int)(bits - cap_h) : 0;
-            leaf_off[i] = qpos;
+            j.lplen[i] = bits >= cap_h ? (int)(bits - cap_h) : 0;
+            j.leaf_off[i] = qpos;
             u64* va = fri_values_[i].get();
             launch_gather_ext_leaves(va, va + M, arity, d_idx + (1 + i) * nqr, nqr, qo + qpos, st_);
             qpos += (size_t)nqr * arity * 2;
-            lpath_off[i] = qpos;
-            launch_gather_paths(fri_digests_[i].get(), M >> ab, lplen[i], d_idx + (1 + i) * nqr, nqr, qo + qpos, st_);
-            qpos += (size_t)nqr * lplen[i] * 4;
+            j.lpath_off[i] = qpos;
+            launch_gather_paths(fri_digests_[i].get(), M >> ab, j.lplen[i], d_idx + (1 + i) * nqr, nqr, qo + qpos, st_);
+            qpos += (size_t)nqr * j.lplen[i] * 4;
             mm >>= ab;
         }
+        if (qpos != q_words_) throw CudaError("internal: query staging layout mismatch");
+        CK(cudaMemcpyAsync(h_stage_ + ho_.q, qo, qpos * 8, cudaMemcpyDeviceToHost, st_));
+        CK(cudaEventRecord(ev_[T_QUERIES + 1], st_));
+        j.stage = ST_QUERIES;
+        return false;
     }
-    u64* h_q = h_final + 2 * fin + 16 + ((1 + L) * nqr + 1) / 2 + 1;
-    if ((size_t)(h_q - h_stage_) + qpos > h_stage_words_) throw CudaError("internal: staging buffer too small");
-    CK(cudaMemcpyAsync(h_q, qo, qpos * 8, cudaMemcpyDeviceToHost, st_));
-    CK(cudaEventRecord(ev_[T_QUERIES + 1], st_));
-    sync();
+    case ST_QUERIES: {
+        serialize_proof();
+        // stage timings: every event was recorded before the wait that just ended
+        for (int s = T_WIRES_INTT; s <= T_QUERIES; ++s) CK(cudaEventElapsedTime(&timings[s], ev_[s], ev_[s + 1]));
+        CK(cudaEventElapsedTime(&timings[T_TOTAL], ev_[0], ev_[T_QUERIES + 1]));
+        timings[T_HOST_TRANSCRIPT] = (float)(j.ch.seconds * 1e3);      // wall time inside the Fiat-Shamir sponge (host, serial)
+        timings[T_HOST_PERMS] = (float)j.ch.permutations;
+        j.stage = ST_IDLE;
+        --g_proofs_in_flight;
+        return true;
+    }
+    default: throw CudaError("internal: bad proof stage");
+    }
+}
 
-    // (l) serialise: ProofWithPublicInputs::to_bytes
-    ByteWriter w{out};
-    w.words(wires_cap, cap_words);
-    w.words(zs_cap, cap_words);
-    w.words(quot_cap, cap_words);
+// (l) ProofWithPublicInputs::to_bytes from the pinned block
+void Circuit::serialize_proof() {
+    Job& j = job_;
+    const int ncs = cs_.ncols, nw = wires_.ncols, nzp = zs_.ncols, nq = quot_.ncols, nch = (int)cd_.num_challenges;
+    const int nall = ncs + nw + nzp + nq;
+    const unsigned cap_h = (unsigned)cd_.cap_height;
+    const size_t cap_words = size_t(4) << cap_h, L = cd_.reduction_arity_bits.size(), fin = j.m;
+    const int nqr = (int)cd_.num_query_rounds, plen0 = (int)(lg_N_ - cap_h);
+    const u64* h_caps = h_stage_ + ho_.caps;
+    const u64* h_open = h_stage_ + ho_.open;
+    const u64* h_final = h_stage_ + ho_.fin;
+    const u64* h_q = h_stage_ + ho_.q;
+    const BatchDev* trees[4] = {&cs_, &wires_, &zs_, &quot_};
+    ByteWriter w{j.out};
+    w.words(h_caps, 3 * cap_words);                  // wires, Z / partial products, quotient caps
     const u64* o_cs = h_open;
     const u64* o_w = h_open + 2 * ncs;
     const u64* o_z = h_open + 2 * (ncs + nw);
@@ -659,31 +832,23 @@ size_t Circuit::prove_resident(const u64* public_inputs, size_t n_pi, const u64*
     for (int q = 0; q < nqr; ++q) {
         for (int t = 0; t < 4; ++t) {
             const int width = trees[t]->ncols + trees[t]->salt;
-            w.words(h_q + row_off[t] + (size_t)q * width, width);
+            w.words(h_q + j.row_off[t] + (size_t)q * width, width);
             w.byte((uint8_t)plen0);
-            w.words(h_q + path_off[t] + (size_t)q * plen0 * 4, (size_t)plen0 * 4);
+            w.words(h_q + j.path_off[t] + (size_t)q * plen0 * 4, (size_t)plen0 * 4);
         }
         for (size_t i = 0; i < L; ++i) {
             const size_t ar2 = size_t(2) << cd_.reduction_arity_bits[i];
-            w.words(h_q + leaf_off[i] + (size_t)q * ar2, ar2);
-            w.byte((uint8_t)lplen[i]);
-            w.words(h_q + lpath_off[i] + (size_t)q * lplen[i] * 4, (size_t)lplen[i] * 4);
+            w.words(h_q + j.leaf_off[i] + (size_t)q * ar2, ar2);
+            w.byte((uint8_t)j.lplen[i]);
+            w.words(h_q + j.lpath_off[i] + (size_t)q * j.lplen[i] * 4, (size_t)j.lplen[i] * 4);
         }
     }
     for (size_t k = 0; k < fin; ++k) { w.w64(h_final[k]); w.w64(h_final[fin + k]); }
-    w.w64(pow_witness);
-    w.w64(n_pi);
-    w.words(public_inputs, n_pi);
-    if (w.pos != psize) throw CudaError("internal: proof size mismatch");
-
-    // stage timings
-    CK(cudaEventRecord(ev_[T_TOTAL + 1], st_));
-    sync();
-    for (int s = T_WIRES_INTT; s <= T_QUERIES; ++s) CK(cudaEventElapsedTime(&timings[s], ev_[s], ev_[s + 1]));
-    CK(cudaEventElapsedTime(&timings[T_TOTAL], ev_[0], ev_[T_QUERIES + 1]));
-    timings[T_HOST_TRANSCRIPT] = (float)(ch.seconds * 1e3);      // wall time inside the Fiat-Shamir sponge (host, serial)
-    timings[T_HOST_PERMS] = (float)ch.permutations;
-    return psize;
+    w.w64(j.pow_witness);
+    w.w64(j.pis.size());
+    w.words(j.pis.data(), j.pis.size());
+    if (w.pos != cd_.proof_size()) throw CudaError("internal: proof size mismatch");
+    j.len = w.pos;
 }
 
 }  // namespace zkb

@@ -10,6 +10,7 @@
 #include <vector>
 #include "common_data.hpp"
 #include "kernels.h"
+#include "host_transcript.hpp"
 
 namespace zkb {
 
@@ -17,6 +18,12 @@ struct CudaError : std::runtime_error { using std::runtime_error::runtime_error;
 struct ArgError : std::runtime_error { using std::runtime_error::runtime_error; };
 struct DigestError : std::runtime_error { using std::runtime_error::runtime_error; };
 struct ZetaError : std::runtime_error { using std::runtime_error::runtime_error; };
+struct UnsatError : std::runtime_error { using std::runtime_error::runtime_error; };
+struct NcclError : std::runtime_error { using std::runtime_error::runtime_error; };
+
+// zkb_prove `flags` (include/zkb200.h): low byte = proof-of-work rule, then option bits
+constexpr u32 PF_POW_MASK = 0xffu, PF_SALTS_FROM_SEED = 0x100u, PF_CHECK_WITNESS = 0x200u, PF_WITNESS_RESIDENT = 0x400u;
+constexpr u32 PF_KNOWN = PF_POW_MASK | PF_SALTS_FROM_SEED | PF_CHECK_WITNESS | PF_WITNESS_RESIDENT;
 struct BufferError : std::runtime_error {
     size_t required;
     BufferError(size_t r) : std::runtime_error("output buffer too small"), required(r) {}
@@ -60,13 +67,28 @@ class Circuit {
 public:
     Circuit(const uint8_t* common, size_t len, const u64* const_sigma, bool is_values, const u64* digest, int device);
     ~Circuit();
+    Circuit(const Circuit&) = delete;
+    Circuit& operator=(const Circuit&) = delete;
 
     const CommonData& common() const { return cd_; }
     void verifier_only(u64* cap_out, u64 digest_out[4]) const;
+    // throws ArgError / BufferError for anything wrong with a prove call's arguments; touches no device state
+    void validate_prove_args(const u64* public_inputs, size_t n_pi, u32 flags, const uint8_t* out, size_t cap) const;
     void upload_witness(const u64* wires_host, bool wait = true);
-    void finish_witness_check();
-    size_t prove_resident(const u64* public_inputs, size_t n_pi, const u64* salts, u64 salt_seed, u32 pow_rule,
-                          uint8_t* out, size_t cap);
+    // One proof, blocking: begin_proof + (sync, advance) until done.
+    size_t prove_resident(const u64* public_inputs, size_t n_pi, const u64* salts, u64 salt_seed, u32 flags, uint8_t* out, size_t cap);
+    // The same proof as a RESUMABLE job, for a driver that keeps several contexts in flight from one host thread
+    // (engine.hpp): begin_proof() queues the first stage on the stream and returns; whenever ready() says the stream has
+    // drained, advance() consumes the stage's results on the host (Fiat-Shamir), queues the next stage and returns true once
+    // the proof bytes are complete. An exception from either leaves the context idle and reusable (abort_proof()).
+    void begin_proof(const u64* public_inputs, size_t n_pi, const u64* salts, u64 salt_seed, u32 flags, uint8_t* out, size_t cap);
+    bool ready();
+    bool advance();
+    void abort_proof();
+    bool busy() const { return job_.stage != ST_IDLE; }
+    size_t proof_len() const { return job_.len; }
+    void wait_stream() { sync(); }
+
     void partial_products(const u64* wires_host, const u64* betas, const u64* gammas, u64* out_host);
     void quotient(const u64* wires_host, const u64* zs_pp_host, const u64* pis, size_t n_pi, const u64* betas,
                   const u64* gammas, const u64* alphas, u64* out_host);
@@ -74,9 +96,18 @@ public:
     int device() const { return device_; }
 
 private:
-    void commit_batch(BatchDev& b, unsigned batch_id, const u64* salts_host, u64 salt_seed, u64* cap_host);
+    void init(const u64* const_sigma, bool is_values, const u64* digest);
+    void cleanup();
+    void commit_batch(BatchDev& b, unsigned batch_id, u64* cap_host);
+    void fill_salts(BatchDev& b, unsigned batch_id);
     void run_partial_products(const u64* betas, const u64* gammas);
+    void fill_quotient_params(const u64* pi_hash, const u64* betas, const u64* gammas, const u64* alphas);
     void run_quotient(const u64* pi_hash, const u64* betas, const u64* gammas, const u64* alphas);
+    void run_witness_check();
+    void queue_flag_readback();
+    void check_flags();
+    void queue_fri_layer();
+    void serialize_proof();
     void sync();
 
     CommonData cd_;
@@ -90,7 +121,8 @@ private:
     // B200 boxes (35 separate buffers made zkb_circuit_create 100-500 ms and the destructor 300 ms; one arena: a few ms)
     DevBuf arena_;
     BatchDev cs_, wires_, zs_, quot_;
-    DevBuf sigma_vals_;          // [num_routed][n] values over H, natural order
+    DevBuf cs_vals_;             // [num_constants + num_routed][n] values over H, natural order (sigmas: partial products;
+                                 // all of them: the witness self-check)
     DevBuf wires_vals_;          // [num_wires][n]
     DevBuf zs_vals_;             // [num_zs_pp][n] values, then coefficients in place (aliased by zs_.coeff_ptr)
     DevBuf q_;                   // [nch][N] quotient values -> coefficients (aliased by quot_.coeff_ptr)
@@ -110,21 +142,44 @@ private:
     std::vector<DevBuf> fri_digests_;
     std::vector<size_t> fri_cap_off_;
     DevBuf pow_dev_;             // 12 state words + 1 result
-    DevBuf flag_dev_;            // witness canonical-check flag
-    // The level chain of every Merkle tree (13 short, strictly dependent launches on fixed buffers) is captured once
-    // into a CUDA graph and replayed: one host call per tree instead of 13, no launch bubbles between 7-45 us kernels.
+    DevBuf flag_dev_;            // bit 0: non-canonical input, bit 1: unsatisfied constraint (witness self-check)
+    // The level chain of every Merkle tree is captured once into a CUDA graph and replayed: one host call per tree.
     struct LevelGraph { cudaGraphExec_t exec = nullptr; size_t cap_offset = 0; unsigned long long kernels = 0; };
     std::map<const u64*, LevelGraph> level_graphs_;
     size_t run_merkle_levels(u64* digests, size_t num_leaves, unsigned cap_height);
-    bool check_pending_ = false;
+    bool witness_loaded_ = false;
     DevBuf query_idx_dev_;       // u32 indices: (1 + layers) * nq, packed in u64 words
     DevBuf query_out_dev_;
-    // pinned host staging
+    // pinned host staging: one block, regions at fixed word offsets computed (exactly) at construction
     u64* h_stage_ = nullptr;
-    size_t h_stage_words_ = 0, h_qp_off_ = 0;
+    size_t h_stage_words_ = 0;
+    struct StageOff { size_t caps, open, apow, fin, pow, flag, idx, q, qp; } ho_{};
+    size_t q_words_ = 0;
     u64 circuit_digest_[4] = {0};
     std::vector<u64> cs_cap_;
     cudaEvent_t ev_[T_COUNT + 1] = {nullptr};
+
+    // ---- the proof in flight ----
+    enum { ST_IDLE = 0, ST_WIRES, ST_ZS, ST_QUOTIENT, ST_OPENINGS, ST_FRI_LAYER, ST_FINAL_POLY, ST_POW, ST_QUERIES };
+    struct Job {
+        int stage = ST_IDLE;
+        std::vector<u64> pis;
+        const u64* salt_ptr[3] = {nullptr, nullptr, nullptr};
+        u64 salt_seed = 0;
+        u32 flags = 0;
+        u32 salt_key[8] = {0};
+        uint8_t* out = nullptr;
+        size_t cap = 0, len = 0;
+        Challenger ch;
+        u64 pi_hash[4] = {0}, betas[2] = {0}, gammas[2] = {0}, alphas[2] = {0};
+        ext2 zeta{}, zeta_next{};
+        size_t fri_i = 0, m = 0;
+        unsigned lg_m = 0;
+        u64 shift = 0, pow_base = 0, pow_witness = 0;
+        size_t row_off[4] = {0}, path_off[4] = {0};
+        std::vector<size_t> leaf_off, lpath_off;
+        std::vector<int> lplen;
+    } job_;
 };
 
 }  // namespace zkb

@@ -32,8 +32,13 @@ EXPORTS = ["zkb_version", "zkb_last_error", "zkb_device_count", "zkb_kernel_laun
            "zkb_circuit_verifier_only", "zkb_proof_size", "zkb_prove", "zkb_witness_upload", "zkb_prove_resident",
            "zkb_last_timings", "zkb_poseidon_permute_batch", "zkb_lde_batch", "zkb_merkle_commit", "zkb_commit_batch",
            "zkb_commit_cosets",
-           "zkb_partial_products", "zkb_quotient", "zkb_synth_create", "zkb_synth_create_recursion", "zkb_synth_num_constants", "zkb_synth_destroy", "zkb_synth_common_len",
-           "zkb_synth_degree", "zkb_synth_get"]
+           "zkb_partial_products", "zkb_quotient", "zkb_engine_create", "zkb_engine_destroy", "zkb_engine_proof_size",
+           "zkb_engine_acquire", "zkb_engine_release", "zkb_engine_submit", "zkb_engine_wait"]
+# `flags` of the prove calls (include/zkb200.h)
+POW_MIN, SALTS_FROM_SEED, CHECK_WITNESS, WITNESS_RESIDENT = 0, 0x100, 0x200, 0x400
+SYNTH_LIB_PATH = os.path.join(_ROOT, "libzkb200_synth.so")
+SYNTH_EXPORTS = ["zkb_synth_last_error", "zkb_synth_create", "zkb_synth_create_recursion", "zkb_synth_num_constants",
+                 "zkb_synth_destroy", "zkb_synth_common_len", "zkb_synth_degree", "zkb_synth_get"]
 
 
 class ZkbError(RuntimeError):
@@ -45,7 +50,7 @@ class ZkbError(RuntimeError):
 
 def build(force=False):
     """Compile libzkb200.so for sm_100a (nvcc cross-compiles without a GPU)."""
-    if force or not os.path.exists(LIB_PATH):
+    if force or not os.path.exists(LIB_PATH) or not os.path.exists(SYNTH_LIB_PATH):
         subprocess.check_call(["make", "-s", "-j4", "-C", _ROOT])
     return LIB_PATH
 
@@ -81,6 +86,31 @@ def lib():
                                         ctypes.c_int, u64p, f32p, ctypes.c_int]
         L.zkb_partial_products.argtypes = [ctypes.c_void_p, u64p, u64p, u64p, u64p]
         L.zkb_quotient.argtypes = [ctypes.c_void_p, u64p, u64p, u64p, ctypes.c_size_t, u64p, u64p, u64p, u64p]
+        L.zkb_engine_create.argtypes = [u8p, ctypes.c_size_t, u64p, ctypes.c_int, u64p, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                        ctypes.POINTER(ctypes.c_void_p)]
+        L.zkb_engine_destroy.argtypes = [ctypes.c_void_p]
+        L.zkb_engine_proof_size.argtypes = [ctypes.c_void_p]
+        L.zkb_engine_proof_size.restype = ctypes.c_size_t
+        L.zkb_engine_acquire.argtypes = [ctypes.c_void_p, ctypes.POINTER(u64p)]
+        L.zkb_engine_release.argtypes = [ctypes.c_void_p, ctypes.c_int]
+        L.zkb_engine_submit.argtypes = [ctypes.c_void_p, ctypes.c_int, u64p, ctypes.c_size_t, u64p, ctypes.c_uint64, ctypes.c_uint32, u8p,
+                                        ctypes.c_size_t]
+        L.zkb_engine_wait.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.POINTER(ctypes.c_size_t)]
+        _lib = L
+    return _lib
+
+
+_synth_lib = None
+
+
+def synth_lib():
+    """libzkb200_synth.so: the synthetic workload generator (test / bench tooling, include/zkb200_synth.h)."""
+    global _synth_lib
+    if _synth_lib is None:
+        if not os.path.exists(SYNTH_LIB_PATH):
+            raise ImportError(f"{SYNTH_LIB_PATH} is missing: build it with `make -C {_ROOT}`")
+        L = ctypes.CDLL(SYNTH_LIB_PATH)
+        L.zkb_synth_last_error.restype = ctypes.c_char_p
         L.zkb_synth_create_recursion.argtypes = [ctypes.c_uint, ctypes.c_int] + [ctypes.c_size_t] * 5 + [ctypes.c_uint64, ctypes.c_void_p,
                                                  ctypes.POINTER(ctypes.c_void_p)]
         L.zkb_synth_num_constants.restype = ctypes.c_size_t
@@ -92,8 +122,13 @@ def lib():
         L.zkb_synth_degree.argtypes = [ctypes.c_void_p]
         L.zkb_synth_degree.restype = ctypes.c_size_t
         L.zkb_synth_get.argtypes = [ctypes.c_void_p, u8p, u64p, u64p, u64p]
-        _lib = L
-    return _lib
+        _synth_lib = L
+    return _synth_lib
+
+
+def _check_synth(rc):
+    if rc != 0:
+        raise ZkbError(-1, synth_lib().zkb_synth_last_error().decode())
 
 
 def _check(rc):
@@ -177,6 +212,10 @@ def commit_cosets(values, rate_bits, cap_height, blk_lo, blk_hi, reps=1, device=
     return part, {"lde_ms": float(t[0]), "merkle_ms": float(t[1])}
 
 
+def _flags(salt_seed, check_witness):
+    return POW_MIN | (SALTS_FROM_SEED if salt_seed is not None else 0) | (CHECK_WITNESS if check_witness else 0)
+
+
 class ProverCircuit:
     """Device-resident circuit context (constants/sigmas commitment, twiddles, work buffers)."""
 
@@ -204,8 +243,12 @@ class ProverCircuit:
         _check(lib().zkb_circuit_verifier_only(self._h, cap.ctypes.data_as(u64p), cap.size, digest.ctypes.data_as(u64p)))
         return cap, digest
 
-    def prove(self, wires, public_inputs, salts=None, salt_seed=0, pow_rule=0):
-        """wires: (num_wires, n) array or pinned host address; returns proof bytes."""
+    def prove(self, wires, public_inputs, salts=None, salt_seed=None, check_witness=False):
+        """wires: (num_wires, n) array or pinned host address; returns proof bytes. Salts of a zk circuit: explicit `salts`,
+        else the device CSPRNG (default), else — salt_seed given — the deterministic test stream (ZKB_SALTS_FROM_SEED).
+        check_witness: ZKB_CHECK_WITNESS (an unsatisfied witness raises ZkbError ZKB_E_UNSAT)."""
+        pow_rule = _flags(salt_seed, check_witness)
+        salt_seed = salt_seed or 0
         _, wp = _ptr(wires)
         pa, pp = _u64(public_inputs)
         sa = sp = None
@@ -220,7 +263,9 @@ class ProverCircuit:
         _, wp = _ptr(wires)
         _check(lib().zkb_witness_upload(self._h, wp))
 
-    def prove_resident(self, public_inputs, salts=None, salt_seed=0, pow_rule=0, out=None):
+    def prove_resident(self, public_inputs, salts=None, salt_seed=None, check_witness=False, out=None):
+        pow_rule = _flags(salt_seed, check_witness)
+        salt_seed = salt_seed or 0
         pa, pp = _u64(public_inputs)
         sa = sp = None
         if salts is not None:
@@ -256,6 +301,69 @@ class ProverCircuit:
         return out
 
 
+class Engine:
+    """zkb_engine: n_contexts prover contexts of one circuit on one GPU behind an asynchronous submit / wait interface with
+    pinned witness slots (include/zkb200.h). `acquire()` returns (slot, wires) where wires is a writable numpy view
+    [num_wires, n] of the slot's pinned buffer."""
+
+    def __init__(self, common_bin, const_sigma, is_values=False, circuit_digest=None, device=0, contexts=8, slots=0, num_wires=135):
+        self._h = ctypes.c_void_p()
+        cb = np.frombuffer(bytes(common_bin), dtype=np.uint8).copy()
+        cs, csp = _u64(const_sigma)
+        dg = dgp = None
+        if circuit_digest is not None:
+            dg, dgp = _u64(circuit_digest)
+        _check(lib().zkb_engine_create(cb.ctypes.data_as(u8p), cb.size, csp, int(is_values), dgp, device, contexts, slots or 2 * contexts,
+                                       ctypes.byref(self._h)))
+        self.proof_size = lib().zkb_engine_proof_size(self._h)
+        self.shape = (num_wires, cs.shape[-1])
+        self._keep = {}
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib().zkb_engine_destroy(self._h)
+            self._h = None
+
+    __del__ = close
+
+    def acquire(self):
+        buf = u64p()
+        slot = lib().zkb_engine_acquire(self._h, ctypes.byref(buf))
+        if slot < 0:
+            _check(slot)
+        n_words = self.shape[0] * self.shape[1]
+        arr = np.ctypeslib.as_array(buf, shape=(n_words,)).reshape(self.shape)
+        return slot, arr
+
+    def release(self, slot):
+        _check(lib().zkb_engine_release(self._h, slot))
+
+    def submit(self, slot, public_inputs, salts=None, salt_seed=None, check_witness=False, resident=False, out=None):
+        flags = _flags(salt_seed, check_witness) | (WITNESS_RESIDENT if resident else 0)
+        pa, pp = _u64(public_inputs)
+        sa = sp = None
+        if salts is not None:
+            sa, sp = _u64(salts)
+        if out is None:
+            out = np.zeros(self.proof_size, dtype=np.uint8)
+        _check(lib().zkb_engine_submit(self._h, slot, pp, pa.size, sp, salt_seed or 0, flags, out.ctypes.data_as(u8p), out.size))
+        self._keep[slot] = (out, sa)
+
+    def wait(self, slot):
+        n = ctypes.c_size_t(0)
+        rc = lib().zkb_engine_wait(self._h, slot, ctypes.byref(n))
+        out, _ = self._keep.pop(slot, (None, None))
+        _check(rc)
+        return out[: n.value]
+
+    def prove(self, wires, public_inputs, **kw):
+        """Blocking convenience: acquire, copy the witness in, submit, wait."""
+        slot, buf = self.acquire()
+        buf[:] = wires
+        self.submit(slot, public_inputs, **kw)
+        return self.wait(slot).tobytes()
+
+
 # row mixes of the reference circuits (SURVEY.md App. C.1, §8d)
 WORMHOLE = dict(n_poseidon=488, n_base_sum=3800, n_arith=2520, n_const=100, num_public_inputs=16)
 VOTING = dict(n_poseidon=34, n_base_sum=33, n_arith=120, n_const=12, num_public_inputs=13)
@@ -278,21 +386,21 @@ class SynthCircuit:
             if set(recursion) - set(self.RECURSION_KEYS):
                 raise ValueError("bad recursion spec")
             rows = (ctypes.c_size_t * 8)(*[int(recursion.get(k, 0)) for k in self.RECURSION_KEYS])
-            _check(lib().zkb_synth_create_recursion(min_degree_bits, int(zk), n_poseidon, n_base_sum, n_arith, n_const, num_public_inputs,
+            _check_synth(synth_lib().zkb_synth_create_recursion(min_degree_bits, int(zk), n_poseidon, n_base_sum, n_arith, n_const, num_public_inputs,
                                                     seed, ctypes.cast(rows, ctypes.c_void_p), ctypes.byref(h)))
         else:
-            _check(lib().zkb_synth_create(min_degree_bits, int(zk), n_poseidon, n_base_sum, n_arith, n_const, num_public_inputs,
+            _check_synth(synth_lib().zkb_synth_create(min_degree_bits, int(zk), n_poseidon, n_base_sum, n_arith, n_const, num_public_inputs,
                                           seed, ctypes.byref(h)))
         try:
-            n = lib().zkb_synth_degree(h)
-            cb = np.zeros(lib().zkb_synth_common_len(h), dtype=np.uint8)
+            n = synth_lib().zkb_synth_degree(h)
+            cb = np.zeros(synth_lib().zkb_synth_common_len(h), dtype=np.uint8)
             self.n = n
             self.zk = bool(zk)
-            self.const_sigma_values = np.zeros((lib().zkb_synth_num_constants(h) + 80, n), dtype=np.uint64)
+            self.const_sigma_values = np.zeros((synth_lib().zkb_synth_num_constants(h) + 80, n), dtype=np.uint64)
             self.wires = np.zeros((135, n), dtype=np.uint64)
             self.public_inputs = np.zeros(num_public_inputs, dtype=np.uint64)
-            _check(lib().zkb_synth_get(h, cb.ctypes.data_as(u8p), self.const_sigma_values.ctypes.data_as(u64p),
+            _check_synth(synth_lib().zkb_synth_get(h, cb.ctypes.data_as(u8p), self.const_sigma_values.ctypes.data_as(u64p),
                                        self.wires.ctypes.data_as(u64p), self.public_inputs.ctypes.data_as(u64p)))
             self.common = cb.tobytes()
         finally:
-            lib().zkb_synth_destroy(h)
+            synth_lib().zkb_synth_destroy(h)

@@ -93,6 +93,27 @@ def synth_columns(np, lg_n, cols):
     return np.where(z >= np.uint64(0xFFFFFFFF00000001), z - np.uint64(0xFFFFFFFF00000001), z).reshape(cols, nn)
 
 
+def golden_cap(lg_n, cols):
+    """16 cap digests of the config-#3 commitment at this shape, computed once by the CPU oracle (tests/golden/make_caps.py);
+    None if the shape has no stored cap."""
+    try:
+        with open(os.path.join(ROOT, "tests", "golden", "config3_caps.json")) as f:
+            e = json.load(f).get(f"{lg_n}x{cols}")
+        return None if e is None else [[int(x, 16) for x in d] for d in e["cap"]]
+    except Exception:
+        return None
+
+
+def cap_matches(np, cap, lg_n, cols):
+    want = golden_cap(lg_n, cols)
+    if want is None:
+        return None
+    ok = bool(np.array_equal(np.asarray(cap, dtype=np.uint64), np.asarray(want, dtype=np.uint64)))
+    if not ok:
+        raise SystemExit(f"bench.py: commitment cap at 2^{lg_n} x {cols} differs from the oracle's golden cap")
+    return ok
+
+
 def reference_arm(args, rank):
     """CPU arm: the reference's own prover cannot be built here (Rust crate qp-plonky2, no toolchain), so this
     times the oracle's restatement of it (kind "port") on the host cores, same circuit, one proof per step."""
@@ -160,6 +181,9 @@ def main():
                     help="proofs in flight per GPU (independent prover contexts, one host thread each); 0 = 8. With more proofs "
                          "in flight than host cores per rank the stream waits sleep-poll instead of spinning (8 GPUs / 32 cores: "
                          "1622 proofs/s with 8 streams sleep-polling, 1419 with 4 streams spinning)")
+    ap.add_argument("--driver", default="engine", choices=["engine", "threads"],
+                    help="engine: zkb_engine (one driver thread per GPU steps all proof contexts); threads: one blocking host thread "
+                         "per proof in flight (round 1)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-sweep", action="store_true", help="skip the LDE/Merkle microbench points (config #3)")
     ap.add_argument("--no-aggregation", action="store_true", help="skip the aggregation-tree measurement (config #4)")
@@ -251,8 +275,37 @@ def main():
     t_single = time.perf_counter() - t0
     launches = (Z.kernel_launch_count() - launches0) // K
     # ---- device-resident throughput arm (`value`): B proofs in flight per GPU ----
-    for i in range(W):
-        run_parallel(lambda b: circs[b].prove_resident(pis, salt_seed=5000 + 100 * b + i, out=outs[b]))
+    # Driver: the proof ENGINE (default) — B prover contexts stepped by ONE host thread inside the library, proofs submitted
+    # asynchronously (zkb_engine_*); `--driver threads` is round 1's form, one blocking host thread per proof in flight.
+    use_engine = args.driver == "engine"
+    eng = None
+    if use_engine:
+        for c in circs[1:]:
+            c.close()
+        del circs[1:]
+        eng = Z.Engine(synth.common, synth.const_sigma_values, is_values=True, device=local_rank, contexts=B, slots=2 * B, num_wires=nw)
+        held = [eng.acquire() for _ in range(2 * B)]          # fill every pinned slot once (what a witness generator would do)
+        for slot, buf in held:
+            buf[:] = synth.wires
+        for slot, _ in held:
+            eng.release(slot)
+        eouts = [np.zeros(eng.proof_size, dtype=np.uint8) for _ in range(2 * B)]
+
+        def engine_step(seed, resident):
+            """one step = B proofs: submit all, then wait for all (the engine overlaps them on its B contexts)"""
+            slots = []
+            for b in range(B):
+                slot, _ = eng.acquire()
+                eng.submit(slot, pis, salt_seed=seed + 100 * b, resident=resident, out=eouts[slot])
+                slots.append(slot)
+            return [eng.wait(sl) for sl in slots]
+
+        engine_step(1, False)                                  # every context now holds the witness
+        for i in range(W):
+            engine_step(5000 + i, True)
+    else:
+        for i in range(W):
+            run_parallel(lambda b: circs[b].prove_resident(pis, salt_seed=5000 + 100 * b + i, out=outs[b]))
     barrier()
 
     class DeviceTimer:
@@ -277,23 +330,33 @@ def main():
     with ClockSampler(local_rank) as clk:
         with DeviceTimer() as tm_res:
             for i in range(K):
-                run_parallel(lambda b: circs[b].prove_resident(pis, salt_seed=2000 * (rank + 1) + 100 * b + i, out=outs[b]))
+                if use_engine:
+                    engine_step(2000 * (rank + 1) + i, True)
+                else:
+                    run_parallel(lambda b: circs[b].prove_resident(pis, salt_seed=2000 * (rank + 1) + 100 * b + i, out=outs[b]))
         t_res = tm_res.seconds
         barrier()
-        # ---- end-to-end arm through zkb_prove() with host buffers ----
+        # ---- end-to-end arm: host buffers in, proof bytes out, through the public C-ABI call (zkb_engine_submit / wait, or
+        # zkb_prove with --driver threads): H2D of the wire matrix from pinned host memory and D2H of the proof inside ----
         proofs = [None] * B
 
         def e2e_step(b, seed):
             proofs[b] = circs[b].prove(host_addr[b], pis, salt_seed=seed + 100 * b)
 
         for i in range(2):
-            run_parallel(lambda b: e2e_step(b, i))
+            if use_engine:
+                engine_step(i, False)
+            else:
+                run_parallel(lambda b: e2e_step(b, i))
         barrier()
         with DeviceTimer() as tm_e2e:
             for i in range(K):
-                run_parallel(lambda b: e2e_step(b, 3000 * (rank + 1) + i))
+                if use_engine:
+                    got = engine_step(3000 * (rank + 1) + i, False)
+                else:
+                    run_parallel(lambda b: e2e_step(b, 3000 * (rank + 1) + i))
         t_e2e = tm_e2e.seconds
-    proof = proofs[0]
+    proof = got[0].tobytes() if use_engine else proofs[0]
     barrier()
 
     t_res, t_e2e, t_single = zbatch.max_over_ranks([t_res, t_e2e, t_single], device="cuda")
@@ -303,22 +366,83 @@ def main():
     # exchange step: one NCCL all-gather of 16 cap digests; SURVEY.md §8e(2), config #3 shape) ----
     sharded_line = None
     if world > 1 and not args.no_sweep and (8 % world) == 0:
-        from zkb200 import sharded as zsh
-
+        # the exchange runs INSIDE libzkb200.so (zkb_comm_* / zkb_commit_sharded / zkb_quotient_chunks_sharded: NCCL over
+        # NVLink); torch.distributed only carries the 128-byte NCCL unique id from rank 0 to the other ranks
+        uid = torch.from_numpy(Z.comm_unique_id() if rank == 0 else np.zeros(128, dtype=np.uint8)).cuda()
+        dist.broadcast(uid, 0)
+        comm = Z.Comm(uid.cpu().numpy(), world, rank, device=local_rank)
         lg_n, cols = 20, 100
         vals = synth_columns(np, lg_n, cols)
         barrier()
         t0 = time.perf_counter()
-        cap, tm = zsh.sharded_commit(vals, 3, 4, device=local_rank, reps=1, gather_device="cuda")
+        cap, tm = comm.commit(vals, 3, 4, reps=2)
         torch.cuda.synchronize()
         t_wall = time.perf_counter() - t0
-        lde_ms, merkle_ms, t_wall = zbatch.max_over_ranks([tm["lde_ms"], tm["merkle_ms"], t_wall], device="cuda")
+        lde_ms, merkle_ms, gather_ms, t_wall = zbatch.max_over_ranks([tm["lde_ms"], tm["merkle_ms"], tm["gather_ms"], t_wall], device="cuda")
         nn = 1 << lg_n
         sharded_line = {"lg_n": lg_n, "cols": cols, "ranks": world, "blocks_per_rank": 8 // world, "lde_ms": lde_ms,
-                        "merkle_ms": merkle_ms, "lde_gbs_aggregate": 80 * nn * cols / (lde_ms * 1e-3) / 1e9,
+                        "merkle_ms": merkle_ms, "coeff_allgather_ms_overlapped": gather_ms,
+                        "lde_gbs_aggregate": 80 * nn * cols / (lde_ms * 1e-3) / 1e9,
                         "perms_per_sec_aggregate": (8 * nn * ((cols + 7) // 8) + 8 * nn - 16) / (merkle_ms * 1e-3),
-                        "collective": "all_gather of 16 x 32 B cap digests (NCCL)", "wall_ms_incl_h2d": 1000 * t_wall,
-                        "cap_word0": int(cap[0, 0])}
+                        "collectives": "NCCL inside libzkb200.so: all-gather of the coefficients (column-sharded iNTT, 8 n cols bytes, "
+                                       "4 chunks pipelined behind the LDE) + all-gather of 16 x 32 B cap digests",
+                        "wall_ms_3_passes_incl_h2d_of_the_rank_slice": 1000 * t_wall,
+                        "cap_word0": int(cap[0, 0]), "cap_equals_oracle_golden": cap_matches(np, cap, lg_n, cols)}
+        # quotient chunks from coset-local evaluations: one all-to-all (2 challenges, n = 2^20); input = random field elements
+        # (timing only: exactness is tests/test_gpu_new_paths.py + the gloo test of the same exchange)
+        qn = 1 << 20
+        qv = synth_columns(np, 20, 2 * (8 // world)).reshape(2, (8 // world) * qn)
+        barrier()
+        _, qt = comm.quotient_chunks(qv, qn, 3)
+        qi, qx = zbatch.max_over_ranks([qt["interpolate_ms"], qt["exchange_ms"]], device="cuda")
+        sharded_line["quotient_chunks_n2^20"] = {"coset_intt_ms": qi, "all_to_all_plus_solve_ms": qx,
+                                                 "bytes_exchanged_per_rank": int(2 * (8 // world) * qn * 8 * (world - 1) / world)}
+        comm.close()
+
+    # ---- config #4/#5: a FOREST of aggregation trees over the GPUs. 8-leaf trees (branching 2, depth 3:
+    # 4 + 2 + 1 chunk proofs each, aggregator/src/circuits/tree.rs:17-20) dealt round-robin to the ranks; inside a rank all chunk
+    # proofs of its trees form one dependency graph fed to a proof engine (zkb200.batch.aggregate_forest), so the narrow upper
+    # levels of one tree overlap the wide lower levels of the next. Chunk circuits: recursion-shaped synthetic, zero-knowledge
+    # (n = 2^14), witness generation (Rust side) not included. ----
+    forest_line = None
+    if not args.no_aggregation:
+        rs = Z.SynthCircuit(zk=True, seed=4, **Z.SynthCircuit.RECURSION)
+        S = min(4, B)
+        reng = Z.Engine(rs.common, rs.const_sigma_values, is_values=True, device=local_rank, contexts=S, slots=2 * S, num_wires=rs.wires.shape[0])
+        held = [reng.acquire() for _ in range(2 * S)]
+        for slot, buf in held:
+            buf[:] = rs.wires                                  # every pinned slot holds the chunk witness (stand-in for the generator)
+        for slot, _ in held:
+            reng.release(slot)
+
+        def prove_chunk_engine(wk, chunk, level, index, tree):
+            slot, _ = reng.acquire()
+            reng.submit(slot, rs.public_inputs, salt_seed=100000 * tree + 1000 * level + index)
+            return reng.wait(slot).tobytes()
+
+        cfg = zbatch.TreeAggregationConfig(2, 3)
+        trees_per_rank = 4
+        forest = [[b"leaf"] * 8 for _ in range(trees_per_rank * world)]
+        zbatch.aggregate_forest(forest, cfg, prove_chunk_engine, workers=2 * S)
+        barrier()
+        t0 = time.perf_counter()
+        roots, fst = zbatch.aggregate_forest(forest, cfg, prove_chunk_engine, workers=2 * S)
+        torch.cuda.synchronize()
+        t_forest = time.perf_counter() - t0
+        t0 = time.perf_counter()
+        one_root, one = zbatch.aggregate_forest(forest[:1] if rank == 0 else [], cfg, prove_chunk_engine, workers=2 * S)
+        t_one = time.perf_counter() - t0
+        t_forest, t_one = zbatch.max_over_ranks([t_forest, t_one], device="cuda")
+        forest_line = {"workload": "aggregation_forest_8_leaf_trees_recursion_zk_synth_n2^14", "trees": len(forest), "ranks": world,
+                       "trees_per_rank": trees_per_rank, "chunk_proofs_per_tree": 7, "contexts_per_gpu": S,
+                       "forest_ms": 1000 * t_forest, "trees_per_sec": len(forest) / t_forest,
+                       "chunk_proofs_per_sec": 7 * len(forest) / t_forest, "single_tree_ms_one_gpu": 1000 * t_one,
+                       "level_concurrency_rank0": fst["level_concurrency"],
+                       "single_tree_level_concurrency": one["level_concurrency"] if rank == 0 else None,
+                       "root_proof_bytes": len(next(iter(roots.values()))),
+                       "note": "level_concurrency[k] = average number of level-k chunk proofs in flight on a GPU while any was; a lone "
+                               "tree shows <= 4, 2, 1 (the reference's level barrier), the forest keeps the contexts filled"}
+        reng.close()
 
     if rank != 0:
         if dist is not None:
@@ -341,6 +465,7 @@ def main():
         "dtype": "u64 (Goldilocks field, F_p^2 extension)", "data": "synthetic",
         "config": {"workload": WORKLOAD, "degree_bits": 14, "zero_knowledge": True, "num_wires": nw, "proof_bytes": len(proof),
                    "proofs_per_step_per_gpu": B, "parallelism": f"replica x{world} (no collective), {B} proof streams per GPU",
+                   "driver": args.driver,
                    "l2": "no flush: one proof streams ~0.5 GB of LDE/leaf data, far above the 126 MB L2",
                    "timer": "CUDA events bracketing the K steps (recorded after a device synchronise on both sides, rank barrier "
                             "before; a step contains host-side Fiat-Shamir work between launches, which the events include), max "
@@ -362,7 +487,7 @@ def main():
                              "traffic = dram read + write of one launch from profiles/r01_ncu_lde_block_v3.md (output partly still in L2)",
                      "from_values_gbs": 80 * n * nw / ((stages["wires_intt"] + lde_ms) * 1e-3) / 1e9,
                      "peak_source": peak_src, "algorithmic_bytes_per_launch": lde_bytes, "avg_ms": lde_ms},
-        "poseidon": {"kernel": "wires Merkle commit (merkle_leaves_kernel + 13 level launches)", "perms_per_launch": perms,
+        "poseidon": {"kernel": "wires Merkle commit (merkle_subtree_kernel + merkle_cap_subtree_kernel: 2 launches)", "perms_per_launch": perms,
                      "avg_ms": pos_ms, "perms_per_sec": perms / (pos_ms * 1e-3), "bound": "integer pipes (fmaheavy/IMAD + alu)",
                      "imad_peak_per_s": 148 * 64 * 1.965e9,
                      "frac_of_imad_peak_algorithmic": perms / (pos_ms * 1e-3) * 6600 / (148 * 64 * 1.965e9),
@@ -370,17 +495,22 @@ def main():
                              "(profiles/r01_ncu_merkle_leaves_v1.md)"},
         "clocks": clk.summary(),
     }
+    # the DOMINANT kernel of a proof is the Poseidon tree hashing (integer-pipe bound); the contract's `roofline` object
+    # describes the HBM-side kernel the north star names (LDE-NTT) and carries the Poseidon block inside it so that both survive
+    line["roofline"]["dominant_kernel"] = "poseidon (see roofline.poseidon): ~65 % of a proof's GPU time; the LDE launch is ~5 %"
+    line["roofline"]["poseidon"] = line["poseidon"]
     if not args.no_sweep:
         # config #3 points: fused from_values commit of synthetic columns, inputs resident in HBM
         sweep = []
-        for lg_n, cols in ((14, 400), (16, 135), (18, 100), (20, 100), (22, 100)):
+        for lg_n, cols in ((14, 135), (14, 200), (14, 400), (16, 135), (16, 200), (18, 100), (20, 100), (22, 100)):
             nn = 1 << lg_n
             vals = synth_columns(np, lg_n, cols)
-            _, tm = Z.commit_batch(vals, 3, 4, reps=3, device=local_rank)
+            cap, tm = Z.commit_batch(vals, 3, 4, reps=3, device=local_rank)
             gbs = 80 * nn * cols / (tm["lde_ms"] * 1e-3) / 1e9
             pp = 8 * nn * ((cols + 7) // 8) + 8 * nn - 16
             sweep.append({"lg_n": lg_n, "cols": cols, "lde_ms": tm["lde_ms"], "lde_gbs": gbs, "lde_frac_hbm": gbs / peak,
-                          "merkle_ms": tm["merkle_ms"], "perms_per_sec": pp / (tm["merkle_ms"] * 1e-3)})
+                          "merkle_ms": tm["merkle_ms"], "perms_per_sec": pp / (tm["merkle_ms"] * 1e-3),
+                          "cap_equals_oracle_golden": cap_matches(np, cap, lg_n, cols)})
         line["lde_merkle_sweep"] = sweep
     if world == 1 and not args.no_aggregation:
         # config #4: the aggregator's default tree (branching 2, depth 3: 8 leaf proofs -> 4 + 2 + 1 chunk proofs,
@@ -419,8 +549,9 @@ def main():
                                "note": "host-buffer zkb_prove() calls (H2D of the 135 x 2^12 wire matrix inside); synthetic "
                                        "recursion-shaped circuit, recursion gate formulas unpinned against qp-plonky2 (DESIGN.md)"}
     if world == 1 and not args.no_aggregation:
-        # config #2: voting-shaped circuit (6-gate set, n = 2^8, non-zk, 13 public inputs): latency of one proof
-        vs = Z.SynthCircuit(zk=False, seed=2, **Z.VOTING)
+        # config #2: voting-shaped circuit (6-gate set, n = 2^9 as SURVEY.md §8d states it, non-zk, 13 public inputs —
+        # voting/src/lib.rs:72-76): latency of one proof
+        vs = Z.SynthCircuit(zk=False, seed=2, min_degree_bits=9, **Z.VOTING)
         vc = Z.ProverCircuit(vs.common, vs.const_sigma_values, is_values=True, device=local_rank)
         for i in range(3):
             vp = vc.prove(vs.wires, vs.public_inputs, salt_seed=i)
@@ -431,6 +562,8 @@ def main():
                           "proof_bytes": len(vp), "stage_ms": vc.timings()}
     if sharded_line is not None:
         line["sharded_commit"] = sharded_line
+    if forest_line is not None:
+        line["aggregation_forest"] = forest_line
     if world == 1 and not args.no_cpu_baseline:
         sys.path.insert(0, os.path.join(ROOT, "oracle"))
         import oracle as O   # CPU baseline leg only

@@ -26,6 +26,9 @@
 #ifdef __cplusplus
 extern "C" {
 #endif
+#if defined(__GNUC__)
+#pragma GCC visibility push(default) /* the libraries are built with -fvisibility=hidden: only this C ABI is exported */
+#endif
 
 typedef enum zkb_status {
     ZKB_OK = 0,
@@ -153,12 +156,38 @@ int zkb_commit_batch(const uint64_t* values, size_t ncols, size_t n, unsigned ra
  * 16 x 32 bytes (NCCL) to obtain MerkleTree::cap. Needs cap_height >= rate_bits and a power-of-two aligned block range. */
 int zkb_commit_cosets(const uint64_t* values, size_t ncols, size_t n, unsigned rate_bits, unsigned cap_height, unsigned blk_lo,
                       unsigned blk_hi, int reps, uint64_t* cap_part_out, float* times_ms, int device);
+/* ---- the same sharding with the exchange INSIDE the library: NCCL over NVLink (the reference is single
+ * process — its only parallelism is rayon over chunks, wormhole/aggregator/src/circuits/tree.rs:93-103). One process per GPU:
+ * rank 0 calls zkb_comm_unique_id and hands the 128 bytes to the other ranks by any means (the Rust host: its own channel;
+ * bench.py: torch.distributed); every rank then calls zkb_comm_create. Errors of the collective layer return ZKB_E_NCCL.
+ * NCCL is loaded at run time (libnccl.so.2 or $ZKB_NCCL_LIB); the library has no link-time dependency on it. */
+typedef struct zkb_comm zkb_comm;
+#define ZKB_COMM_ID_BYTES 128
+int zkb_comm_unique_id(uint8_t id_out[ZKB_COMM_ID_BYTES]);
+int zkb_comm_create(const uint8_t id[ZKB_COMM_ID_BYTES], int nranks, int rank, int device, zkb_comm** out);
+int zkb_comm_destroy(zkb_comm* c);
+/* PolynomialBatch::from_values of ONE batch across the ranks of `c` (nranks | 2^rate_bits, cap_height >= rate_bits): every rank
+ * passes the same values [ncols][n] but uploads and interpolates only ITS column slice; the coefficients are all-gathered over
+ * NVLink in column chunks behind the LDE; the rank extends and hashes its own leaf blocks and builds their subtrees; one
+ * all-gather of the cap digests. cap_out (all 2^cap_height digests) is identical on every rank and equals the single-GPU
+ * commitment's cap. times_ms (may be NULL): {lde_ms (iNTT + gather + LDE), merkle_ms, coefficient all-gather ms (overlapped)} */
+int zkb_commit_sharded(zkb_comm* c, const uint64_t* values, size_t ncols, size_t n, unsigned rate_bits, unsigned cap_height, int reps,
+                       uint64_t* cap_out, float* times_ms);
+/* Chunks of the quotient polynomial from COSET-LOCAL evaluations (compute_quotient_polys sharded by coset): q_values
+ * [num_challenges][B n] = t on this rank's B = 2^rate_bits / nranks leaf blocks (leaf order); one coset iNTT per block, ONE
+ * all-to-all of coefficient slices, an R x R Vandermonde solve per coefficient index. chunks_out [num_challenges][2^rate_bits][n / nranks]:
+ * coefficients [rank n / nranks, (rank + 1) n / nranks) of chunk m of challenge ch. times_ms: {interpolation, exchange + solve} */
+int zkb_quotient_chunks_sharded(zkb_comm* c, const uint64_t* q_values, size_t num_challenges, size_t n, unsigned rate_bits,
+                                uint64_t* chunks_out, float* times_ms);
 /* wires_permutation_partial_products_and_zs: out [num_challenges*(1+num_partial_products)][n] */
 int zkb_partial_products(zkb_circuit* c, const uint64_t* wires, const uint64_t* betas, const uint64_t* gammas, uint64_t* out);
 /* compute_quotient_polys from wire / Z-partial-product VALUES (unsalted): out [num_challenges*qdf][n] coefficients */
 int zkb_quotient(zkb_circuit* c, const uint64_t* wires, const uint64_t* zs_pp, const uint64_t* public_inputs, size_t n_pi,
                  const uint64_t* betas, const uint64_t* gammas, const uint64_t* alphas, uint64_t* out);
 
+#if defined(__GNUC__)
+#pragma GCC visibility pop
+#endif
 #ifdef __cplusplus
 }
 #endif

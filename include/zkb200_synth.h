@@ -13,6 +13,9 @@
 #ifdef __cplusplus
 extern "C" {
 #endif
+#if defined(__GNUC__)
+#pragma GCC visibility push(default) /* the libraries are built with -fvisibility=hidden: only this C ABI is exported */
+#endif
 
 /* 0 on success, -1 on a bad argument (text via zkb_synth_last_error) */
 const char* zkb_synth_last_error(void);
@@ -35,6 +38,9 @@ size_t zkb_synth_degree(const zkb_synth* s);
  * public_inputs [num_public_inputs] */
 int zkb_synth_get(const zkb_synth* s, uint8_t* common, uint64_t* const_sigma_values, uint64_t* wires, uint64_t* public_inputs);
 
+#if defined(__GNUC__)
+#pragma GCC visibility pop
+#endif
 #ifdef __cplusplus
 }
 #endif

@@ -34,10 +34,14 @@ struct OrcTrace {
 };
 
 extern "C" {
+#pragma GCC visibility push(default)   // built with -fvisibility=hidden: only these entry points are exported
 
 const char* orc_last_error() { return g_err.c_str(); }
 int orc_num_threads() { return omp_get_max_threads(); }
 void orc_set_num_threads(int n) { omp_set_num_threads(n); }
+// 1: the optimised host forms (CPU-baseline arm); 0: the readable restatement (default: what the parity tests use)
+void orc_set_fast(int on) { g_fast_poseidon = on != 0; }
+int orc_get_fast() { return g_fast_poseidon ? 1 : 0; }
 
 // ---- field / Poseidon ----
 void orc_round_constants(u64* out360) { std::memcpy(out360, poseidon_round_constants(), 360 * 8); }
@@ -326,4 +330,5 @@ int orc_quotient(const OrcCircuit* c, const u64* wires, const u64* zs_pp, const 
 
 u64 orc_salt_value(u64 seed, unsigned batch, unsigned s, u64 leaf) { return salt_value(seed, batch, s, leaf); }
 
+#pragma GCC visibility pop
 }  // extern "C"

@@ -75,6 +75,12 @@ def set_num_threads(n):
     lib().orc_set_num_threads(int(n))
 
 
+def set_fast(on):
+    """True: the optimised host forms of the hot loops (CPU-baseline arm of bench.py); False (default): the readable
+    restatement the parity tests are written against. Same results bit for bit (tests/test_oracle_kats.py)."""
+    lib().orc_set_fast(int(bool(on)))
+
+
 def round_constants():
     out = np.zeros(360, dtype=np.uint64)
     lib().orc_round_constants(out.ctypes.data_as(u64p))

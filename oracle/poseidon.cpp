@@ -1,8 +1,12 @@
 // ORACLE — TEST INFRASTRUCTURE ONLY (see poseidon.hpp header).
 #include "poseidon.hpp"
+#include "poseidon_fast.hpp"
 #include <mutex>
 
 namespace orc {
+
+bool g_fast_poseidon = false;
+void poseidon_permute_fast(u64* st) { poseidon_permute_fast_impl(st); }
 
 // ---- round-constant regeneration: ChaCha8 keystream keyed by rand_core's
 // seed_from_u64(0) PCG32 expansion; u64 draws mapped to [0,p) by the widening-multiply rule.

@@ -61,7 +61,10 @@ inline void mds_layer<BaseOps>(u64* st) {
     for (int r = 0; r < 12; ++r) st[r] = out[r];
 }
 
-inline void poseidon_permute(u64* st) {
+void poseidon_permute_fast(u64* st);      // poseidon_fast.hpp: the CPU-baseline arm's optimised form of the same function
+extern bool g_fast_poseidon;
+
+inline void poseidon_permute_naive(u64* st) {
     const u64* rc = poseidon_round_constants();
     for (int r = 0; r < N_ROUNDS; ++r) {
         for (int i = 0; i < 12; ++i) st[i] = fadd(st[i], rc[12 * r + i]);
@@ -73,6 +76,11 @@ inline void poseidon_permute(u64* st) {
         }
         mds_layer<BaseOps>(st);
     }
+}
+
+inline void poseidon_permute(u64* st) {
+    if (g_fast_poseidon) poseidon_permute_fast(st);
+    else poseidon_permute_naive(st);
 }
 
 using Digest = std::array<u64, 4>;

@@ -2,6 +2,9 @@
 #include "prover.hpp"
 #include "gates.hpp"
 #include <algorithm>
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
 
 namespace orc {
 
@@ -158,6 +161,15 @@ Proof prove(const CircuitData& cd, const std::vector<std::vector<u64>>& wires, c
     bool zk = c.zero_knowledge;
     if (wires.size() != c.num_wires) throw std::runtime_error("wrong wire column count");
     if (public_inputs.size() != c.num_public_inputs) throw std::runtime_error("wrong public input count");
+    // ORC_TIMING=1: wall-clock per stage on stderr (where the CPU baseline spends its time)
+    const bool timing = std::getenv("ORC_TIMING") != nullptr;
+    auto t_prev = std::chrono::steady_clock::now();
+    auto lap = [&](const char* what) {
+        if (!timing) return;
+        auto now = std::chrono::steady_clock::now();
+        std::fprintf(stderr, "[orc prove] %-22s %9.1f ms\n", what, std::chrono::duration<double, std::milli>(now - t_prev).count());
+        t_prev = now;
+    };
     Proof pr;
     pr.public_inputs = public_inputs;
     Digest pi_hash = hash_no_pad(public_inputs);
@@ -165,6 +177,7 @@ Proof prove(const CircuitData& cd, const std::vector<std::vector<u64>>& wires, c
 
     PolyBatch wires_b = batch_from_values(wires, rate_bits, zk, cap_h, salt_ptr(0), salt_seed, 0);
     pr.wires_cap = wires_b.tree.cap;
+    lap("wires commit");
     Challenger chal;
     chal.observe_digest(cd.vo.circuit_digest);
     chal.observe_digest(pi_hash);
@@ -174,16 +187,20 @@ Proof prove(const CircuitData& cd, const std::vector<std::vector<u64>>& wires, c
     for (size_t i = 0; i < nch; ++i) gammas.push_back(chal.get());
 
     auto zs_pp = partial_products_and_zs(cd, wires, betas, gammas);
+    lap("partial products");
     if (trace) trace->zs_pp_values = zs_pp;
     PolyBatch zs_b = batch_from_values(zs_pp, rate_bits, zk, cap_h, salt_ptr(1), salt_seed, 1);
     pr.zs_pp_cap = zs_b.tree.cap;
+    lap("zs commit");
     chal.observe_cap(pr.zs_pp_cap);
     for (size_t i = 0; i < nch; ++i) alphas.push_back(chal.get());
 
     auto chunks = compute_quotient_chunks(cd, wires_b, zs_b, pi_hash, betas, gammas, alphas);
+    lap("quotient");
     if (trace) trace->quotient_chunks = chunks;
     PolyBatch quot_b = batch_from_coeffs(chunks, rate_bits, zk, cap_h, salt_ptr(2), salt_seed, 2);
     pr.quotient_cap = quot_b.tree.cap;
+    lap("quotient commit");
     chal.observe_cap(pr.quotient_cap);
     E2 zeta = chal.get_ext();
     if (epow2k(zeta, (unsigned)c.degree_bits) == E2(1)) throw std::runtime_error("Opening point is in the subgroup.");
@@ -212,6 +229,7 @@ Proof prove(const CircuitData& cd, const std::vector<std::vector<u64>>& wires, c
         for (E2 e : *v) chal.observe_ext(e);
     for (E2 e : o.plonk_zs_next) chal.observe_ext(e);
 
+    lap("openings");
     // ---- prove_openings ----
     E2 alpha = chal.get_ext();
     std::vector<E2> final_poly(n);
@@ -246,6 +264,7 @@ Proof prove(const CircuitData& cd, const std::vector<std::vector<u64>>& wires, c
     }
     if (trace) trace->final_poly_pre_fri = final_poly;
 
+    lap("fri combine");
     // ---- FRI commit phase ----
     std::vector<E2> coeffs(final_poly);
     coeffs.resize(N);
@@ -283,6 +302,7 @@ Proof prove(const CircuitData& cd, const std::vector<std::vector<u64>>& wires, c
     pr.final_poly = coeffs;
     for (E2 e : pr.final_poly) chal.observe_ext(e);
 
+    lap("fri commit phase");
     // ---- PoW (MIN rule) ----
     {
         u64 st0[12];
@@ -314,6 +334,7 @@ Proof prove(const CircuitData& cd, const std::vector<std::vector<u64>>& wires, c
         if (lz < c.fri_config.proof_of_work_bits) throw std::runtime_error("PoW recheck failed");
     }
 
+    lap("pow");
     // ---- query rounds ----
     std::vector<size_t> qidx;
     for (u64 i = 0; i < c.fri_config.num_query_rounds; ++i) qidx.push_back((size_t)(chal.get() % N));

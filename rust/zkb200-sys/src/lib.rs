@@ -11,6 +11,11 @@ pub struct zkb_circuit {
 pub struct zkb_engine {
     _private: [u8; 0],
 }
+#[repr(C)]
+pub struct zkb_comm {
+    _private: [u8; 0],
+}
+pub const ZKB_COMM_ID_BYTES: usize = 128;
 
 // zkb_status
 pub const ZKB_OK: c_int = 0;
@@ -56,6 +61,13 @@ extern "C" {
     pub fn zkb_engine_submit(e: *mut zkb_engine, slot: c_int, public_inputs: *const u64, n_pi: usize, salts: *const u64,
                              salt_seed: u64, flags: u32, proof_out: *mut u8, proof_cap: usize) -> c_int;
     pub fn zkb_engine_wait(e: *mut zkb_engine, slot: c_int, proof_len: *mut usize) -> c_int;
+    pub fn zkb_comm_unique_id(id_out: *mut u8) -> c_int;
+    pub fn zkb_comm_create(id: *const u8, nranks: c_int, rank: c_int, device: c_int, out: *mut *mut zkb_comm) -> c_int;
+    pub fn zkb_comm_destroy(c: *mut zkb_comm) -> c_int;
+    pub fn zkb_commit_sharded(c: *mut zkb_comm, values: *const u64, ncols: usize, n: usize, rate_bits: c_uint, cap_height: c_uint,
+                              reps: c_int, cap_out: *mut u64, times_ms: *mut c_float) -> c_int;
+    pub fn zkb_quotient_chunks_sharded(c: *mut zkb_comm, q_values: *const u64, num_challenges: usize, n: usize, rate_bits: c_uint,
+                                       chunks_out: *mut u64, times_ms: *mut c_float) -> c_int;
     pub fn zkb_last_timings(c: *const zkb_circuit, ms_out: *mut c_float, cap: c_int) -> c_int;
 
     pub fn zkb_poseidon_permute_batch(states: *mut u64, count: usize, device: c_int) -> c_int;

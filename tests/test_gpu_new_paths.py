@@ -154,3 +154,40 @@ def test_engine_proofs_are_byte_identical_and_overlap(zkb, oracle):
     eng.release(slot)
     assert first == oc.prove(s.wires, s.public_inputs, salt_seed=5)
     eng.close()
+
+
+def _chunks_to_coset_values(oracle, chunks, n, rate_bits=3):
+    """LDE (leaf order) of t(X) = sum_m X^(m n) t_m(X) from its chunks: on coset j every x has x^n = c_j = (g w_N^j)^n, so
+    t = sum_m c_j^m t_m there — built from the oracle's LDE of the chunks with plain integer arithmetic."""
+    R = 1 << rate_bits
+    _, lde = oracle.lde_batch(chunks, rate_bits, from_coeffs=True)          # [R][R n], leaf order
+    g, w_N = 0xC65C18B67785D900, oracle.root_of_unity(n.bit_length() - 1 + rate_bits)
+    out = np.zeros(R * n, dtype=np.uint64)
+    for jb in range(R):
+        j = int(format(jb, f"0{rate_bits}b")[::-1], 2)
+        c = pow(g * pow(w_N, j, oracle.P) % oracle.P, n, oracle.P)
+        acc = [0] * n
+        for m in range(R):
+            cm = pow(c, m, oracle.P)
+            blk = lde[m, jb * n:(jb + 1) * n]
+            acc = [(a + cm * int(v)) % oracle.P for a, v in zip(acc, blk)]
+        out[jb * n:(jb + 1) * n] = acc
+    return out
+
+
+def test_nccl_comm_single_rank_commit_and_quotient_chunks(zkb, oracle):
+    """The NCCL-backed sharded entry points on a one-rank communicator (the collectives degenerate; the N > 1 exchange is run by
+    bench.py --gpus N and, for the host logic, by tests/test_batch_gloo.py): commit cap = the plain commitment's cap, and the
+    chunk recovery from coset-local evaluations inverts the LDE of X^(m n)-stacked chunks."""
+    comm = zkb.Comm(zkb.comm_unique_id(), 1, 0)
+    rng = np.random.default_rng(4)
+    vals = rng.integers(0, oracle.P, size=(37, 1 << 12), dtype=np.uint64)
+    cap, tm = comm.commit(vals, 3, 4, reps=2)
+    want, _ = zkb.commit_batch(vals, 3, 4)
+    assert np.array_equal(cap, want) and tm["lde_ms"] > 0
+    n = 1 << 7
+    chunks = rng.integers(0, oracle.P, size=(2, 8, n), dtype=np.uint64)
+    q = np.stack([_chunks_to_coset_values(oracle, chunks[ch], n) for ch in range(2)])
+    got, _ = comm.quotient_chunks(q, n, 3)
+    assert np.array_equal(got, chunks)
+    comm.close()

@@ -41,6 +41,12 @@ def test_voting_shaped_proof_bytes(zkb, oracle):
     run_case(zkb, oracle, oracle.Synth.VOTING, False, seed=2)
 
 
+def test_voting_shaped_proof_bytes_at_the_surveyed_degree(zkb, oracle):
+    """Config #2 as SURVEY.md §8d states it: n = 2^9, non-zk, 13 public inputs (voting/src/lib.rs:72-76)."""
+    s, oc, gc, proof = run_case(zkb, oracle, oracle.Synth.VOTING, False, seed=2, min_degree_bits=9)
+    assert s.info["degree_bits"] == 9 and s.info["num_public_inputs"] == 13
+
+
 def test_recursion_gate_set_proof_bytes(zkb, oracle):
     """Config #4/#5 gate set (the 14 gates of a recursive-verifier circuit, 4 selector groups): the CUDA
     quotient's third launch evaluates ArithmeticExtension, MulExtension, Reducing(Extension), RandomAccess, Exponentiation,
@@ -132,11 +138,14 @@ def test_batch_of_proofs_on_two_streams(zkb, oracle):
     from zkb200 import batch
 
     s = zkb.SynthCircuit(zk=True, seed=21, **zkb.TINY)
+    so = oracle.Synth(zk=True, seed=21, **oracle.Synth.TINY)
+    assert so.check() == "" and np.array_equal(s.wires, so.wires) and np.array_equal(s.public_inputs, so.public_inputs)
     provers = [zkb.ProverCircuit(s.common, s.const_sigma_values, is_values=True) for _ in range(2)]
     oc = oracle.Circuit(s.common, s.const_sigma_values)
     seeds = [7, 8, 9, 10, 11]
     proofs = batch.prove_batch(seeds, provers, lambda p, w, i: p.prove(s.wires, s.public_inputs, salt_seed=w))
     assert len(proofs) == len(seeds)
+    assert np.array_equal(s.wires, so.wires), "the witness changed under the provers"
     for seed, proof in zip(seeds, proofs):
         assert proof == oc.prove(s.wires, s.public_inputs, salt_seed=seed)
         assert oc.verify(proof) == ""

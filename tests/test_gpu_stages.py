@@ -243,3 +243,28 @@ def test_lde_max_microbench_size_properties(zkb, oracle):
     assert horner(g * pow(w, i, P) % P) == int(la[0, l])
     j = 3141592
     assert horner(pow(oracle.root_of_unity(lg_n), j, P)) == int(a[0, j])
+
+
+def _config3_columns(lg_n, cols):
+    nn = 1 << lg_n
+    idx = np.arange(nn * cols, dtype=np.uint64) + np.uint64(0xB200000000000001)
+    with np.errstate(over="ignore"):
+        z = idx
+        z = (z ^ (z >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
+        z = (z ^ (z >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
+        z = z ^ (z >> np.uint64(31))
+    return np.where(z >= np.uint64(P), z - np.uint64(P), z).reshape(cols, nn)
+
+
+@pytest.mark.parametrize("lg_n,cols", [(14, 135), (14, 400), (16, 135), (16, 200), (18, 100), (20, 100)])
+def test_commit_cap_matches_the_oracle_golden_at_microbench_sizes(zkb, lg_n, cols):
+    """Exact parity at BASELINE.json config #3's sizes: the 16 cap digests of the fused from_values commitment (iNTT + coset
+    LDE, single-block and two-step transforms, fused Merkle trees up to 2^23 leaves) equal the caps the CPU oracle computed once
+    for the same seeded columns (tests/golden/make_caps.py -> config3_caps.json)."""
+    import json
+    import os
+
+    with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "config3_caps.json")) as f:
+        want = np.array([[int(x, 16) for x in d] for d in json.load(f)[f"{lg_n}x{cols}"]["cap"]], dtype=np.uint64)
+    cap, _ = zkb.commit_batch(_config3_columns(lg_n, cols), 3, 4)
+    assert np.array_equal(cap, want)

@@ -2,6 +2,7 @@
 #include "../../include/zkb200.h"
 #include "prover.hpp"
 #include "engine.hpp"
+#include "sharded.hpp"
 #include <cstring>
 #include <new>
 
@@ -12,6 +13,9 @@ struct zkb_circuit {
 };
 struct zkb_engine {
     std::unique_ptr<Engine> impl;
+};
+struct zkb_comm {
+    std::unique_ptr<Comm> impl;
 };
 
 namespace {
@@ -247,8 +251,7 @@ int zkb_merkle_commit(const uint64_t* leaves, size_t width, size_t num_leaves, u
         size_t nd = merkle_digest_count(num_leaves, cap_height);
         DevBuf dg(nd * 4);
         cuda_check(cudaMemcpy(d.get(), leaves, width * num_leaves * 8, cudaMemcpyHostToDevice), "H2D");
-        launch_merkle_leaves(d.get(), num_leaves, (int)width, num_leaves, dg.get(), 0);
-        size_t cap_off = launch_merkle_levels(dg.get(), num_leaves, cap_height, 0);
+        size_t cap_off = launch_merkle_tree(d.get(), num_leaves, (int)width, num_leaves, dg.get(), cap_height, 0);
         cuda_check(cudaGetLastError(), "merkle launch");
         if (digests_out) cuda_check(cudaMemcpy(digests_out, dg.get(), nd * 32, cudaMemcpyDeviceToHost), "D2H digests");
         cuda_check(cudaMemcpy(cap_out, dg.get() + cap_off * 4, (size_t(32)) << cap_height, cudaMemcpyDeviceToHost), "D2H cap");
@@ -281,8 +284,7 @@ int zkb_commit_batch(const uint64_t* values, size_t ncols, size_t n, unsigned ra
             launch_intt_natural(v.get(), n, c.get(), n, (int)ncols, lg_n, nullptr, 0);
             launch_lde(c.get(), n, l.get(), N, (int)ncols, lg_n, rate_bits, GL_GEN, 0);
             cuda_check(cudaEventRecord(e1, 0), "record");
-            launch_merkle_leaves(l.get(), N, (int)ncols, N, dg.get(), 0);
-            cap_off = launch_merkle_levels(dg.get(), N, cap_height, 0);
+            cap_off = launch_merkle_tree(l.get(), N, (int)ncols, N, dg.get(), cap_height, 0);
             cuda_check(cudaEventRecord(e2, 0), "record");
             cuda_check(cudaEventSynchronize(e2), "sync");
             float a, b;
@@ -325,8 +327,7 @@ int zkb_commit_cosets(const uint64_t* values, size_t ncols, size_t n, unsigned r
             launch_intt_natural(v.get(), n, c.get(), n, (int)ncols, lg_n, nullptr, 0);      // every rank needs all coefficients
             launch_lde_blocks(c.get(), n, l.get(), L, (int)ncols, lg_n, rate_bits, GL_GEN, blk_lo, blk_hi, 0);
             cuda_check(cudaEventRecord(e1, 0), "record");
-            launch_merkle_leaves(l.get(), L, (int)ncols, L, dg.get(), 0);
-            cap_off = launch_merkle_levels(dg.get(), L, cap_local, 0);
+            cap_off = launch_merkle_tree(l.get(), L, (int)ncols, L, dg.get(), cap_local, 0);
             cuda_check(cudaEventRecord(e2, 0), "record");
             cuda_check(cudaEventSynchronize(e2), "sync");
             float a, b;
@@ -337,6 +338,46 @@ int zkb_commit_cosets(const uint64_t* values, size_t ncols, size_t n, unsigned r
         cudaEventDestroy(e0); cudaEventDestroy(e1); cudaEventDestroy(e2);
         if (times_ms) { times_ms[0] = t_lde / reps; times_ms[1] = t_merkle / reps; }
         cuda_check(cudaMemcpy(cap_part_out, dg.get() + cap_off * 4, (size_t(32)) << cap_local, cudaMemcpyDeviceToHost), "D2H cap");
+        return (int)ZKB_OK;
+    });
+}
+
+// ---- multi-GPU sharding over NCCL ----
+int zkb_comm_unique_id(uint8_t id_out[ZKB_COMM_ID_BYTES]) {
+    return guarded([&] {
+        if (!id_out) throw ArgError("id_out is null");
+        Comm::unique_id(id_out);
+        return (int)ZKB_OK;
+    });
+}
+int zkb_comm_create(const uint8_t id[ZKB_COMM_ID_BYTES], int nranks, int rank, int device, zkb_comm** out) {
+    return guarded([&] {
+        if (!out) throw ArgError("out is null");
+        *out = nullptr;
+        if (!id) throw ArgError("id is null");
+        require_device(device);
+        auto c = std::make_unique<zkb_comm>();
+        c->impl = std::make_unique<Comm>(id, nranks, rank, device);
+        *out = c.release();
+        return (int)ZKB_OK;
+    });
+}
+int zkb_comm_destroy(zkb_comm* c) {
+    return guarded([&] { delete c; return (int)ZKB_OK; });
+}
+int zkb_commit_sharded(zkb_comm* c, const uint64_t* values, size_t ncols, size_t n, unsigned rate_bits, unsigned cap_height, int reps,
+                       uint64_t* cap_out, float* times_ms) {
+    return guarded([&] {
+        if (!c) throw ArgError("comm is null");
+        c->impl->commit(values, ncols, n, rate_bits, cap_height, reps, cap_out, times_ms);
+        return (int)ZKB_OK;
+    });
+}
+int zkb_quotient_chunks_sharded(zkb_comm* c, const uint64_t* q_values, size_t num_challenges, size_t n, unsigned rate_bits,
+                                uint64_t* chunks_out, float* times_ms) {
+    return guarded([&] {
+        if (!c) throw ArgError("comm is null");
+        c->impl->quotient_chunks(q_values, num_challenges, n, rate_bits, chunks_out, times_ms);
         return (int)ZKB_OK;
     });
 }

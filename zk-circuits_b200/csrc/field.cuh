@@ -340,6 +340,35 @@ ZKB_D u64 f_mul(u64 a, u64 b) {
     return f_canon(gl_pack(o0, o1));
 }
 
+
+// x * 2^K (mod p) for a compile-time K in (0, 96), canonical in / canonical out, WITHOUT a 64x64 multiply: the radix-8 / radix-16
+// butterflies' internal twiddles are powers of two (w_16 = 2^12, w_8 = 2^24, w_4 = 2^48: SURVEY.md A.1). x << (K mod 32) is three
+// limbs (y2:y1:y0); the word offset K / 32 places them at 2^0, 2^32 or 2^64, and 2^64 = 2^32 - 1, 2^96 = -1, 2^128 = -2^32 fold
+// them back with one f_add / f_sub on values that are canonical by construction:
+//   K < 32 : canon(y1:y0) + y2 (2^32 - 1)                10-17 instructions instead of the ~30 issue slots of f_mul
+//   K < 64 : (y0:0) + y1 (2^32 - 1) - y2
+//   K < 96 : y0 (2^32 - 1) - (y2:y1)
+// (multiplication by 2^(96 + K) is the same applied to -x: the caller swaps the operands of the butterfly's subtraction)
+template <int K>
+ZKB_D u64 f_shl(u64 x) {
+    static_assert(K > 0 && K < 96, "shift out of range");
+    constexpr int r = K & 31, w = K >> 5;
+    u32 x0, x1;
+    gl_unpack(x, x0, x1);
+    const u32 y0 = x0 << r, y1 = r ? __funnelshift_l(x0, x1, r) : x1, y2 = r ? (x1 >> (32 - r)) : 0u;
+    auto times_eps = [](u32 v) { return gl_pack(0u - v, v - (v != 0u)); };      // v (2^32 - 1) = (v << 32) - v  < p
+    if (w == 0) return f_add(f_canon(gl_pack(y0, y1)), times_eps(y2));
+    if (w == 1) return f_sub(f_add(gl_pack(0u, y0), times_eps(y1)), (u64)y2);
+    return f_sub(times_eps(y0), gl_pack(y1, y2));                                // (y2:y1) < 2^63: canonical
+}
+// d * w_16^(+-IDX): the butterfly's twiddle for d = a - b, with the sign of the inverse twiddle (w_16^-i = -2^(96 - 12 i)) taken
+// by the subtraction itself
+template <int IDX, bool INV>
+ZKB_D u64 f_sub_twiddle16(u64 a, u64 b) {
+    static_assert(IDX > 0 && IDX < 8, "w_16 exponent");
+    if (!INV) return f_shl<12 * IDX>(f_sub(a, b));
+    return f_shl<96 - 12 * IDX>(f_sub(b, a));
+}
 #endif
 
 // ---- quadratic extension, canonical components ----

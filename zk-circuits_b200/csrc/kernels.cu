@@ -340,20 +340,89 @@ __global__ void __launch_bounds__(128) merkle_leaves_wide_kernel(const u64* __re
 }
 
 constexpr size_t MERKLE_WIDE_MAX_NODES = 4096;   // levels this small are latency-bound with one node per thread
-size_t launch_merkle_levels(u64* digests, size_t num_leaves, unsigned cap_height, cudaStream_t st) {
-    unsigned lg = 0;
-    while ((size_t(1) << lg) < num_leaves) ++lg;
-    size_t off = 0;
-    for (unsigned k = 0; k + cap_height < lg; ++k) {
-        size_t n_in = num_leaves >> k, n_out = n_in >> 1;
-        ZKB_COUNT_LAUNCH();
-        if (n_out <= MERKLE_WIDE_MAX_NODES)
-            merkle_level_wide_kernel<<<(unsigned)((n_out + 7) / 8), 128, 0, st>>>(digests + off * 4, digests + (off + n_in) * 4, n_out);
-        else
-            merkle_level_kernel<<<(unsigned)((n_out + 127) / 128), 128, 0, st>>>(digests + off * 4, digests + (off + n_in) * 4, n_out);
-        off += n_in;
+
+// ---- tree levels --------------------------------------------------------------------------------------------------------
+// A tree used to be one leaf kernel + one launch per level (13 for the wormhole trees). The levels with many nodes are real
+// work (a level of 65 536 nodes is 2.6 % of the wires tree's permutations), but from ~8 k nodes down every level costs one
+// permutation's dependency chain whatever its size, and the GPU idles between the launches. Now: one node per thread while a
+// level has more than 4096 parents, then ONE launch for everything above —
+//   merkle_cap_subtree_kernel  one CTA per cap digest finishes that digest's subtree (<= 256 entry nodes) with the lane-parallel
+//                              permutation (12 lanes per node, MDS through warp shuffles): a level costs ~1/4 of the
+//                              one-node-per-thread latency and no launch; 7 launches per wormhole tree instead of 14.
+// Measured and rejected (round 2, profiles/r02_merkle_fusion.md): building the bottom 7 levels inside the leaf kernel (a CTA
+// hashes 128 leaves, then its subtree through shared memory, one permutation call site) — 2 launches per tree, bit-exact, but
+// every CTA reaches its narrow levels at the same time and holds its registers through seven mostly idle permutation
+// latencies: wires tree 2.52 -> 2.78 ms, 8-stream throughput 213 -> 187 proofs/s.
+// levels above `in` (nodes_total digests) down to nodes_total >> levels digests; CTA b owns output digest b of the last level
+__global__ void __launch_bounds__(1024) merkle_cap_subtree_kernel(u64* __restrict__ base, size_t nodes_total, int levels) {
+    __shared__ u32 s_rc[3 * P_WIDTH * P_ROUNDS];
+    wide_load_rc(s_rc);
+    const unsigned lane = threadIdx.x & 31, j = lane & 15, jj = j < 12 ? j : 11;
+    const unsigned nwarps = blockDim.x >> 5, warp = threadIdx.x >> 5;
+    u64* in = base;
+    for (int lv = 0; lv < levels; ++lv) {
+        const size_t n_in = nodes_total >> lv;
+        u64* out = in + n_in * 4;
+        const unsigned m_out = (1u << levels) >> (lv + 1);                // parents of this subtree at this level
+        const u64* in_sub = in + (size_t)blockIdx.x * 2 * m_out * 4;
+        u64* out_sub = out + (size_t)blockIdx.x * m_out * 4;
+        for (unsigned b0 = 0; b0 < m_out; b0 += 2 * nwarps) {             // warp-uniform trip count (shuffles inside)
+            const unsigned node = b0 + 2 * warp + (lane >> 4);
+            const bool live = node < m_out;
+            u32 x0, x1, x2;
+            limb_split((live && j < 8) ? in_sub[(size_t)node * 8 + j] : 0, x0, x1, x2);
+            wide_permute(x0, x1, x2, s_rc, jj);
+            if (live && j < 4) out_sub[(size_t)node * 4 + j] = gl_canon(limb_to_u64(x0, x1, x2));
+        }
+        __syncthreads();                                                  // this CTA's next level reads what it just wrote
+        in = out;
     }
-    return off;
+}
+
+static unsigned lg2_size(size_t x) { unsigned k = 0; while ((size_t(1) << k) < x) ++k; return k; }
+constexpr unsigned MERKLE_CAP_SUBTREE_MAX_ENTRY = 256;
+
+// levels above level `done` (whose digests are in place) of a tree whose leaf level has num_leaves digests; returns the cap offset
+static size_t merkle_finish_levels(u64* digests, size_t num_leaves, unsigned cap_height, unsigned done, cudaStream_t st) {
+    const unsigned lg = lg2_size(num_leaves);
+    const unsigned T = lg >= cap_height ? lg - cap_height : 0;
+    unsigned level = done;
+    while (level < T) {
+        const size_t nodes = num_leaves >> level, off = merkle_level_offset(num_leaves, level);
+        const unsigned remaining = T - level;
+        if (remaining <= lg2_size(MERKLE_CAP_SUBTREE_MAX_ENTRY) && nodes <= 2 * MERKLE_WIDE_MAX_NODES) {
+            const unsigned parents = (1u << remaining) >> 1;                // per cap digest
+            unsigned threads = parents * 16;
+            threads = threads < 32 ? 32 : (threads > 1024 ? 1024 : threads);
+            ZKB_COUNT_LAUNCH();
+            merkle_cap_subtree_kernel<<<(unsigned)(nodes >> remaining), threads, 0, st>>>(digests + off * 4, nodes, (int)remaining);
+            level = T;
+        } else {                                                            // one level per launch
+            const size_t n_out = nodes >> 1;
+            ZKB_COUNT_LAUNCH();
+            if (n_out <= MERKLE_WIDE_MAX_NODES)
+                merkle_level_wide_kernel<<<(unsigned)((n_out + 7) / 8), 128, 0, st>>>(digests + off * 4, digests + (off + nodes) * 4, n_out);
+            else
+                merkle_level_kernel<<<(unsigned)((n_out + 127) / 128), 128, 0, st>>>(digests + off * 4, digests + (off + nodes) * 4, n_out);
+            level += 1;
+        }
+    }
+    return merkle_level_offset(num_leaves, T);
+}
+size_t launch_merkle_levels(u64* digests, size_t num_leaves, unsigned cap_height, cudaStream_t st) {
+    return merkle_finish_levels(digests, num_leaves, cap_height, 0, st);
+}
+size_t launch_merkle_tree(const u64* leaves, size_t col_stride, int width, size_t num_leaves, u64* digests, unsigned cap_height,
+                          cudaStream_t st) {
+    if (!num_leaves) return 0;
+    launch_merkle_leaves(leaves, col_stride, width, num_leaves, digests, st);
+    return merkle_finish_levels(digests, num_leaves, cap_height, 0, st);
+}
+size_t launch_merkle_tree_ext(const u64* a_, const u64* b_, int arity, size_t num_leaves, u64* digests, unsigned cap_height,
+                              cudaStream_t st) {
+    if (!num_leaves) return 0;
+    launch_merkle_leaves_ext(a_, b_, arity, num_leaves, digests, st);
+    return merkle_finish_levels(digests, num_leaves, cap_height, 0, st);
 }
 
 // every element must be a canonical field element (< p): *flag |= 1 otherwise (the reference's types guarantee this; a
@@ -575,6 +644,24 @@ void launch_lde_blocks(const u64* coeffs, size_t coeff_stride, u64* out, size_t 
 void launch_lde(const u64* coeffs, size_t coeff_stride, u64* out, size_t out_stride, int ncols, unsigned lg_n,
                 unsigned rate_bits, u64 shift, cudaStream_t st) {
     launch_lde_blocks(coeffs, coeff_stride, out, out_stride, ncols, lg_n, rate_bits, shift, 0, 1u << rate_bits, st);
+}
+
+// out[m][k] = sum_j mat[m][j] in[j][k]: recovers the R chunk polynomials from the R per-coset interpolants (sharded.hpp)
+__global__ void vandermonde_solve_kernel(const u64* __restrict__ in, u64* __restrict__ out, size_t len, unsigned R, const u64* __restrict__ mat) {
+    const size_t k = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if (k >= len) return;
+    u64 v[16];
+    for (unsigned j = 0; j < R; ++j) v[j] = in[(size_t)j * len + k];
+    for (unsigned m = 0; m < R; ++m) {
+        u64 acc = 0;
+        for (unsigned j = 0; j < R; ++j) acc = f_add(acc, f_mul(v[j], mat[m * R + j]));
+        out[(size_t)m * len + k] = acc;
+    }
+}
+void launch_vandermonde_solve(const u64* in, u64* out, size_t len, unsigned R, const u64* mat_dev, cudaStream_t st) {
+    if (!len) return;
+    ZKB_COUNT_LAUNCH();
+    vandermonde_solve_kernel<<<(unsigned)((len + 127) / 128), 128, 0, st>>>(in, out, len, R, mat_dev);
 }
 
 // data[k] *= c0 * base^k

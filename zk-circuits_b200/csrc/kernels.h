@@ -27,6 +27,11 @@ void launch_merkle_leaves_ext(const u64* a, const u64* b, int arity, size_t num_
 // builds all levels above level 0 in `digests` (levels concatenated: num_leaves, num_leaves/2, ...) down to
 // 2^cap_height nodes; returns the offset (in digests) of the cap level
 size_t launch_merkle_levels(u64* digests, size_t num_leaves, unsigned cap_height, cudaStream_t st);
+// whole trees (leaf digests + every level, 2 launches for the prover's trees): return the digest offset of the cap level
+size_t launch_merkle_tree(const u64* leaves, size_t col_stride, int width, size_t num_leaves, u64* digests, unsigned cap_height,
+                          cudaStream_t st);
+size_t launch_merkle_tree_ext(const u64* a, const u64* b, int arity, size_t num_leaves, u64* digests, unsigned cap_height,
+                              cudaStream_t st);
 size_t merkle_digest_count(size_t num_leaves, unsigned cap_height);   // total digests over all levels
 size_t merkle_level_offset(size_t num_leaves, unsigned level);        // digest offset of level k
 
@@ -43,6 +48,9 @@ void launch_lde_blocks(const u64* coeffs, size_t coeff_stride, u64* out, size_t 
                        unsigned rate_bits, u64 shift, unsigned blk_lo, unsigned blk_hi, cudaStream_t st);
 // evaluations on shift*<w_m> given in bit-reversed order -> coefficients in natural order (in place)
 void launch_coset_intt_bitrev(u64* data, size_t stride, int ncols, unsigned lg_m, u64 shift, cudaStream_t st);
+
+// out[m * len + k] = sum_j mat[m * R + j] * in[j * len + k], R <= 16 (chunk recovery of the coset-sharded quotient)
+void launch_vandermonde_solve(const u64* in, u64* out, size_t len, unsigned R, const u64* mat_dev, cudaStream_t st);
 
 // in-place bit-reversal permutation of each column (leaf order <-> natural order)
 void launch_bitrev_permute(u64* data, size_t stride, int ncols, unsigned lg_n, cudaStream_t st);

@@ -22,23 +22,25 @@ __constant__ u64 c_w16[16];                              // w_16^k, k < 8, then 
 ZKB_D unsigned ntt_pad(unsigned i) { return i + (i >> 4); }          // one spare word per 16: keeps small-stride passes off one bank
 inline size_t ntt_smem_bytes(unsigned lg) { return sizeof(u64) * ((size_t(1) << lg) + (size_t(1) << lg) / 16 + 1); }
 
-// in-register DIF of 2^K elements (K <= 4); r[p] ends up holding output index bitrev_K(p). w16 = c_w16 (+8 for inverse)
-template <int K>
-ZKB_D void radix_dif(u64* r, const u64* w16) {
-#pragma unroll
-    for (int t = 0; t < K; ++t) {
-        const int half = 1 << (K - 1 - t);
-#pragma unroll
-        for (int g = 0; g < (1 << K); g += 2 * half) {
-#pragma unroll
-            for (int j = 0; j < half; ++j) {
-                u64 a = r[g + j], b = r[g + j + half];
-                r[g + j] = f_add(a, b);
-                u64 d = f_sub(a, b);
-                r[g + j + half] = j ? f_mul(d, w16[j * (8 / half)]) : d;
-            }
-        }
+// in-register DIF of 2^K elements (K <= 4); r[p] ends up holding output index bitrev_K(p). The internal twiddles w_16^i are
+// powers of two: shift forms (field.cuh f_shl), no 64x64 multiply. INV: inverse twiddles.
+template <int K, bool INV, int T, int G, int J>
+struct RadixStep {      // butterfly (g + j, g + j + half) of stage T, half = 2^(K-1-T); recursion over j, g, t at compile time
+    static ZKB_D void run(u64* r) {
+        constexpr int half = 1 << (K - 1 - T);
+        const u64 a = r[G + J], b = r[G + J + half];
+        r[G + J] = f_add(a, b);
+        if constexpr (J == 0) r[G + J + half] = f_sub(a, b);
+        else r[G + J + half] = f_sub_twiddle16<J * (8 / half), INV>(a, b);
+        if constexpr (J + 1 < half) RadixStep<K, INV, T, G, J + 1>::run(r);
+        else if constexpr (G + 2 * half < (1 << K)) RadixStep<K, INV, T, G + 2 * half, 0>::run(r);
+        else if constexpr (T + 1 < K) RadixStep<K, INV, T + 1, 0, 0>::run(r);
     }
+};
+template <int K>
+ZKB_D void radix_dif(u64* r, bool inv) {
+    if (inv) RadixStep<K, true, 0, 0, 0>::run(r);
+    else RadixStep<K, false, 0, 0, 0>::run(r);
 }
 
 // One radix-2^K pass over sm[0 .. 2^L). The array is 2^lgC interleaved transforms (element index = row * 2^lgC + c;
@@ -48,7 +50,6 @@ template <int K>
 ZKB_D void ntt_dif_pass(u64* sm, unsigned L, unsigned s, unsigned lgC, bool inv) {
     constexpr int R = 1 << K;
     const unsigned lgM = s - K, M = 1u << lgM, ntiles = 1u << (L - K);
-    const u64* w16 = c_w16 + (inv ? 8 : 0);
     const unsigned tmask = (1u << NTT_SM_LG) - 1;
     for (unsigned t = threadIdx.x; t < ntiles; t += blockDim.x) {
         const unsigned b = t & (M - 1), base = ((t >> lgM) << s) + b;
@@ -66,7 +67,7 @@ ZKB_D void ntt_dif_pass(u64* sm, unsigned L, unsigned s, unsigned lgC, bool inv)
         u64 r[R];
 #pragma unroll
         for (int e = 0; e < R; ++e) r[e] = sm[ntt_pad(base + ((unsigned)e << lgM))];
-        radix_dif<K>(r, w16);
+        radix_dif<K>(r, inv);
         if (lgM > lgC) {
 #pragma unroll
             for (int p = 1; p < R; ++p) r[p] = f_mul(r[p], tw[p]);
@@ -164,7 +165,11 @@ __global__ void __launch_bounds__(256) ntt_cols_kernel(ColsNttArgs a) {
         const unsigned q1 = bitrev32(r, a.lg_n1), b = b0 + c;
         u32 E = (u32)(((u64)b * q1) << (32 - a.lg_n));       // b q1 < n
         if (a.inv) E = 0u - E;
-        dst[(size_t)r * n2 + b] = f_mul(sm[ntt_pad(idx)], root_pow(E));
+        // T^E from the split tables; for n <= 2^21 the low 11 bits of E are zero, so two factors (and two multiplies) suffice
+        u64 v = f_mul(sm[ntt_pad(idx)], d_rootB[(E >> 11) & 2047]);
+        v = f_mul(v, d_rootC[E >> 22]);
+        if (a.lg_n > 21) v = f_mul(v, d_rootA[E & 2047]);
+        dst[(size_t)r * n2 + b] = v;
     }
 }
 

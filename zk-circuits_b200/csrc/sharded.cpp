@@ -1,0 +1,217 @@
+#include "sharded.hpp"
+#include <dlfcn.h>
+#include <nccl.h>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+#include <vector>
+
+namespace zkb {
+
+namespace {
+// the NCCL entry points used here, resolved at run time
+struct NcclApi {
+    ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+    ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*Send)(const void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*Recv)(void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*GroupStart)() = nullptr;
+    ncclResult_t (*GroupEnd)() = nullptr;
+    const char* (*GetErrorString)(ncclResult_t) = nullptr;
+};
+const NcclApi& nccl() {
+    static NcclApi api;
+    static std::once_flag once;
+    static std::string err;
+    std::call_once(once, [] {
+        const char* names[] = {std::getenv("ZKB_NCCL_LIB"), "libnccl.so.2", "libnccl.so"};
+        void* h = nullptr;
+        for (const char* nm : names)
+            if (nm && (h = dlopen(nm, RTLD_NOW | RTLD_LOCAL))) break;
+        if (!h) { err = std::string("cannot load NCCL (libnccl.so.2): ") + dlerror(); return; }
+        auto sym = [&](const char* s) { void* p = dlsym(h, s); if (!p && err.empty()) err = std::string("NCCL symbol missing: ") + s; return p; };
+        api.GetUniqueId = reinterpret_cast<decltype(api.GetUniqueId)>(sym("ncclGetUniqueId"));
+        api.CommInitRank = reinterpret_cast<decltype(api.CommInitRank)>(sym("ncclCommInitRank"));
+        api.CommDestroy = reinterpret_cast<decltype(api.CommDestroy)>(sym("ncclCommDestroy"));
+        api.AllGather = reinterpret_cast<decltype(api.AllGather)>(sym("ncclAllGather"));
+        api.Send = reinterpret_cast<decltype(api.Send)>(sym("ncclSend"));
+        api.Recv = reinterpret_cast<decltype(api.Recv)>(sym("ncclRecv"));
+        api.GroupStart = reinterpret_cast<decltype(api.GroupStart)>(sym("ncclGroupStart"));
+        api.GroupEnd = reinterpret_cast<decltype(api.GroupEnd)>(sym("ncclGroupEnd"));
+        api.GetErrorString = reinterpret_cast<decltype(api.GetErrorString)>(sym("ncclGetErrorString"));
+    });
+    if (!err.empty()) throw NcclError(err);
+    return api;
+}
+void nccl_check(ncclResult_t r, const char* what) {
+    if (r != ncclSuccess) throw NcclError(std::string(what) + ": " + nccl().GetErrorString(r));
+}
+#define NK(x) nccl_check((x), #x)
+#define CK(x) cuda_check((x), #x)
+unsigned lg2u(size_t x) { unsigned k = 0; while ((size_t(1) << k) < x) ++k; return k; }
+struct Events {
+    std::vector<cudaEvent_t> ev;
+    explicit Events(size_t n, bool timing = true) : ev(n, nullptr) {
+        for (auto& e : ev) CK(cudaEventCreateWithFlags(&e, timing ? cudaEventDefault : cudaEventDisableTiming));
+    }
+    ~Events() { for (auto e : ev) if (e) cudaEventDestroy(e); }
+    cudaEvent_t operator[](size_t i) const { return ev[i]; }
+};
+}  // namespace
+
+static_assert(sizeof(ncclUniqueId) == COMM_ID_BYTES, "ncclUniqueId size");
+
+void Comm::unique_id(uint8_t out[COMM_ID_BYTES]) {
+    ncclUniqueId id;
+    NK(nccl().GetUniqueId(&id));
+    std::memcpy(out, &id, COMM_ID_BYTES);
+}
+
+Comm::Comm(const uint8_t id_bytes[COMM_ID_BYTES], int nranks, int rank, int device) : nranks_(nranks), rank_(rank), device_(device) {
+    if (nranks < 1 || rank < 0 || rank >= nranks) throw ArgError("bad rank / nranks");
+    if (nranks & (nranks - 1)) throw ArgError("the number of ranks must be a power of two");
+    CK(cudaSetDevice(device));
+    device_tables_init(device);
+    ncclUniqueId id;
+    std::memcpy(&id, id_bytes, COMM_ID_BYTES);
+    ncclComm_t c = nullptr;
+    NK(nccl().CommInitRank(&c, nranks, id, rank));
+    comm_ = c;
+    try {
+        CK(cudaStreamCreateWithFlags(&st_, cudaStreamNonBlocking));
+        CK(cudaStreamCreateWithFlags(&comm_st_, cudaStreamNonBlocking));
+    } catch (...) {
+        if (st_) cudaStreamDestroy(st_);
+        nccl().CommDestroy(c);
+        throw;
+    }
+}
+Comm::~Comm() {
+    cudaSetDevice(device_);
+    if (st_) { cudaStreamSynchronize(st_); cudaStreamDestroy(st_); }
+    if (comm_st_) { cudaStreamSynchronize(comm_st_); cudaStreamDestroy(comm_st_); }
+    if (comm_) nccl().CommDestroy(static_cast<ncclComm_t>(comm_));
+}
+
+void Comm::commit(const u64* values, size_t ncols, size_t n, unsigned rate_bits, unsigned cap_height, int reps, u64* cap_out,
+                  float* times_ms) {
+    if (!values || !cap_out) throw ArgError("null argument");
+    if (n < 2 || (n & (n - 1)) || rate_bits > 4 || !ncols) throw ArgError("bad shape");
+    const unsigned G = (unsigned)nranks_, R = 1u << rate_bits;
+    if (G > R) throw ArgError("more ranks than coset blocks");
+    if (cap_height < rate_bits) throw ArgError("coset sharding needs cap_height >= rate_bits (each block must hold whole cap subtrees)");
+    if (reps < 1) reps = 1;
+    CK(cudaSetDevice(device_));
+    ncclComm_t comm = static_cast<ncclComm_t>(comm_);
+    const unsigned lg_n = lg2u(n), B = R / G, blk_lo = (unsigned)rank_ * B;
+    const size_t N = n << rate_bits, L = n * B;
+    if ((size_t(1) << cap_height) > N) throw ArgError("cap_height exceeds tree height");
+    const unsigned cap_local = cap_height - rate_bits + lg2u(B);
+    // columns in chunks of G * w: rank r interpolates columns [k G w + r w, + w) of chunk k (zero padding past ncols)
+    const size_t per_rank = (ncols + G - 1) / G;
+    const size_t nchunks = per_rank >= 8 ? 4 : 1, w = (per_rank + nchunks - 1) / nchunks, padded = nchunks * G * w;
+    DevBuf coeffs(padded * n), lde(ncols * L), dg(merkle_digest_count(L, cap_local) * 4), cap_all((size_t(4) << cap_height));
+    DevBuf vals(nchunks * w * n);
+    CK(cudaMemsetAsync(vals.get(), 0, nchunks * w * n * 8, st_));
+    for (size_t k = 0; k < nchunks; ++k) {      // H2D of this rank's column slices only: 1 / G of the matrix
+        const size_t c0 = k * G * w + (size_t)rank_ * w;
+        if (c0 >= ncols) continue;
+        const size_t cnt = std::min(w, ncols - c0);
+        CK(cudaMemcpyAsync(vals.get() + k * w * n, values + c0 * n, cnt * n * 8, cudaMemcpyHostToDevice, st_));
+    }
+    Events tm(5), chain(2 * nchunks, false);
+    float t_lde = 0, t_merkle = 0, t_gather = 0;
+    size_t cap_off = 0;
+    auto pass = [&] {
+        CK(cudaEventRecord(tm[0], st_));
+        for (size_t k = 0; k < nchunks; ++k) {             // interpolate my slice of chunk k, then gather the chunk (comm stream)
+            u64* mine = coeffs.get() + (k * G * w + (size_t)rank_ * w) * n;
+            launch_intt_natural(vals.get() + k * w * n, n, mine, n, (int)w, lg_n, nullptr, st_);
+            CK(cudaEventRecord(chain[2 * k], st_));
+            CK(cudaStreamWaitEvent(comm_st_, chain[2 * k], 0));
+            if (k == 0) CK(cudaEventRecord(tm[3], comm_st_));
+            NK(nccl().AllGather(mine, coeffs.get() + k * G * w * n, w * n, ncclUint64, comm, comm_st_));   // in place
+            CK(cudaEventRecord(chain[2 * k + 1], comm_st_));
+        }
+        CK(cudaEventRecord(tm[4], comm_st_));
+        for (size_t k = 0; k < nchunks; ++k) {             // the gather of chunk k + 1 runs behind the LDE of chunk k
+            CK(cudaStreamWaitEvent(st_, chain[2 * k + 1], 0));
+            const size_t c0 = k * G * w;
+            if (c0 >= ncols) break;
+            const size_t cnt = std::min(G * w, ncols - c0);
+            launch_lde_blocks(coeffs.get() + c0 * n, n, lde.get() + c0 * L, L, (int)cnt, lg_n, rate_bits, GL_GEN, blk_lo, blk_lo + B, st_);
+        }
+        CK(cudaEventRecord(tm[1], st_));
+        cap_off = launch_merkle_tree(lde.get(), L, (int)ncols, L, dg.get(), cap_local, st_);
+        NK(nccl().AllGather(dg.get() + cap_off * 4, cap_all.get(), (size_t(4) << cap_local), ncclUint64, comm, st_));
+        CK(cudaEventRecord(tm[2], st_));
+        CK(cudaEventSynchronize(tm[2]));
+        CK(cudaStreamSynchronize(comm_st_));
+    };
+    if (reps > 1) pass();                                  // untimed: twiddle / coset tables, NCCL channel setup
+    for (int r = 0; r < reps; ++r) {
+        pass();
+        float a, b, c;
+        CK(cudaEventElapsedTime(&a, tm[0], tm[1]));
+        CK(cudaEventElapsedTime(&b, tm[1], tm[2]));
+        CK(cudaEventElapsedTime(&c, tm[3], tm[4]));
+        t_lde += a; t_merkle += b; t_gather += c;
+    }
+    if (times_ms) { times_ms[0] = t_lde / reps; times_ms[1] = t_merkle / reps; times_ms[2] = t_gather / reps; }
+    CK(cudaMemcpyAsync(cap_out, cap_all.get(), (size_t(32)) << cap_height, cudaMemcpyDeviceToHost, st_));
+    CK(cudaStreamSynchronize(st_));
+}
+
+void Comm::quotient_chunks(const u64* q_values, size_t nch, size_t n, unsigned rate_bits, u64* chunks_out, float* times_ms) {
+    if (!q_values || !chunks_out) throw ArgError("null argument");
+    if (n < 2 || (n & (n - 1)) || rate_bits > 4 || !nch || nch > 4) throw ArgError("bad shape");
+    const unsigned G = (unsigned)nranks_, R = 1u << rate_bits;
+    if (G > R) throw ArgError("more ranks than coset blocks");
+    if (n % G) throw ArgError("n must be a multiple of the number of ranks");
+    CK(cudaSetDevice(device_));
+    ncclComm_t comm = static_cast<ncclComm_t>(comm_);
+    const unsigned lg_n = lg2u(n), B = R / G;
+    const size_t sl = n / G;                                  // coefficient indices per rank
+    const u64 w_N = gl_root_of_unity(lg_n + rate_bits);
+    DevBuf u(nch * B * n), all((size_t)nch * R * sl), out((size_t)nch * R * sl), mat((size_t)R * R);
+    Events tm(3);
+    CK(cudaMemcpyAsync(u.get(), q_values, nch * B * n * 8, cudaMemcpyHostToDevice, st_));
+    // V^-1[m][j] = c_0^-m w_R^(-j m) / R with c_j = (g w_N^j)^n = c_0 w_R^j
+    std::vector<u64> vinv((size_t)R * R);
+    const u64 c0_inv = gl_inv(gl_pow(GL_GEN, n)), wR_inv = gl_inv(gl_pow(w_N, n)), r_inv = gl_inv(R);
+    for (unsigned m = 0; m < R; ++m)
+        for (unsigned j = 0; j < R; ++j)
+            vinv[(size_t)m * R + j] = gl_mul(gl_mul(gl_pow(c0_inv, m), gl_pow(wR_inv, (u64)j * m)), r_inv);
+    CK(cudaMemcpyAsync(mat.get(), vinv.data(), vinv.size() * 8, cudaMemcpyHostToDevice, st_));
+    CK(cudaEventRecord(tm[0], st_));
+    // u_j: interpolant of t on coset j (block i of this rank is leaf block jb = rank B + i, coset j = bitrev(jb))
+    for (size_t ch = 0; ch < nch; ++ch)
+        for (unsigned i = 0; i < B; ++i) {
+            const unsigned jb = (unsigned)rank_ * B + i, j = bitrev32(jb, rate_bits);
+            launch_coset_intt_bitrev(u.get() + (ch * B + i) * n, n, 1, lg_n, gl_mul(GL_GEN, gl_pow(w_N, j)), st_);
+        }
+    CK(cudaEventRecord(tm[1], st_));
+    // all-to-all: peer p gets coefficient slice p of every (challenge, block) interpolant of this rank; placed by coset index
+    NK(nccl().GroupStart());
+    for (unsigned p = 0; p < G; ++p)
+        for (size_t ch = 0; ch < nch; ++ch)
+            for (unsigned i = 0; i < B; ++i) {
+                NK(nccl().Send(u.get() + (ch * B + i) * n + (size_t)p * sl, sl, ncclUint64, (int)p, comm, st_));
+                const unsigned j = bitrev32(p * B + i, rate_bits);
+                NK(nccl().Recv(all.get() + (ch * R + j) * sl, sl, ncclUint64, (int)p, comm, st_));
+            }
+    NK(nccl().GroupEnd());
+    for (size_t ch = 0; ch < nch; ++ch)
+        launch_vandermonde_solve(all.get() + ch * R * sl, out.get() + ch * R * sl, sl, R, mat.get(), st_);
+    CK(cudaEventRecord(tm[2], st_));
+    CK(cudaMemcpyAsync(chunks_out, out.get(), (size_t)nch * R * sl * 8, cudaMemcpyDeviceToHost, st_));
+    CK(cudaStreamSynchronize(st_));
+    if (times_ms) {
+        CK(cudaEventElapsedTime(&times_ms[0], tm[0], tm[1]));
+        CK(cudaEventElapsedTime(&times_ms[1], tm[1], tm[2]));
+    }
+}
+
+}  // namespace zkb

@@ -33,7 +33,8 @@ EXPORTS = ["zkb_version", "zkb_last_error", "zkb_device_count", "zkb_kernel_laun
            "zkb_last_timings", "zkb_poseidon_permute_batch", "zkb_lde_batch", "zkb_merkle_commit", "zkb_commit_batch",
            "zkb_commit_cosets",
            "zkb_partial_products", "zkb_quotient", "zkb_engine_create", "zkb_engine_destroy", "zkb_engine_proof_size",
-           "zkb_engine_acquire", "zkb_engine_release", "zkb_engine_submit", "zkb_engine_wait"]
+           "zkb_engine_acquire", "zkb_engine_release", "zkb_engine_submit", "zkb_engine_wait", "zkb_comm_unique_id", "zkb_comm_create",
+           "zkb_comm_destroy", "zkb_commit_sharded", "zkb_quotient_chunks_sharded"]
 # `flags` of the prove calls (include/zkb200.h)
 POW_MIN, SALTS_FROM_SEED, CHECK_WITNESS, WITNESS_RESIDENT = 0, 0x100, 0x200, 0x400
 SYNTH_LIB_PATH = os.path.join(_ROOT, "libzkb200_synth.so")
@@ -96,6 +97,12 @@ def lib():
         L.zkb_engine_submit.argtypes = [ctypes.c_void_p, ctypes.c_int, u64p, ctypes.c_size_t, u64p, ctypes.c_uint64, ctypes.c_uint32, u8p,
                                         ctypes.c_size_t]
         L.zkb_engine_wait.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.POINTER(ctypes.c_size_t)]
+        L.zkb_comm_unique_id.argtypes = [u8p]
+        L.zkb_comm_create.argtypes = [u8p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.POINTER(ctypes.c_void_p)]
+        L.zkb_comm_destroy.argtypes = [ctypes.c_void_p]
+        L.zkb_commit_sharded.argtypes = [ctypes.c_void_p, u64p, ctypes.c_size_t, ctypes.c_size_t, ctypes.c_uint, ctypes.c_uint, ctypes.c_int,
+                                         u64p, f32p]
+        L.zkb_quotient_chunks_sharded.argtypes = [ctypes.c_void_p, u64p, ctypes.c_size_t, ctypes.c_size_t, ctypes.c_uint, u64p, f32p]
         _lib = L
     return _lib
 
@@ -301,6 +308,48 @@ class ProverCircuit:
         return out
 
 
+def comm_unique_id():
+    """128 bytes from ncclGetUniqueId: rank 0 creates them, every rank passes them to Comm()."""
+    out = np.zeros(128, dtype=np.uint8)
+    _check(lib().zkb_comm_unique_id(out.ctypes.data_as(u8p)))
+    return out
+
+
+class Comm:
+    """zkb_comm: this process's rank in an NCCL communicator owned by libzkb200.so (one process per GPU)."""
+
+    def __init__(self, unique_id, nranks, rank, device=0):
+        self._h = ctypes.c_void_p()
+        uid = np.ascontiguousarray(unique_id, dtype=np.uint8)
+        _check(lib().zkb_comm_create(uid.ctypes.data_as(u8p), nranks, rank, device, ctypes.byref(self._h)))
+        self.nranks, self.rank = nranks, rank
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib().zkb_comm_destroy(self._h)
+            self._h = None
+
+    __del__ = close
+
+    def commit(self, values, rate_bits=3, cap_height=4, reps=1):
+        """Coset-sharded from_values commitment; returns (cap [2^cap_height][4], {'lde_ms','merkle_ms','gather_ms'})."""
+        a, p = _u64(values)
+        ncols, n = a.shape
+        cap = np.zeros((1 << cap_height, 4), dtype=np.uint64)
+        t = np.zeros(3, dtype=np.float32)
+        _check(lib().zkb_commit_sharded(self._h, p, ncols, n, rate_bits, cap_height, reps, cap.ctypes.data_as(u64p), t.ctypes.data_as(f32p)))
+        return cap, {"lde_ms": float(t[0]), "merkle_ms": float(t[1]), "gather_ms": float(t[2])}
+
+    def quotient_chunks(self, q_values, n, rate_bits=3):
+        """q_values [nch][B n]: the quotient's evaluations on this rank's leaf blocks -> [nch][2^rate_bits][n / nranks]."""
+        a, p = _u64(q_values)
+        nch = a.shape[0]
+        out = np.zeros((nch, 1 << rate_bits, n // self.nranks), dtype=np.uint64)
+        t = np.zeros(2, dtype=np.float32)
+        _check(lib().zkb_quotient_chunks_sharded(self._h, p, nch, n, rate_bits, out.ctypes.data_as(u64p), t.ctypes.data_as(f32p)))
+        return out, {"interpolate_ms": float(t[0]), "exchange_ms": float(t[1])}
+
+
 class Engine:
     """zkb_engine: n_contexts prover contexts of one circuit on one GPU behind an asynchronous submit / wait interface with
     pinned witness slots (include/zkb200.h). `acquire()` returns (slot, wires) where wires is a writable numpy view
@@ -351,8 +400,11 @@ class Engine:
 
     def wait(self, slot):
         n = ctypes.c_size_t(0)
+        # take our buffers out of the table BEFORE the C call: zkb_engine_wait frees the slot, and another thread may acquire
+        # and submit on the same slot id before this thread runs again
+        out, salts_keep = self._keep.pop(slot, (None, None))
         rc = lib().zkb_engine_wait(self._h, slot, ctypes.byref(n))
-        out, _ = self._keep.pop(slot, (None, None))
+        del salts_keep
         _check(rc)
         return out[: n.value]
 

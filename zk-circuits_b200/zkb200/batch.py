@@ -141,3 +141,128 @@ def max_over_ranks(values, device=None):
     t = torch.tensor(list(values), dtype=torch.float64, device=device or "cpu")
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     return [float(x) for x in t]
+
+
+# ---------------------------------------------------------------------------------------------------------------------------
+# Aggregator orchestration: the host logic around the chunk proofs of
+# /root/reference/wormhole/aggregator/src/{aggregator.rs:74-93, util.rs:11-29, circuits/tree.rs:17-103}, scheduled so that a box
+# of GPUs stays busy: trees are dealt to ranks (one process per GPU, no proof ever crosses a GPU), and inside a rank the chunk
+# proofs of ALL its trees form one dependency graph — a chunk is ready as soon as its `branching` children are proved — fed to
+# the rank's prover contexts. With the reference's level-by-level schedule an 8-leaf tree shows the GPU 4, then 2, then 1
+# concurrent proofs; with several trees in flight the narrow upper levels of one tree overlap the wide lower levels of the next.
+# ---------------------------------------------------------------------------------------------------------------------------
+class TreeAggregationConfig:
+    """tree.rs:32-52: num_leaf_proofs = branching ** depth (default 2, 3 -> 8 leaves, 4 + 2 + 1 chunk proofs)."""
+
+    def __init__(self, tree_branching_factor=2, tree_depth=3):
+        if tree_branching_factor < 2 or tree_depth < 1:
+            raise ValueError("branching factor >= 2 and depth >= 1")
+        self.tree_branching_factor = tree_branching_factor
+        self.tree_depth = tree_depth
+        self.num_leaf_proofs = tree_branching_factor ** tree_depth
+
+
+def pad_with_dummy_proofs(proofs, proof_len, dummy_proof):
+    """util.rs:11-29: append copies of the dummy leaf proof up to proof_len; more proofs than that is an error."""
+    proofs = list(proofs)
+    if len(proofs) > proof_len:
+        raise ValueError("proofs to aggregate was more than the maximum allowed")
+    return proofs + [dummy_proof] * (proof_len - len(proofs))
+
+
+def split_aggregated_public_inputs(public_inputs, leaf_pi_len, num_leaves):
+    """circuit/src/inputs.rs:57-89 (`try_from_aggregated`): the root proof's public inputs are the leaves' public inputs in
+    order (every chunk circuit registers its children's, tree.rs:121-123); returns num_leaves slices of leaf_pi_len."""
+    pis = list(public_inputs)
+    expected = leaf_pi_len * num_leaves
+    if len(pis) != expected:
+        raise ValueError(f"aggregated public inputs should contain: {expected} (= {num_leaves} leaves x {leaf_pi_len} fields), "
+                         f"got: {len(pis)}")
+    return [pis[i:i + leaf_pi_len] for i in range(0, expected, leaf_pi_len)]
+
+
+def tree_for_rank(num_trees, rank, world_size):
+    """trees dealt round-robin: tree t is aggregated wholly on rank t % world_size"""
+    return [t for t in range(num_trees) if t % world_size == rank]
+
+
+def aggregate_forest(forest, config, prove_chunk, workers, dummy_proof=None, clock=None):
+    """Aggregate this rank's share of `forest` (a list of leaf-proof lists, identical on every rank) — every tree padded to
+    config.num_leaf_proofs with dummy_proof as `aggregate()` does (aggregator.rs:79-83) — with a dependency-driven schedule
+    over `workers` concurrent prove calls.
+
+    prove_chunk(worker_index, chunk, level, index, tree) -> proof     (level 0 = chunks of leaf proofs)
+    Returns ({tree: root_proof} for this rank's trees, stats) where stats['level_concurrency'][k] is the average number of
+    level-k chunk proofs in flight while any was (the per-level occupancy of this GPU's proof contexts) and stats['spans'] the
+    (tree, level, index, start, end) records."""
+    import queue
+    import time as _time
+
+    clock = clock or _time.perf_counter
+    rank, ws = world()
+    mine = tree_for_rank(len(forest), rank, ws)
+    b, depth = config.tree_branching_factor, config.tree_depth
+    done = {}                    # (tree, level, index) -> proof; level -1 = (padded) leaves
+    pending = {}                 # (tree, level, index) -> children still missing
+    ready = queue.Queue()
+    lock = threading.Lock()
+    for t in mine:
+        leaves = pad_with_dummy_proofs(forest[t], config.num_leaf_proofs, dummy_proof) if dummy_proof is not None else list(forest[t])
+        if len(leaves) != config.num_leaf_proofs:
+            raise ValueError("a tree needs exactly branching ** depth leaf proofs (pass dummy_proof to pad)")
+        for i, p in enumerate(leaves):
+            done[(t, -1, i)] = p
+        for i in range(config.num_leaf_proofs // b):
+            ready.put((t, 0, i))
+        for lvl in range(1, depth):
+            for i in range(config.num_leaf_proofs // b ** (lvl + 1)):
+                pending[(t, lvl, i)] = b
+    total = sum(config.num_leaf_proofs // b ** (lvl + 1) for lvl in range(depth)) * len(mine)
+    spans, errors = [], []
+    remaining = [total]
+
+    def worker(w):
+        while True:
+            job = ready.get()
+            if job is None:
+                return
+            t, lvl, i = job
+            try:
+                chunk = [done[(t, lvl - 1, b * i + k)] for k in range(b)]
+                t0 = clock()
+                proof = prove_chunk(w, chunk, lvl, i, t)
+                t1 = clock()
+            except Exception as e:  # noqa: BLE001
+                errors.append(e)
+                for _ in range(workers):
+                    ready.put(None)
+                return
+            with lock:
+                done[(t, lvl, i)] = proof
+                spans.append((t, lvl, i, t0, t1))
+                remaining[0] -= 1
+                parent = (t, lvl + 1, i // b)
+                if parent in pending:
+                    pending[parent] -= 1
+                    if pending[parent] == 0:
+                        ready.put(parent)
+                if remaining[0] == 0:
+                    for _ in range(workers):
+                        ready.put(None)
+
+    if total == 0:
+        return {}, {"level_concurrency": [], "spans": []}
+    threads = [threading.Thread(target=worker, args=(w,)) for w in range(workers)]
+    for th in threads:
+        th.start()
+    for th in threads:
+        th.join()
+    if errors:
+        raise errors[0]
+    conc = []
+    for lvl in range(depth):
+        s = [(t0, t1) for (_, l, _, t0, t1) in spans if l == lvl]
+        busy = sum(t1 - t0 for t0, t1 in s)
+        span = max(t1 for _, t1 in s) - min(t0 for t0, _ in s)
+        conc.append(busy / span if span > 0 else float(len(s)))
+    return {t: done[(t, depth - 1, 0)] for t in mine}, {"level_concurrency": conc, "spans": spans}

@@ -1,12 +1,26 @@
 // ORACLE — TEST INFRASTRUCTURE ONLY (see poseidon.hpp header).
 #include "poseidon.hpp"
 #include "poseidon_fast.hpp"
+#include "ntt.hpp"
+#include <map>
 #include <mutex>
 
 namespace orc {
 
 bool g_fast_poseidon = false;
 void poseidon_permute_fast(u64* st) { poseidon_permute_fast_impl(st); }
+const std::vector<u64>& fastntt::twiddles(unsigned lg) {
+    static std::mutex mu;
+    static std::map<unsigned, std::vector<u64>> cache;
+    std::lock_guard<std::mutex> lk(mu);
+    auto it = cache.find(lg);
+    if (it != cache.end()) return it->second;
+    std::vector<u64> t(lg ? (size_t(1) << (lg - 1)) : 1);
+    const u64 w = root_of_unity(lg);
+    t[0] = 1;
+    for (size_t k = 1; k < t.size(); ++k) t[k] = fmul(t[k - 1], w);
+    return cache.emplace(lg, std::move(t)).first->second;
+}
 
 // ---- round-constant regeneration: ChaCha8 keystream keyed by rand_core's
 // seed_from_u64(0) PCG32 expansion; u64 draws mapped to [0,p) by the widening-multiply rule.

@@ -22,6 +22,12 @@ PolyBatch batch_from_coeffs(std::vector<std::vector<u64>> coeffs, unsigned rate_
 #pragma omp parallel for schedule(dynamic)
     for (long c = 0; c < (long)b.ncols; ++c) {
         if (coeffs[c].size() != b.n) continue;
+        if (g_fast_poseidon) {       // CPU-baseline arm: 2^rate_bits coset transforms of size n, already in leaf order
+            std::vector<u64> v(N);
+            lde_coset_leaf_order_fast(coeffs[c], rate_bits, GEN, v.data());
+            for (size_t l = 0; l < N; ++l) leaves[l * width + c] = v[l];
+            continue;
+        }
         std::vector<u64> v = lde_coset<u64>(coeffs[c], rate_bits);
         for (size_t i = 0; i < N; ++i) leaves[reverse_bits(i, lg) * width + c] = v[i];
     }
@@ -234,15 +240,23 @@ Proof prove(const CircuitData& cd, const std::vector<std::vector<u64>>& wires, c
     E2 alpha = chal.get_ext();
     std::vector<E2> final_poly(n);
     {
-        // batch 0: all polys at zeta
+        // batch 0: all polys at zeta. comp[k] = sum_j alpha^j c_j[k]: independent per coefficient index k
         std::vector<E2> comp(n);
+        std::vector<E2> apow;
+        std::vector<const std::vector<u64>*> cols;
         E2 ap(1);
         for (int t = 0; t < 4; ++t)
             for (size_t j = 0; j < oracles[t]->ncols; ++j) {
-                const auto& cf = oracles[t]->coeffs[j];
-                for (size_t k = 0; k < n; ++k) comp[k] = comp[k] + emul_base(ap, cf[k]);
+                cols.push_back(&oracles[t]->coeffs[j]);
+                apow.push_back(ap);
                 ap = ap * alpha;
             }
+#pragma omp parallel for schedule(static)
+        for (long k = 0; k < (long)n; ++k) {
+            E2 acc;
+            for (size_t j = 0; j < cols.size(); ++j) acc = acc + emul_base(apow[j], (*cols[j])[k]);
+            comp[k] = acc;
+        }
         auto divide_by_linear = [&](const std::vector<E2>& p, E2 z) {
             std::vector<E2> qv(n);  // n-1 coefficients + a zero pad
             E2 acc;

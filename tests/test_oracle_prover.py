@@ -101,3 +101,17 @@ def test_lde_definition(oracle):
             for k in reversed(range(n)):
                 acc = (acc * x + int(coeffs[c, k])) % oracle.P
             assert acc == int(lde[c, l])
+
+
+def test_fast_mode_proof_is_byte_identical(oracle):
+    """The CPU-baseline arm (oracle.set_fast(True): AVX2 Poseidon) emits the same proof bytes as the readable restatement."""
+    s = oracle.Synth(zk=True, seed=5, **oracle.Synth.TINY)
+    c = oracle.Circuit(s.common, s.const_sigma_values)
+    try:
+        oracle.set_fast(False)
+        want = c.prove(s.wires, s.public_inputs, salt_seed=3)
+        oracle.set_fast(True)
+        got = c.prove(s.wires, s.public_inputs, salt_seed=3)
+        assert got == want and c.verify(got) == ""
+    finally:
+        oracle.set_fast(False)

@@ -342,17 +342,16 @@ __global__ void __launch_bounds__(128) merkle_leaves_wide_kernel(const u64* __re
 constexpr size_t MERKLE_WIDE_MAX_NODES = 4096;   // levels this small are latency-bound with one node per thread
 
 // ---- tree levels --------------------------------------------------------------------------------------------------------
-// A tree used to be one leaf kernel + one launch per level (13 for the wormhole trees). The levels with many nodes are real
-// work (a level of 65 536 nodes is 2.6 % of the wires tree's permutations), but from ~8 k nodes down every level costs one
-// permutation's dependency chain whatever its size, and the GPU idles between the launches. Now: one node per thread while a
-// level has more than 4096 parents, then ONE launch for everything above —
-//   merkle_cap_subtree_kernel  one CTA per cap digest finishes that digest's subtree (<= 256 entry nodes) with the lane-parallel
-//                              permutation (12 lanes per node, MDS through warp shuffles): a level costs ~1/4 of the
-//                              one-node-per-thread latency and no launch; 7 launches per wormhole tree instead of 14.
-// Measured and rejected (round 2, profiles/r02_merkle_fusion.md): building the bottom 7 levels inside the leaf kernel (a CTA
-// hashes 128 leaves, then its subtree through shared memory, one permutation call site) — 2 launches per tree, bit-exact, but
-// every CTA reaches its narrow levels at the same time and holds its registers through seven mostly idle permutation
-// latencies: wires tree 2.52 -> 2.78 ms, 8-stream throughput 213 -> 187 proofs/s.
+// One launch per level while a level is real work: one node per thread above 4096 parents (a level of 65 536 nodes is 2.6 % of
+// the wires tree's permutations), 12 lanes per node below that (merkle_level_wide_kernel: nodes spread over many CTAs so that
+// every SM holds a few lane-parallel chains). The last levels — at most 64 entry nodes per cap digest — are ONE launch:
+//   merkle_cap_subtree_kernel  one CTA per cap digest finishes that digest's subtree with the lane-parallel permutation.
+// The prover replays each tree's chain of level launches as a CUDA graph (prover.cpp run_merkle_levels).
+// Measured and rejected in round 2 (profiles/r02_merkle_fusion.md): (a) building the bottom 7 levels inside the leaf kernel
+// (2 launches per tree, bit-exact): every CTA reaches its narrow levels at the same time and holds its registers through seven
+// mostly idle permutation latencies — wires tree 2.52 -> 2.78 ms, 8-stream throughput 213 -> 187 proofs/s; (b) one CTA per cap
+// digest for the last EIGHT levels (256 entry nodes): 32 warps of lane-parallel chains on one SM serialise on its four
+// schedulers (~26 us per pass instead of ~11) — wires tree 2.74 ms.
 // levels above `in` (nodes_total digests) down to nodes_total >> levels digests; CTA b owns output digest b of the last level
 __global__ void __launch_bounds__(1024) merkle_cap_subtree_kernel(u64* __restrict__ base, size_t nodes_total, int levels) {
     __shared__ u32 s_rc[3 * P_WIDTH * P_ROUNDS];
@@ -380,7 +379,7 @@ __global__ void __launch_bounds__(1024) merkle_cap_subtree_kernel(u64* __restric
 }
 
 static unsigned lg2_size(size_t x) { unsigned k = 0; while ((size_t(1) << k) < x) ++k; return k; }
-constexpr unsigned MERKLE_CAP_SUBTREE_MAX_ENTRY = 256;
+constexpr unsigned MERKLE_CAP_SUBTREE_MAX_ENTRY = 64;      // per cap digest: 32 parents x 16 lanes = one 512-thread CTA per digest
 
 // levels above level `done` (whose digests are in place) of a tree whose leaf level has num_leaves digests; returns the cap offset
 static size_t merkle_finish_levels(u64* digests, size_t num_leaves, unsigned cap_height, unsigned done, cudaStream_t st) {
@@ -390,7 +389,7 @@ static size_t merkle_finish_levels(u64* digests, size_t num_leaves, unsigned cap
     while (level < T) {
         const size_t nodes = num_leaves >> level, off = merkle_level_offset(num_leaves, level);
         const unsigned remaining = T - level;
-        if (remaining <= lg2_size(MERKLE_CAP_SUBTREE_MAX_ENTRY) && nodes <= 2 * MERKLE_WIDE_MAX_NODES) {
+        if (remaining <= lg2_size(MERKLE_CAP_SUBTREE_MAX_ENTRY) && nodes <= MERKLE_WIDE_MAX_NODES) {
             const unsigned parents = (1u << remaining) >> 1;                // per cap digest
             unsigned threads = parents * 16;
             threads = threads < 32 ? 32 : (threads > 1024 ? 1024 : threads);

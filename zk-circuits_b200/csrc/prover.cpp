@@ -224,6 +224,8 @@ void Circuit::init(const u64* const_sigma, bool is_values, const u64* digest) {
 void Circuit::cleanup() {
     cudaSetDevice(device_);
     if (st_) cudaStreamSynchronize(st_);
+    for (auto& kv : level_graphs_) if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
+    level_graphs_.clear();
     for (auto& e : ev_) if (e) { cudaEventDestroy(e); e = nullptr; }
     for (auto& a : qfork_.aux) if (a) { cudaStreamSynchronize(a); cudaStreamDestroy(a); a = nullptr; }
     if (qfork_.fork) { cudaEventDestroy(qfork_.fork); qfork_.fork = nullptr; }
@@ -274,6 +276,29 @@ void Circuit::sync() {
     }
 }
 
+size_t Circuit::run_merkle_levels(u64* digests, size_t num_leaves, unsigned cap_height) {
+    LevelGraph& g = level_graphs_[digests];
+    if (!g.exec) {
+        // one capture at a time per process: it happens once per tree and context, keeps the launch count of the captured
+        // chain exact when several contexts warm up together, and profilers (ncu) crash on concurrent stream captures
+        static std::mutex capture_mu;
+        std::lock_guard<std::mutex> lk(capture_mu);
+        const unsigned long long before = kernel_launch_count();
+        cudaGraph_t graph = nullptr;
+        CK(cudaStreamBeginCapture(st_, cudaStreamCaptureModeThreadLocal));
+        g.cap_offset = launch_merkle_levels(digests, num_leaves, cap_height, st_);
+        CK(cudaStreamEndCapture(st_, &graph));
+        g.kernels = kernel_launch_count() - before;      // counted once at capture; every replay adds them again
+        if (!graph) return g.cap_offset;                 // a tree with no level above the leaves
+        CK(cudaGraphInstantiate(&g.exec, graph, 0));
+        CK(cudaGraphDestroy(graph));
+    } else {
+        kernel_launch_count_add(g.kernels);
+    }
+    CK(cudaGraphLaunch(g.exec, st_));
+    return g.cap_offset;
+}
+
 void Circuit::verifier_only(u64* cap_out, u64 digest_out[4]) const {
     if (cap_out) std::memcpy(cap_out, cs_cap_.data(), cs_cap_.size() * 8);
     if (digest_out) std::memcpy(digest_out, circuit_digest_, 32);
@@ -300,7 +325,8 @@ void Circuit::commit_batch(BatchDev& b, unsigned batch_id, u64* cap_host) {
     const unsigned cap_h = (unsigned)cd_.cap_height;
     launch_lde(b.coeff_ptr, b.coeff_stride, b.lde.get(), N_, b.ncols, lg_n_, (unsigned)cd_.rate_bits, GL_GEN, st_);
     if (&b != &cs_) fill_salts(b, batch_id);
-    b.cap_offset = launch_merkle_tree(b.lde.get(), N_, b.ncols + b.salt, N_, b.digests.get(), cap_h, st_);
+    launch_merkle_leaves(b.lde.get(), N_, b.ncols + b.salt, N_, b.digests.get(), st_);
+    b.cap_offset = run_merkle_levels(b.digests.get(), N_, cap_h);
     CK(cudaMemcpyAsync(cap_host, b.digests.get() + b.cap_offset * 4, (size_t(32)) << cap_h, cudaMemcpyDeviceToHost, st_));
 }
 
@@ -535,7 +561,8 @@ void Circuit::begin_proof(const u64* public_inputs, size_t n_pi, const u64* salt
     launch_lde(wires_.coeff_ptr, n_, wires_.lde.get(), N_, nw, lg_n_, (unsigned)cd_.rate_bits, GL_GEN, st_);
     CK(cudaEventRecord(ev_[T_WIRES_LDE + 1], st_));      // exactly the coset-LDE launch: bench.py's roofline kernel
     fill_salts(wires_, 0);
-    wires_.cap_offset = launch_merkle_tree(wires_.lde.get(), N_, nw + wires_.salt, N_, wires_.digests.get(), cap_h, st_);
+    launch_merkle_leaves(wires_.lde.get(), N_, nw + wires_.salt, N_, wires_.digests.get(), st_);
+    wires_.cap_offset = run_merkle_levels(wires_.digests.get(), N_, cap_h);
     CK(cudaMemcpyAsync(h_stage_ + ho_.caps, wires_.digests.get() + wires_.cap_offset * 4, cap_words * 8, cudaMemcpyDeviceToHost, st_));
     CK(cudaEventRecord(ev_[T_WIRES_MERKLE + 1], st_));
     queue_flag_readback();
@@ -553,7 +580,8 @@ void Circuit::queue_fri_layer() {
     u64* va = fri_values_[i].get();
     launch_lde(ca, j.m, va, M, 2, j.lg_m, rate_bits, j.shift, st_);
     const size_t leaves = M >> ab;
-    fri_cap_off_[i] = launch_merkle_tree_ext(va, va + M, 1 << ab, leaves, fri_digests_[i].get(), cap_h, st_);
+    launch_merkle_leaves_ext(va, va + M, 1 << ab, leaves, fri_digests_[i].get(), st_);
+    fri_cap_off_[i] = run_merkle_levels(fri_digests_[i].get(), leaves, cap_h);
     CK(cudaMemcpyAsync(h_stage_ + ho_.caps + (3 + i) * cap_words, fri_digests_[i].get() + fri_cap_off_[i] * 4, cap_words * 8,
                        cudaMemcpyDeviceToHost, st_));
 }

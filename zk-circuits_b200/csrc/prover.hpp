@@ -143,6 +143,11 @@ private:
     std::vector<size_t> fri_cap_off_;
     DevBuf pow_dev_;             // 12 state words + 1 result
     DevBuf flag_dev_;            // bit 0: non-canonical input, bit 1: unsatisfied constraint (witness self-check)
+    // A tree's chain of level launches (8 short, strictly dependent kernels on fixed buffers) is captured once into a CUDA
+    // graph and replayed: one host call per tree, no launch gaps between 10-50 us kernels.
+    struct LevelGraph { cudaGraphExec_t exec = nullptr; size_t cap_offset = 0; unsigned long long kernels = 0; };
+    std::map<const u64*, LevelGraph> level_graphs_;
+    size_t run_merkle_levels(u64* digests, size_t num_leaves, unsigned cap_height);
     bool witness_loaded_ = false;
     DevBuf query_idx_dev_;       // u32 indices: (1 + layers) * nq, packed in u64 words
     DevBuf query_out_dev_;

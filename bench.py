@@ -286,6 +286,12 @@ def main():
     torch.cuda.synchronize()
     t_single = time.perf_counter() - t0
     launches = (Z.kernel_launch_count() - launches0) // K
+    # the same with ZKB_CHECK_WITNESS (every constraint evaluated on the subgroup before Z is committed)
+    circ.prove_resident(pis, salt_seed=1, check_witness=True, out=outs[0])
+    t0 = time.perf_counter()
+    for i in range(K):
+        circ.prove_resident(pis, salt_seed=2000 * (rank + 1) + i, check_witness=True, out=outs[0])
+    t_single_checked = time.perf_counter() - t0
     # ---- device-resident throughput arm (`value`): B proofs in flight per GPU ----
     # Driver: the proof ENGINE (default) — B prover contexts stepped by ONE host thread inside the library, proofs submitted
     # asynchronously (zkb_engine_*); `--driver threads` is round 1's form, one blocking host thread per proof in flight.
@@ -404,6 +410,7 @@ def main():
         # (timing only: exactness is tests/test_gpu_new_paths.py + the gloo test of the same exchange)
         qn = 1 << 20
         qv = synth_columns(np, 20, 2 * (8 // world)).reshape(2, (8 // world) * qn)
+        comm.quotient_chunks(qv, qn, 3)                      # untimed: NCCL sets up its point-to-point channels on first use
         barrier()
         _, qt = comm.quotient_chunks(qv, qn, 3)
         qi, qx = zbatch.max_over_ranks([qt["interpolate_ms"], qt["exchange_ms"]], device="cuda")
@@ -486,7 +493,7 @@ def main():
                                       "device + every work buffer (SURVEY 8f rank 1; cached per circuit by zkb200.batch.ContextPool). One "
                                       "cudaMalloc of ~0.6 GB dominates and varies by box (2 ms to 400 ms, fresh memory being cleared); the "
                                       "rest is ~5 ms (ZKB_TRACE=1)"},
-        "prove_ms_single_stream": 1000 * t_single / K, "device_ms_per_proof": stages["total"], "stage_ms": stages,
+        "prove_ms_single_stream": 1000 * t_single / K, "prove_ms_single_stream_with_witness_check": 1000 * t_single_checked / K, "device_ms_per_proof": stages["total"], "stage_ms": stages,
         "e2e": {"value": world * K * B / t_e2e, "unit": UNIT, "ms_per_step": 1000 * t_e2e / K,
                 "h2d_bytes_per_step": int(B * (nw * n * 8 + pis.size * 8)), "d2h_bytes_per_step": int(B * len(proof))},
         "gpu_launches": int(launches) * B,

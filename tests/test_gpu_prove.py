@@ -62,7 +62,9 @@ def test_recursion_gate_set_proof_bytes(zkb, oracle):
 
 
 def test_recursion_shaped_circuit_proof_bytes(zkb, oracle):
-    """A recursion-shaped circuit at the size class of one aggregation chunk (n = 2^12, non-zk as in tree.rs:165)."""
+    """A recursion-shaped circuit at the size class of one aggregation chunk, NON-zk: n = 2^12. (The reference's own tree tests
+    build their toy circuits with the non-zk `standard_recursion_config`, tree.rs:165; the production aggregator inherits the
+    leaf circuit's zk config — aggregator.rs:21, tree.rs:111 — which is the next test's shape.)"""
     s, oc, gc, proof = run_case(zkb, oracle, oracle.Synth.RECURSION, False, seed=4)
     assert s.info["degree_bits"] == 12 and len(proof) == gc.proof_size
 

@@ -70,6 +70,19 @@ __global__ void field_selfcheck_kernel(unsigned long long* bad) {
         mism += f_mul(a, b) != want_mul;
         mism += f_mul(z, b) != (u64)(((unsigned __int128)z * b) % GL_P);          // lazy (non-canonical) left operand
         mism += f_canon(z) != gl_canon(z);
+        // the shift forms of the NTT's power-of-two twiddles (every word offset, edge shift counts)
+        auto pow2 = [](int k) { u64 r = 1; for (int t = 0; t < k; ++t) r = gl_add(r, r); return r; };
+        mism += f_shl<12>(a) != (u64)(((unsigned __int128)a * pow2(12)) % GL_P);
+        mism += f_shl<24>(a) != (u64)(((unsigned __int128)a * pow2(24)) % GL_P);
+        mism += f_shl<31>(b) != (u64)(((unsigned __int128)b * pow2(31)) % GL_P);
+        mism += f_shl<32>(a) != (u64)(((unsigned __int128)a * pow2(32)) % GL_P);
+        mism += f_shl<48>(b) != (u64)(((unsigned __int128)b * pow2(48)) % GL_P);
+        mism += f_shl<63>(a) != (u64)(((unsigned __int128)a * pow2(63)) % GL_P);
+        mism += f_shl<64>(b) != (u64)(((unsigned __int128)b * pow2(64)) % GL_P);
+        mism += f_shl<72>(a) != (u64)(((unsigned __int128)a * pow2(72)) % GL_P);
+        mism += f_shl<84>(b) != (u64)(((unsigned __int128)b * pow2(84)) % GL_P);
+        mism += f_shl<95>(a) != (u64)(((unsigned __int128)a * pow2(95)) % GL_P);
+        mism += f_sub_twiddle16<3, true>(a, b) != (u64)(((unsigned __int128)gl_sub(b, a) * pow2(60)) % GL_P);
     }
     if (mism) atomicAdd(bad, mism);
 }
@@ -119,12 +132,6 @@ void device_tables_init(int device) {
         W14[0] = 1;
         for (size_t i = 1; i < full; ++i) W14[i] = gl_mul(W14[i - 1], w);
         ZKB_CUDA_CHECK(cudaMemcpyToSymbol(d_W14, W14.data(), full * 8));
-        u64 w16[16];
-        for (int k = 0; k < 8; ++k) {
-            w16[k] = W14[(size_t)k << (NTT_SM_LG - 4)];
-            w16[8 + k] = W14[(full - ((size_t)k << (NTT_SM_LG - 4))) & (full - 1)];
-        }
-        ZKB_CUDA_CHECK(cudaMemcpyToSymbol(c_w16, w16, sizeof(w16)));
     }
     ntt_set_func_attributes();
     field_selfcheck();
@@ -704,6 +711,8 @@ struct PPArgs {
 };
 
 constexpr int PP_MAX_CHUNKS = 16;
+// one copy of the 84-multiplication inversion chain instead of one per unrolled chunk slot (the kernel was 310 KB of code)
+__device__ __noinline__ u64 gl_inv_call(u64 a) { return gl_inv(a); }
 __global__ void __launch_bounds__(128) pp_chunk_kernel(PPArgs a) {
     size_t n = size_t(1) << a.lg_n;
     size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
@@ -720,11 +729,12 @@ __global__ void __launch_bounds__(128) pp_chunk_kernel(PPArgs a) {
         if (k < a.nchunks) {
             u64 nu = 1, de = 1;
             int j1 = min(a.num_routed, (k + 1) * a.chunk);
+#pragma unroll 1
             for (int j = k * a.chunk; j < j1; ++j) {
                 u64 w = a.wires[(size_t)j * a.wire_stride + i];
-                u64 wg = gl_add(w, gamma);
-                nu = gl_mul(nu, gl_add(wg, gl_mul(bx, a.k_is[j])));
-                de = gl_mul(de, gl_add(wg, gl_mul(beta, a.sigmas[(size_t)j * a.sigma_stride + i])));
+                u64 wg = f_add(w, gamma);
+                nu = f_mul(nu, f_add(wg, f_mul(bx, a.k_is[j])));
+                de = f_mul(de, f_add(wg, f_mul(beta, a.sigmas[(size_t)j * a.sigma_stride + i])));
             }
             num[k] = nu; den[k] = de;
             pre[k] = run;                       // product of den[0..k)
@@ -732,14 +742,14 @@ __global__ void __launch_bounds__(128) pp_chunk_kernel(PPArgs a) {
         }
     }
     const bool degenerate = run == 0;            // some denominator is zero: keep the per-chunk definition (inv(0) = 0)
-    u64 inv_run = gl_inv(run);
+    u64 inv_run = gl_inv_call(run);
     u64 tot = 1;
     u64 q[PP_MAX_CHUNKS];
 #pragma unroll
     for (int k = PP_MAX_CHUNKS - 1; k >= 0; --k) {
         q[k] = 1;
         if (k < a.nchunks) {
-            u64 inv_k = degenerate ? gl_inv(den[k]) : gl_mul(inv_run, pre[k]);
+            u64 inv_k = degenerate ? gl_inv_call(den[k]) : gl_mul(inv_run, pre[k]);
             inv_run = gl_mul(inv_run, den[k]);
             q[k] = gl_mul(num[k], inv_k);
         }
@@ -923,6 +933,7 @@ __global__ void __launch_bounds__(128, PART == 3 ? 4 : 8) quotient_kernel(Quotie
         const u64 b0 = P.betas[0], b1 = P.betas[1], gm0 = P.gammas[0], gm1 = P.gammas[1];
         const u64 bx0 = f_mul(b0, x), bx1 = f_mul(b1, x);
         u64 prev0 = z[0], prev1 = z[a.z_stride];
+#pragma unroll 1
         for (int k = 0; k < nchunks; ++k) {
             const u64 next0 = k < npp ? z[(size_t)(nch + k) * a.z_stride] : a.z[l_next];
             const u64 next1 = k < npp ? z[(size_t)(nch + npp + k) * a.z_stride] : a.z[a.z_stride + l_next];
@@ -950,10 +961,12 @@ __global__ void __launch_bounds__(128, PART == 3 ? 4 : 8) quotient_kernel(Quotie
         u64 beta = P.betas[ch], gamma = P.gammas[ch];
         u64 bx = f_mul(beta, x);
         u64 prev = z[(size_t)ch * a.z_stride];
+#pragma unroll 1
         for (int k = 0; k < nchunks; ++k) {
             u64 next = k < npp ? z[(size_t)(nch + ch * npp + k) * a.z_stride] : a.z[(size_t)ch * a.z_stride + l_next];
             u64 num = 1, den = 1;
             int j1 = min(P.num_routed, (k + 1) * chunk);
+#pragma unroll 1
             for (int j = k * chunk; j < j1; ++j) {
                 u64 wg = f_add(w[(size_t)j * a.w_stride], gamma);
                 num = f_mul(num, f_add(wg, f_mul(bx, P.k_is[j])));
@@ -975,6 +988,7 @@ __global__ void __launch_bounds__(128, PART == 3 ? 4 : 8) quotient_kernel(Quotie
         if (nsl > 1 && (PART == 1 ? slice != nsl - 1 : (ordinal++ % nsl) != slice)) continue;
         u64 s = cs[(size_t)gd.selector_index * a.cs_stride];
         u64 filter = 1;
+#pragma unroll 1
         for (u32 r = gd.group_lo; r < gd.group_hi; ++r)
             if (r != gd.row) filter = f_mul(filter, f_sub((u64)r, s));
         if (nsel > 1) filter = f_mul(filter, f_sub(0xFFFFFFFFULL, s));
@@ -991,6 +1005,7 @@ __global__ void __launch_bounds__(128, PART == 3 ? 4 : 8) quotient_kernel(Quotie
             case TAG_NOOP: break;
             case TAG_CONSTANT:
                 if (PART != 1) break;      // PART is a template constant: the other launches' cases compile to nothing
+#pragma unroll 1
                 for (u32 j = 0; j < gd.param; ++j) add_c(f_sub(K(j), W(j)));
                 break;
             case TAG_PUBLIC_INPUT:
@@ -1000,14 +1015,17 @@ __global__ void __launch_bounds__(128, PART == 3 ? 4 : 8) quotient_kernel(Quotie
             case TAG_BASE_SUM: {
                 if (PART != 1) break;
                 u64 sum = 0;
+#pragma unroll 4
                 for (int j = (int)gd.param; j-- > 0;) sum = f_add(f_add(sum, sum), W(1 + j));
                 add_c(f_sub(sum, W(0)));
+#pragma unroll 1
                 for (u32 j = 0; j < gd.param; ++j) { u64 b = W(1 + j); add_c(f_mul(b, f_sub(b, 1))); }
                 break;
             }
             case TAG_ARITHMETIC: {
                 if (PART != 1) break;
                 u64 c0 = K(0), c1 = K(1);
+#pragma unroll 1
                 for (u32 j = 0; j < gd.param; ++j) {
                     u64 prod = f_mul(f_mul(W(4 * j), W(4 * j + 1)), c0);
                     add_c(f_sub(W(4 * j + 3), f_add(prod, f_mul(W(4 * j + 2), c1))));

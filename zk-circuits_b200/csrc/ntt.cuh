@@ -1,8 +1,9 @@
 // Shared-memory NTT for transform sizes up to 2^14 (one column = one CTA), the size class of the wormhole / voting
 // circuits: replaces qp-plonky2-field's `ifft` / `coset_fft` / `lde` on the device.
 //
-//  * radix-16 decimation-in-frequency passes: a thread loads 16 elements (stride 2^(s-4)) into registers, runs four
-//    butterfly stages there (internal twiddles are the constants w_16^k) and multiplies by the pass twiddle
+//  * radix-8 / radix-16 decimation-in-frequency passes: a thread loads 8 / 16 elements (stride 2^(s-K)) into registers, runs
+//    the butterfly stages there — the internal twiddles w_16^k are powers of two (w_16 = 2^12), applied as shift forms
+//    (field.cuh f_shl), no 64x64 multiply — and multiplies by the pass twiddle
 //    w_{2^s}^(b * bitrev4(p)) from one table of w_{2^14}^t — 4 block-wide barriers and 4 shared-memory round trips for
 //    14 stages instead of 14;
 //  * natural order in, bit-reversed order out, which IS the Merkle leaf order of PolynomialBatch, so the LDE is written
@@ -17,7 +18,6 @@ namespace zkb {
 
 constexpr unsigned NTT_SM_LG = 14;                       // largest transform held in shared memory
 __device__ u64 d_W14[1u << NTT_SM_LG];                   // w_{2^14}^t, 0 <= t < 2^14
-__constant__ u64 c_w16[16];                              // w_16^k, k < 8, then w_16^-k, k < 8
 
 ZKB_D unsigned ntt_pad(unsigned i) { return i + (i >> 4); }          // one spare word per 16: keeps small-stride passes off one bank
 inline size_t ntt_smem_bytes(unsigned lg) { return sizeof(u64) * ((size_t(1) << lg) + (size_t(1) << lg) / 16 + 1); }

@@ -1113,6 +1113,7 @@ __global__ void __launch_bounds__(128, PART == 3 ? 4 : 8) quotient_kernel(Quotie
                 const bool addend = gd.tag == TAG_ARITHMETIC_EXT;
                 const int per = addend ? 8 : 6;
                 const u64 c0 = K(0), c1 = addend ? K(1) : 0;
+#pragma unroll 1
                 for (u32 j = 0; j < gd.param; ++j) {
                     const int b = per * (int)j;
                     QE t = qe_scale(qe_mul(QE{W(b), W(b + 1)}, QE{W(b + 2), W(b + 3)}), c0);
@@ -1129,6 +1130,7 @@ __global__ void __launch_bounds__(128, PART == 3 ? 4 : 8) quotient_kernel(Quotie
                 const int nc = (int)gd.param, start_accs = 6 + (ext ? 2 * nc : nc);
                 const QE alpha{W(2), W(3)};
                 QE acc{W(4), W(5)};
+#pragma unroll 1
                 for (int j = 0; j < nc; ++j) {
                     QE t = qe_mul(acc, alpha);
                     if (ext) t = qe_add(t, QE{W(6 + 2 * j), W(7 + 2 * j)});
@@ -1144,6 +1146,7 @@ __global__ void __launch_bounds__(128, PART == 3 ? 4 : 8) quotient_kernel(Quotie
                 if (PART != 3) break;
                 const int bits = (int)gd.param, vec = 1 << bits, copies = (int)gd.p2, extra = (int)gd.p3;
                 const int routed = (2 + vec) * copies + extra;
+#pragma unroll 1
                 for (int cpy = 0; cpy < copies; ++cpy) {
                     const int base = (2 + vec) * cpy, wb = routed + cpy * bits;
                     u64 idx = 0;
@@ -1153,6 +1156,7 @@ __global__ void __launch_bounds__(128, PART == 3 ? 4 : 8) quotient_kernel(Quotie
                     // fold the list pairwise, level j with bit j: x + b (y - x); streamed through a stack of one partial
                     // result per level so that the items are read once and never all live at once
                     u64 stack[6];
+#pragma unroll 1
                     for (int k = 0; k < vec; k += 2) {
                         u64 x = W(base + 2 + k), y = W(base + 3 + k);
                         u64 v = f_add(x, f_mul(W(wb), f_sub(y, x)));
@@ -1170,6 +1174,7 @@ __global__ void __launch_bounds__(128, PART == 3 ? 4 : 8) quotient_kernel(Quotie
                 const int nb = (int)gd.param;
                 const u64 bm1 = f_sub(W(0), 1);
                 u64 prev = 1;
+#pragma unroll 1
                 for (int j = 0; j < nb; ++j) {
                     const u64 factor = f_add(f_mul(W(nb - j), bm1), 1);      // bit * base + (1 - bit)
                     const u64 cur = W(nb + 2 + j);
@@ -1190,7 +1195,9 @@ __global__ void __launch_bounds__(128, PART == 3 ? 4 : 8) quotient_kernel(Quotie
                 }
                 QE eval{0, 0}, prod{1, 0};
                 int lo = 0, hi = deg;
+#pragma unroll 1
                 for (int seg = 0; seg <= ni; ++seg) {
+#pragma unroll 1
                     for (int k = lo; k < hi; ++k) {      // eval <- eval (z - x_k) + w_k v_k prod;  prod <- prod (z - x_k)
                         const QE term{f_sub(shifted.a, P.bary_x[k]), shifted.b};
                         const QE wv = qe_scale(QE{W(1 + 2 * k), W(2 + 2 * k)}, P.bary_w[k]);
@@ -1214,16 +1221,21 @@ __global__ void __launch_bounds__(128, PART == 3 ? 4 : 8) quotient_kernel(Quotie
             }
             case TAG_POSEIDON_MDS: {       // 12 F_{p^2} inputs at 2 i, outputs at 24 + 2 i: the MDS matrix acts on each component
                 if (PART != 3) break;
-                u64 sa[12], sb[12];
+                // one component at a time (12 live words instead of 24); constraint 2 j + comp gets alpha^(k + 2 j + comp)
+#pragma unroll 1
+                for (int comp = 0; comp < 2; ++comp) {
+                    u64 sv[12];
 #pragma unroll
-                for (int j = 0; j < 12; ++j) { sa[j] = W(2 * j); sb[j] = W(2 * j + 1); }
-                mds_layer(sa);
-                mds_layer(sb);
+                    for (int j = 0; j < 12; ++j) sv[j] = W(2 * j + comp);
+                    mds_layer(sv);
 #pragma unroll
-                for (int j = 0; j < 12; ++j) {
-                    add_c(f_sub(W(24 + 2 * j), f_canon(sa[j])));
-                    add_c(f_sub(W(25 + 2 * j), f_canon(sb[j])));
+                    for (int j = 0; j < 12; ++j) {
+                        const u64 c = f_sub(W(24 + 2 * j + comp), f_canon(sv[j]));
+                        const ulonglong2 g = q_acc2(make_ulonglong2(g0, g1), c, apow0[k + 2 * j + comp], nch > 1 ? apow1[k + 2 * j + comp] : 0);
+                        g0 = g.x; g1 = g.y;
+                    }
                 }
+                k += 24;
                 break;
             }
             default: break;   // rejected on the host (ZKB_E_UNSUPPORTED_GATE)

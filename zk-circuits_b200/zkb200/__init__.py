@@ -17,7 +17,7 @@ import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _ROOT = os.path.dirname(_HERE)
-LIB_PATH = os.path.join(_ROOT, "libzkb200.so")
+LIB_PATH = os.environ.get("ZKB200_LIB") or os.path.join(_ROOT, "libzkb200.so")      # ZKB200_LIB: a variant build (lab experiments)
 
 u64p = ctypes.POINTER(ctypes.c_uint64)
 u8p = ctypes.POINTER(ctypes.c_uint8)

@@ -250,10 +250,12 @@ std::vector<typename Ops::T> eval_vanishing(const CommonData& c, typename Ops::T
                                             const u64* alphas) {
     using T = typename Ops::T;
     size_t nch = c.num_challenges, npp = c.num_partial_products, chunk = c.quotient_degree_factor;
-    std::vector<T> z1_terms, pp_terms;
+    // scratch reused across calls (the prover calls this once per LDE point from every OpenMP thread)
+    static thread_local std::vector<T> z1_terms, pp_terms, accs, constraints, gc, terms;
+    z1_terms.clear(); pp_terms.clear();
     for (size_t ch = 0; ch < nch; ++ch) {
         z1_terms.push_back(Ops::mul(l0_x, Ops::sub(zs[ch], Ops::one())));
-        std::vector<T> accs;
+        accs.clear();
         accs.push_back(zs[ch]);
         for (size_t k = 0; k < npp; ++k) accs.push_back(pps[ch * npp + k]);
         accs.push_back(zs_next[ch]);
@@ -270,8 +272,7 @@ std::vector<typename Ops::T> eval_vanishing(const CommonData& c, typename Ops::T
             pp_terms.push_back(Ops::sub(Ops::mul(accs[k], num), Ops::mul(accs[k + 1], den)));
         }
     }
-    std::vector<T> constraints(c.num_gate_constraints, Ops::zero());
-    std::vector<T> gc;
+    constraints.assign(c.num_gate_constraints, Ops::zero());
     size_t nsel = c.num_selectors();
     for (size_t gi = 0; gi < c.gates.size(); ++gi) {
         u64 sel = c.selector_indices[gi];
@@ -279,7 +280,7 @@ std::vector<typename Ops::T> eval_vanishing(const CommonData& c, typename Ops::T
         eval_gate_unfiltered<Ops>(c.gates[gi], constants + nsel, wires, pi_hash, gc);
         for (size_t k = 0; k < gc.size(); ++k) constraints[k] = Ops::add(constraints[k], Ops::mul(filter, gc[k]));
     }
-    std::vector<T> terms;
+    terms.clear();
     terms.insert(terms.end(), z1_terms.begin(), z1_terms.end());
     terms.insert(terms.end(), pp_terms.begin(), pp_terms.end());
     terms.insert(terms.end(), constraints.begin(), constraints.end());

@@ -27,24 +27,24 @@ constexpr u64 GEN = 0xc65c18b67785d900ULL; // multiplicative generator g = coset
 constexpr u64 TWO_ADIC_ROOT = 0x64fdd1a46201e246ULL; // order 2^32 (A.1): g^((p-1)/2^32)
 constexpr u64 EXT_W = 7;                   // F_{p^2} = F_p[X]/(X^2 - 7)
 
+// (written with conditional expressions rather than branches: the conditions are data-dependent coin flips, and a mispredicted
+// branch costs more than the whole reduction)
 inline u64 fadd(u64 a, u64 b) {
     u64 s = a + b;
-    if (s < a || s >= P) s -= P;
-    return s;
+    return s - (((s < a) | (s >= P)) ? P : 0);
 }
-inline u64 fsub(u64 a, u64 b) { return a >= b ? a - b : a - b + P; }
+inline u64 fsub(u64 a, u64 b) { return a - b + ((a < b) ? P : 0); }
 inline u64 fneg(u64 a) { return a ? P - a : 0; }
 inline u64 reduce128(u128 x) {
     u64 lo = (u64)x, hi = (u64)(x >> 64);
     u64 hi_hi = hi >> 32, hi_lo = hi & EPS;
     // x = lo + hi_lo*2^64 + hi_hi*2^96,  2^64 = 2^32-1,  2^96 = -1  (mod P)
     u64 t0 = lo - hi_hi;
-    if (lo < hi_hi) t0 -= EPS;            // borrow: subtracting 2^64 is subtracting EPS
-    u64 t1 = hi_lo * EPS;                 // < 2^64, no overflow
+    t0 -= (lo < hi_hi) ? EPS : 0;          // borrow: subtracting 2^64 is subtracting EPS
+    u64 t1 = hi_lo * EPS;                  // < 2^64, no overflow
     u64 r = t0 + t1;
-    if (r < t0) r += EPS;                 // carry: adding 2^64 is adding EPS (cannot carry twice)
-    if (r >= P) r -= P;
-    return r;
+    r += (r < t0) ? EPS : 0;               // carry: adding 2^64 is adding EPS (cannot carry twice)
+    return r - ((r >= P) ? P : 0);
 }
 inline u64 fmul(u64 a, u64 b) { return reduce128((u128)a * b); }
 inline u64 fsqr(u64 a) { return fmul(a, a); }

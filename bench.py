@@ -25,7 +25,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, os.path.join(ROOT, "zk-circuits_b200"))
 
 WORKLOAD = "wormhole_zk_synth_n2^14"
-NCU_LDE_TRAFFIC_BYTES = 18886912 + 82320640   # dram__bytes_read.sum + dram__bytes_write.sum, one lde_block_kernel_t<3, 1024> launch
+NCU_LDE_TRAFFIC_BYTES = 19055104 + 83806720   # dram__bytes_read.sum + dram__bytes_write.sum, one lde_block_kernel_t<3, 1024, 14> launch (profiles/r02_ncu_lde_block_v2.md)
 METRIC = "wormhole_proofs_per_sec"
 UNIT = "proofs/s"
 
@@ -497,19 +497,22 @@ def main():
         "e2e": {"value": world * K * B / t_e2e, "unit": UNIT, "ms_per_step": 1000 * t_e2e / K,
                 "h2d_bytes_per_step": int(B * (nw * n * 8 + pis.size * 8)), "d2h_bytes_per_step": int(B * len(proof))},
         "gpu_launches": int(launches) * B,
-        "roofline": {"kernel": "lde_block_kernel_t<3, 1024>: coset pre-scale + 8 x NTT of the 135 wire columns, n = 2^14 (one launch)",
+        "roofline": {"kernel": "lde_block_kernel_t<3, 1024, 14>: coset pre-scale + 8 x NTT of the 135 wire columns, n = 2^14 (one launch)",
                      "bound": "hbm", "achieved": lde_gbs, "peak": peak, "unit": "GB/s", "frac": lde_gbs / peak,
                      "traffic": NCU_LDE_TRAFFIC_BYTES,
-                     "note": "integer-issue bound in practice (47 instr/byte vs 5.7 the chip can issue per HBM byte; DESIGN.md 4.2); "
-                             "traffic = dram read + write of one launch from profiles/r01_ncu_lde_block_v3.md (output partly still in L2)",
+                     "note": "integer-issue bound in practice (322 thread instructions per element and transform = 36 per algorithmic byte vs "
+                             "5.7 the chip can issue per HBM byte; operation-count floor ~32: DESIGN.md 4.2); traffic = dram read + write of one "
+                             "launch from profiles/r02_ncu_lde_block_v2.md (output partly still in L2)",
                      "from_values_gbs": 80 * n * nw / ((stages["wires_intt"] + lde_ms) * 1e-3) / 1e9,
                      "peak_source": peak_src, "algorithmic_bytes_per_launch": lde_bytes, "avg_ms": lde_ms},
-        "poseidon": {"kernel": "wires Merkle commit (merkle_subtree_kernel + merkle_cap_subtree_kernel: 2 launches)", "perms_per_launch": perms,
+        "poseidon": {"kernel": "wires Merkle commit (merkle_leaves_kernel + 7 level launches + merkle_cap_subtree_kernel, levels replayed as a CUDA graph)", "perms_per_launch": perms,
                      "avg_ms": pos_ms, "perms_per_sec": perms / (pos_ms * 1e-3), "bound": "integer pipes (fmaheavy/IMAD + alu)",
                      "imad_peak_per_s": 148 * 64 * 1.965e9,
                      "frac_of_imad_peak_algorithmic": perms / (pos_ms * 1e-3) * 6600 / (148 * 64 * 1.965e9),
-                     "note": "6.6 k IMAD issue slots per permutation (SURVEY 8d); ncu: fmaheavy pipe 81 % of cycles active "
-                             "(profiles/r01_ncu_merkle_leaves_v1.md)"},
+                     "ncu_fmaheavy_pipe_cycles_active_pct": 75.2, "ncu_alu_pipe_pct": 68.3, "ncu_issue_slots_busy_pct": 69.3,
+                     "ncu_thread_instructions_per_permutation": 23673,
+                     "note": "6.6 k IMAD issue slots per permutation (SURVEY 8d) is the ALGORITHMIC fraction; the ncu figures are the leaf "
+                             "kernel's measured pipe utilisation (profiles/r02_ncu_merkle_leaves.md): both integer pipes ~70 % busy"},
         "clocks": clk.summary(),
     }
     # the DOMINANT kernel of a proof is the Poseidon tree hashing (integer-pipe bound); the contract's `roofline` object

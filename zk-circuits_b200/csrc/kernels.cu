@@ -521,7 +521,13 @@ static LargePlan large_plan(unsigned lg_n) {
 static void ntt_set_func_attributes() {   // per device: opt in to > 48 KB dynamic shared memory
     ZKB_CUDA_CHECK(cudaFuncSetAttribute(lde_block_kernel_t<4, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ntt_smem_bytes(NTT_SM_LG)));
     ZKB_CUDA_CHECK(cudaFuncSetAttribute(lde_block_kernel_t<3, 1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ntt_smem_bytes(NTT_SM_LG)));
+    ZKB_CUDA_CHECK(cudaFuncSetAttribute(lde_block_kernel_t<3, 1024, 14>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ntt_smem_bytes(14)));
+    ZKB_CUDA_CHECK(cudaFuncSetAttribute(lde_block_kernel_t<3, 1024, 13>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ntt_smem_bytes(13)));
+    ZKB_CUDA_CHECK(cudaFuncSetAttribute(lde_block_kernel_t<3, 512, 12>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ntt_smem_bytes(12)));
     ZKB_CUDA_CHECK(cudaFuncSetAttribute(intt_block_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ntt_smem_bytes(NTT_SM_LG)));
+    ZKB_CUDA_CHECK(cudaFuncSetAttribute(intt_block_kernel_c<14, 1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ntt_smem_bytes(14)));
+    ZKB_CUDA_CHECK(cudaFuncSetAttribute(intt_block_kernel_c<13, 1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ntt_smem_bytes(13)));
+    ZKB_CUDA_CHECK(cudaFuncSetAttribute(intt_block_kernel_c<12, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ntt_smem_bytes(12)));
     ZKB_CUDA_CHECK(cudaFuncSetAttribute(ntt_cols_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ntt_smem_bytes(NTT_SM_LG)));
 }
 static unsigned ntt_block_threads(unsigned lg_n) {
@@ -535,10 +541,24 @@ static bool ntt_radix8() {
     static const bool on = [] { const char* e = std::getenv("ZKB_NTT_RADIX8"); return !(e && e[0] == '0'); }();
     return on;
 }
+static bool ntt_specialised() {
+    static const bool on = [] { const char* e = std::getenv("ZKB_NTT_GENERIC"); return !(e && e[0] == '1'); }();
+    return on;
+}
 static void launch_lde_block(dim3 grid, unsigned lg_n, cudaStream_t st, const u64* coeffs, size_t coeff_stride, u64* out,
                              size_t out_stride, const u64* prescale, size_t src_block_stride, int inv, unsigned jb0) {
     ZKB_COUNT_LAUNCH();
-    if (lg_n >= 13 && ntt_radix8())
+    const bool specialised = ntt_specialised();
+    if (specialised && !inv && ntt_radix8() && lg_n == 14)
+        lde_block_kernel_t<3, 1024, 14><<<grid, 1024, ntt_smem_bytes(14), st>>>(coeffs, coeff_stride, out, out_stride, lg_n, prescale,
+                                                                               src_block_stride, inv, jb0);
+    else if (specialised && !inv && ntt_radix8() && lg_n == 13)
+        lde_block_kernel_t<3, 1024, 13><<<grid, 1024, ntt_smem_bytes(13), st>>>(coeffs, coeff_stride, out, out_stride, lg_n, prescale,
+                                                                               src_block_stride, inv, jb0);
+    else if (specialised && !inv && ntt_radix8() && lg_n == 12)
+        lde_block_kernel_t<3, 512, 12><<<grid, 512, ntt_smem_bytes(12), st>>>(coeffs, coeff_stride, out, out_stride, lg_n, prescale,
+                                                                             src_block_stride, inv, jb0);
+    else if (lg_n >= 13 && ntt_radix8())
         lde_block_kernel_t<3, 1024><<<grid, 1024, ntt_smem_bytes(lg_n), st>>>(coeffs, coeff_stride, out, out_stride, lg_n, prescale,
                                                                              src_block_stride, inv, jb0);
     else
@@ -620,14 +640,26 @@ void launch_bitrev_permute(u64* data, size_t stride, int ncols, unsigned lg_n, c
     run_bitrev_scale(data, stride, ncols, lg_n, 1, st);
 }
 
+// one column per CTA: values -> coefficients (times scale), specialised for the circuit sizes
+static void launch_intt_block(const u64* in, size_t in_stride, u64* out, size_t out_stride, int ncols, unsigned lg_n, int in_bitrev,
+                              u64 scale, cudaStream_t st) {
+    ZKB_COUNT_LAUNCH();
+    if (ntt_specialised() && lg_n == 14)
+        intt_block_kernel_c<14, 1024><<<(unsigned)ncols, 1024, ntt_smem_bytes(14), st>>>(in, in_stride, out, out_stride, in_bitrev, scale);
+    else if (ntt_specialised() && lg_n == 13)
+        intt_block_kernel_c<13, 1024><<<(unsigned)ncols, 1024, ntt_smem_bytes(13), st>>>(in, in_stride, out, out_stride, in_bitrev, scale);
+    else if (ntt_specialised() && lg_n == 12)
+        intt_block_kernel_c<12, 512><<<(unsigned)ncols, 512, ntt_smem_bytes(12), st>>>(in, in_stride, out, out_stride, in_bitrev, scale);
+    else
+        intt_block_kernel<<<(unsigned)ncols, ntt_block_threads(lg_n), ntt_smem_bytes(lg_n), st>>>(in, in_stride, out, out_stride, lg_n, in_bitrev, scale);
+}
 void launch_intt_natural(const u64* src, size_t src_stride, u64* dst, size_t dst_stride, int ncols, unsigned lg_n,
                          u64* scratch, cudaStream_t st) {
     (void)scratch;
     if (ncols <= 0) return;
     u64 ninv = gl_inv(u64(1) << lg_n);
     if (lg_n <= NTT_SM_LG) {
-        ZKB_COUNT_LAUNCH();
-        intt_block_kernel<<<(unsigned)ncols, ntt_block_threads(lg_n), ntt_smem_bytes(lg_n), st>>>(src, src_stride, dst, dst_stride, lg_n, 0, ninv);
+        launch_intt_block(src, src_stride, dst, dst_stride, ncols, lg_n, 0, ninv, st);
         return;
     }
     run_large_transform(src, src_stride, dst, dst_stride, ncols, lg_n, 1, nullptr, nullptr, true, st);   // bit-reversed result
@@ -682,8 +714,7 @@ void launch_coset_intt_bitrev(u64* data, size_t stride, int ncols, unsigned lg_m
     if (ncols <= 0) return;
     size_t m = size_t(1) << lg_m;
     if (lg_m <= NTT_SM_LG) {
-        ZKB_COUNT_LAUNCH();
-        intt_block_kernel<<<(unsigned)ncols, ntt_block_threads(lg_m), ntt_smem_bytes(lg_m), st>>>(data, stride, data, stride, lg_m, 1, 1);
+        launch_intt_block(data, stride, data, stride, ncols, lg_m, 1, 1, st);
     } else {
         run_bitrev_scale(data, stride, ncols, lg_m, 1, st);                                             // leaf order -> natural
         run_large_transform(data, stride, data, stride, ncols, lg_m, 1, nullptr, nullptr, true, st);   // -> bit-reversed coefficients

@@ -91,33 +91,88 @@ ZKB_D void ntt_dif_smem(u64* sm, unsigned L, unsigned lgC = 0, bool inv = false)
     if (rem) __syncthreads();
 }
 
+// ---- the same passes with EVERYTHING known at compile time (transform size L, pass position S, block size): all shared-memory
+// offsets become immediates (pad(base + e M) = pad(base) + e M + (e M >> 4): the low four bits never carry, see the table in
+// DESIGN.md §4.2), the twiddle-index arithmetic folds, the tile loops unroll, and the passes with stride < 16 remap lanes to
+// tiles so that a half-warp's 16 eight-byte accesses fall into 16 different bank pairs (the generic pass had 2-way conflicts
+// at stride 4: 15 % of the kernel's shared-memory wavefronts). Forward transforms of the sizes the circuits use (2^12 - 2^14).
+template <int K, int S, int L, int THREADS>
+ZKB_D void ntt_pass_c(u64* sm) {
+    constexpr int R = 1 << K, lgM = S - K, M = 1 << lgM, NT = 1 << (L - K);
+    constexpr unsigned tmask = (1u << NTT_SM_LG) - 1;
+#pragma unroll
+    for (int it = 0; it < (NT + THREADS - 1) / THREADS; ++it) {
+        unsigned t = threadIdx.x + it * THREADS;
+        if ((NT % THREADS) != 0 && t >= (unsigned)NT) break;
+        if (M == 4) {            // half-warp: 8 groups x 2 residues -> bank pairs 2 g + b all different
+            const unsigned l = t & 15, half = (t >> 4) & 1;
+            t = (t & ~31u) + ((l >> 1) << 2) + (l & 1) + 2 * half;
+        } else if (M == 2) {     // half-warp: 16 groups, one residue
+            const unsigned l = t & 15, half = (t >> 4) & 1;
+            t = (t & ~31u) + (l << 1) + half;
+        }
+        const unsigned b = t & (M - 1), base = ((t >> lgM) << S) + b, pbase = base + (base >> 4);
+        u64 tw[R];
+        if (lgM > 0) {
+#pragma unroll
+            for (int p = 1; p < R; ++p) {
+                constexpr int dummy = 0; (void)dummy;
+                const unsigned q = __brev((unsigned)p) >> (32 - K);
+                tw[p] = __ldg(&d_W14[((b * q) << (NTT_SM_LG - S)) & tmask]);
+            }
+        }
+        u64 r[R];
+#pragma unroll
+        for (int e = 0; e < R; ++e) r[e] = sm[pbase + e * M + ((e * M) >> 4)];
+        radix_dif<K>(r, false);
+        if (lgM > 0) {
+#pragma unroll
+            for (int p = 1; p < R; ++p) r[p] = f_mul(r[p], tw[p]);
+        }
+#pragma unroll
+        for (int p = 0; p < R; ++p) sm[pbase + p * M + ((p * M) >> 4)] = r[p];
+    }
+}
+template <int L, int S, int THREADS>
+ZKB_D void ntt_dif_smem_c_from(u64* sm) {       // radix-8 passes from position S down, then the radix-4 / radix-2 remainder
+    if constexpr (S >= 3) {
+        ntt_pass_c<3, S, L, THREADS>(sm);
+        __syncthreads();
+        ntt_dif_smem_c_from<L, S - 3, THREADS>(sm);
+    } else if constexpr (S > 0) {
+        ntt_pass_c<S, S, L, THREADS>(sm);
+        __syncthreads();
+    }
+}
+
 // coset LDE of one column block: out[jb * n + i] = sum_k coeff[k] (shift w_N^j)^k w_n^(k bitrev(i)),  j = bitrev_r(jb)
 // prescale: [2^rate_bits][n] table of (shift w_N^j)^k, or null for the plain transform (shift 1, rate 0)
 // src_block_stride = 0: every block jb transforms the same n coefficients (LDE); = n: block jb transforms its own
 // contiguous run (second step of the two-step transform for n > 2^14; coeffs may alias out). inv: inverse twiddles.
-template <int KMAX, int THREADS>
+template <int KMAX, int THREADS, int LGN = 0>      // LGN != 0: forward transform of exactly 2^LGN points, compile-time passes
 __global__ void __launch_bounds__(THREADS) lde_block_kernel_t(const u64* coeffs, size_t coeff_stride, u64* out,
                                                               size_t out_stride, unsigned lg_n, const u64* __restrict__ prescale,
                                                               size_t src_block_stride, int inv, unsigned jb0) {
     extern __shared__ u64 sm[];
-    const unsigned n = 1u << lg_n, jb = blockIdx.x;       // jb: destination block; jb0 + jb: coset (pre-scale table row)
+    const unsigned n = LGN ? (1u << LGN) : (1u << lg_n), jb = blockIdx.x;   // jb: destination block; jb0 + jb: coset (pre-scale table row)
     const u64* src = coeffs + (size_t)blockIdx.y * coeff_stride + (size_t)jb * src_block_stride;
     const u64* ps = prescale ? prescale + (size_t)(jb0 + jb) * n : nullptr;
     // n is a multiple of U * blockDim for the large sizes: U independent loads in flight per thread
     constexpr int U = KMAX == 4 ? 8 : 4;
-    if ((n & (U * blockDim.x - 1)) == 0) {
-        for (unsigned i0 = threadIdx.x; i0 < n; i0 += U * blockDim.x) {
+    if ((n & (U * THREADS - 1)) == 0 && blockDim.x == THREADS) {
+#pragma unroll
+        for (unsigned i0 = threadIdx.x; i0 < n; i0 += U * THREADS) {
             u64 v[U], w[U];
 #pragma unroll
-            for (int u = 0; u < U; ++u) v[u] = src[i0 + u * blockDim.x];
+            for (int u = 0; u < U; ++u) v[u] = src[i0 + u * THREADS];
             if (ps) {
 #pragma unroll
-                for (int u = 0; u < U; ++u) w[u] = __ldg(ps + i0 + u * blockDim.x);
+                for (int u = 0; u < U; ++u) w[u] = __ldg(ps + i0 + u * THREADS);
 #pragma unroll
                 for (int u = 0; u < U; ++u) v[u] = f_mul(v[u], w[u]);
             }
 #pragma unroll
-            for (int u = 0; u < U; ++u) sm[ntt_pad(i0 + u * blockDim.x)] = v[u];
+            for (int u = 0; u < U; ++u) sm[ntt_pad(i0 + u * THREADS)] = v[u];
         }
     } else {
         for (unsigned i = threadIdx.x; i < n; i += blockDim.x) {
@@ -127,7 +182,8 @@ __global__ void __launch_bounds__(THREADS) lde_block_kernel_t(const u64* coeffs,
         }
     }
     __syncthreads();
-    ntt_dif_smem<KMAX>(sm, lg_n, 0, inv != 0);
+    if constexpr (LGN != 0) ntt_dif_smem_c_from<LGN, LGN, THREADS>(sm);
+    else ntt_dif_smem<KMAX>(sm, lg_n, 0, inv != 0);
     u64* dst = out + (size_t)blockIdx.y * out_stride + (size_t)jb * n;
 #pragma unroll 8
     for (unsigned i = threadIdx.x; i < n; i += blockDim.x) dst[i] = sm[ntt_pad(i)];
@@ -175,6 +231,27 @@ __global__ void __launch_bounds__(256) ntt_cols_kernel(ColsNttArgs a) {
 
 // inverse transform of one column: values on <w_n> (natural order, or bit-reversed if in_bitrev) -> coefficients
 // (natural order), times `scale` (= 1/n). Uses the forward code: c_k = X[(n - k) mod n] / n.
+// the same with compile-time passes for the circuit sizes (radix-8, 1024 / 512 threads)
+template <int LGN, int THREADS>
+__global__ void __launch_bounds__(THREADS) intt_block_kernel_c(const u64* __restrict__ in, size_t in_stride, u64* __restrict__ out,
+                                                               size_t out_stride, int in_bitrev, u64 scale) {
+    extern __shared__ u64 sm[];
+    constexpr unsigned n = 1u << LGN;
+    const u64* src = in + (size_t)blockIdx.x * in_stride;
+#pragma unroll 4
+    for (unsigned i = threadIdx.x; i < n; i += THREADS) {
+        const unsigned pos = in_bitrev ? bitrev32(i, LGN) : i;
+        sm[ntt_pad(pos)] = src[i];
+    }
+    __syncthreads();
+    ntt_dif_smem_c_from<LGN, LGN, THREADS>(sm);
+    u64* dst = out + (size_t)blockIdx.x * out_stride;
+#pragma unroll 4
+    for (unsigned k = threadIdx.x; k < n; k += THREADS) {
+        const unsigned q = (n - k) & (n - 1);
+        dst[k] = f_mul(sm[ntt_pad(bitrev32(q, LGN))], scale);
+    }
+}
 __global__ void __launch_bounds__(512) intt_block_kernel(const u64* __restrict__ in, size_t in_stride, u64* __restrict__ out,
                                                          size_t out_stride, unsigned lg_n, int in_bitrev, u64 scale) {
     extern __shared__ u64 sm[];

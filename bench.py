@@ -198,6 +198,8 @@ def main():
                          "per proof in flight (round 1)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-sweep", action="store_true", help="skip the LDE/Merkle microbench points (config #3)")
+    ap.add_argument("--full-grid", action="store_true",
+                    help="config #3 as SURVEY 8d states it: n in 2^14..2^22 x cols in 100/135/200/400 (2^22 x 200/400 left out: > 120 GB)")
     ap.add_argument("--no-aggregation", action="store_true", help="skip the aggregation-tree measurement (config #4)")
     args = ap.parse_args()
 
@@ -522,7 +524,10 @@ def main():
     if not args.no_sweep:
         # config #3 points: fused from_values commit of synthetic columns, inputs resident in HBM
         sweep = []
-        for lg_n, cols in ((14, 135), (14, 200), (14, 400), (16, 135), (16, 200), (18, 100), (20, 100), (22, 100)):
+        grid = ((14, 135), (14, 200), (14, 400), (16, 135), (16, 200), (18, 100), (20, 100), (22, 100))
+        if args.full_grid:
+            grid = tuple((lg, c) for lg in (14, 16, 18, 20, 22) for c in (100, 135, 200, 400) if not (lg == 22 and c > 135))
+        for lg_n, cols in grid:
             nn = 1 << lg_n
             vals = synth_columns(np, lg_n, cols)
             cap, tm = Z.commit_batch(vals, 3, 4, reps=3, device=local_rank)

@@ -52,7 +52,7 @@ unsigned lg2(size_t x) { unsigned k = 0; while ((size_t(1) << k) < x) ++k; retur
 
 extern "C" {
 
-const char* zkb_version(void) { return "zkb200 0.1.0 (sm_100a)"; }
+const char* zkb_version(void) { return "zkb200 0.2.0 (sm_100a)"; }
 const char* zkb_last_error(void) { return g_last_error.c_str(); }
 unsigned long long zkb_kernel_launch_count(void) { return kernel_launch_count(); }
 int zkb_device_count(void) {

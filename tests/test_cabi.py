@@ -74,6 +74,27 @@ def test_no_cpu_fallback(zkb):
     with pytest.raises(zkb.ZkbError) as e:
         zkb.lde_batch(np.zeros((1, 8), dtype=np.uint64))
     assert e.value.status == "ZKB_E_CUDA"
+    # the round-2 entry points fail the same way: no engine, no communicator, no sharded commitment without a device
+    from conftest import golden_bytes
+
+    cs = np.zeros((84, 1 << 14), dtype=np.uint64)
+    with pytest.raises(zkb.ZkbError) as e:
+        zkb.Engine(golden_bytes("bench_common.bin"), cs, contexts=2)
+    assert e.value.status == "ZKB_E_CUDA"
+    with pytest.raises(zkb.ZkbError) as e:
+        zkb.Comm(np.zeros(128, dtype=np.uint8), 1, 0)
+    assert e.value.status == "ZKB_E_CUDA"
+
+
+def test_flag_values_match_header(zkb):
+    src = open(os.path.join(ROOT, "include", "zkb200.h")).read()
+    for name, val in (("ZKB_POW_MIN", zkb.POW_MIN), ("ZKB_SALTS_FROM_SEED", zkb.SALTS_FROM_SEED), ("ZKB_CHECK_WITNESS", zkb.CHECK_WITNESS),
+                      ("ZKB_WITNESS_RESIDENT", zkb.WITNESS_RESIDENT)):
+        m = re.search(r"#define " + name + r"\s+(0x[0-9a-fA-F]+|\d+)u", src)
+        assert m and int(m.group(1), 0) == val, name
+    rs = open(os.path.join(ROOT, "rust", "zkb200-sys", "src", "lib.rs")).read()
+    for name, val in (("ZKB_SALTS_FROM_SEED", 0x100), ("ZKB_CHECK_WITNESS", 0x200), ("ZKB_WITNESS_RESIDENT", 0x400)):
+        assert re.search(r"pub const " + name + r": u32 = " + hex(val) + ";", rs), name
 
 
 def test_rust_sys_crate_declares_every_header_symbol():

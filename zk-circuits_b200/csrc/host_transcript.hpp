@@ -49,7 +49,10 @@ inline void h_mds_half(u64* x) {
     }
     x[0] += 8 * x0;
 }
-inline void h_poseidon_permute(u64* s) {
+// host_poseidon_avx2.cpp (compiled with -mavx2, used when the CPU has it): the same permutation, ~2.5x faster
+void h_poseidon_permute_avx2(u64* s);
+const u64* host_round_constants_ptr();
+inline void h_poseidon_permute_scalar(u64* s) {
     const u64* rc = host_round_constants();
     for (int r = 0; r < 30; ++r) {
         u64 t[12];
@@ -75,6 +78,15 @@ inline void h_poseidon_permute(u64* s) {
     }
     for (int i = 0; i < 12; ++i) s[i] = gl_canon(s[i]);
 }
+#if defined(ZKB_HOST_AVX2)
+inline void h_poseidon_permute(u64* s) {
+    static const bool avx2 = __builtin_cpu_supports("avx2");
+    if (avx2) h_poseidon_permute_avx2(s);
+    else h_poseidon_permute_scalar(s);
+}
+#else
+inline void h_poseidon_permute(u64* s) { h_poseidon_permute_scalar(s); }
+#endif
 inline void h_hash_no_pad(const u64* v, size_t len, u64 out[4]) {
     u64 s[12] = {0};
     for (size_t off = 0; off < len; off += 8) {

@@ -12,6 +12,8 @@
 
 namespace zkb {
 
+const u64* host_round_constants_ptr() { return host_round_constants(); }
+
 void cuda_check(cudaError_t e, const char* what) {
     if (e != cudaSuccess) throw CudaError(std::string(what) + ": " + cudaGetErrorString(e));
 }

@@ -115,7 +115,9 @@ int zkb_prove_resident(zkb_circuit* c, const uint64_t* public_inputs, size_t n_p
  *     zkb_engine_submit(e, slot, public_inputs, n_pi, salts, salt_seed, flags, proof_out, cap);     returns at once
  *     zkb_engine_wait(e, slot, &len);         blocks until THAT proof is done; returns its status; frees the slot
  * Any number of caller threads may use one engine. public_inputs are copied at submit; salts (if not NULL) and proof_out
- * must stay valid until the wait returns. Argument errors are reported by submit, proving errors by wait. */
+ * must stay valid until the wait returns. Argument errors are reported by submit, proving errors by wait (a failed proof
+ * fails only its own slot; the context is reset and reused). The driver thread spins while proofs are in flight and sleeps
+ * otherwise. zkb_engine_destroy drains queued and running proofs first; call it only when no thread is inside acquire / wait. */
 typedef struct zkb_engine zkb_engine;
 int zkb_engine_create(const uint8_t* common_bin, size_t common_len, const uint64_t* const_sigma, int is_values,
                       const uint64_t circuit_digest[4], int device, int n_contexts, int n_slots, zkb_engine** out);

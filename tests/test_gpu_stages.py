@@ -56,7 +56,7 @@ def test_merkle_commit_matches_oracle(zkb, oracle, width, lg, cap_h):
 
 
 @pytest.mark.parametrize("lg_n,ncols,rate_bits", [(1, 3, 3), (2, 1, 3), (5, 7, 3), (8, 4, 0), (10, 5, 1), (12, 3, 3),
-                                                  (13, 2, 3), (14, 3, 3), (15, 2, 3), (16, 1, 2), (17, 2, 3), (18, 1, 1)])
+                                                  (13, 2, 3), (14, 3, 3), (15, 2, 3), (16, 1, 2), (17, 2, 3), (18, 1, 1), (19, 1, 3)])
 def test_lde_matches_oracle(zkb, oracle, lg_n, ncols, rate_bits):
     rng = np.random.default_rng(lg_n * 10 + ncols)
     vals = rand_felts(rng, (ncols, 1 << lg_n))

@@ -369,6 +369,22 @@ ZKB_D u64 f_sub_twiddle16(u64 a, u64 b) {
     if (!INV) return f_shl<12 * IDX>(f_sub(a, b));
     return f_shl<96 - 12 * IDX>(f_sub(b, a));
 }
+// the same for w_64 = 8 (w_64^IDX = 2^(3 IDX), IDX < 32): every twiddle inside a transform of up to 64 points is a shift
+template <int IDX, bool INV>
+ZKB_D u64 f_sub_twiddle64(u64 a, u64 b) {
+    static_assert(IDX > 0 && IDX < 32, "w_64 exponent");
+    if (!INV) return f_shl<3 * IDX>(f_sub(a, b));
+    return f_shl<96 - 3 * IDX>(f_sub(b, a));
+}
+// x * w_64^E for any compile-time E (mod 64): 2^(3 E mod 192), 2^96 = -1
+template <int E>
+ZKB_D u64 f_mul_w64(u64 x) {
+    constexpr int S = 3 * (((E % 64) + 64) % 64);
+    if constexpr (S == 0) return x;
+    else if constexpr (S < 96) return f_shl<S>(x);
+    else if constexpr (S == 96) return f_sub(0, x);
+    else return f_sub(0, f_shl<S - 96>(x));
+}
 #endif
 
 // ---- quadratic extension, canonical components ----

@@ -508,10 +508,23 @@ void launch_salt_fill_csprng(u64* out, size_t words, const u32 key[8], unsigned 
 // NTT family: host side. Kernels are in ntt.cuh. n <= 2^14: one shared-memory kernel per transform; larger n: two steps
 // (n = n1 * n2: n1-point transforms down TB-wide column tiles + twiddle, then contiguous n2-point transforms).
 // ---------------------------------------------------------------------------------------------
+// n <= 2^20: the first step runs in registers (ntt_cols_reg_kernel: n1 <= 64 points per thread, shift twiddles, one merged table
+// multiply), the second is the compile-time 2^14 block kernel. ZKB_NTT_COLS_GENERIC=1 (or n > 2^20) selects the shared-memory
+// first step.
+static bool large_in_registers(unsigned lg_n) {
+    static const bool on = [] { const char* e = std::getenv("ZKB_NTT_COLS_GENERIC"); return !(e && e[0] == '1'); }();
+    return on && lg_n <= NTT_SM_LG + 6;
+}
 struct LargePlan { unsigned lb, lg_n1, lg_tb; };
 static LargePlan large_plan(unsigned lg_n) {
     if (lg_n > NTT_SM_LG + 10) throw std::runtime_error("NTT size too large (max 2^24)");
     LargePlan p;
+    if (large_in_registers(lg_n)) {
+        p.lb = NTT_SM_LG;
+        p.lg_n1 = lg_n - NTT_SM_LG;
+        p.lg_tb = 0;
+        return p;
+    }
     p.lb = lg_n >= 20 ? (lg_n - 8 > NTT_SM_LG ? NTT_SM_LG : (lg_n - 8 < 12 ? 12 : lg_n - 8)) : 12;
     if (lg_n - p.lb > 10) p.lb = lg_n - 10;
     p.lg_n1 = lg_n - p.lb;
@@ -529,6 +542,8 @@ static void ntt_set_func_attributes() {   // per device: opt in to > 48 KB dynam
     ZKB_CUDA_CHECK(cudaFuncSetAttribute(intt_block_kernel_c<13, 1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ntt_smem_bytes(13)));
     ZKB_CUDA_CHECK(cudaFuncSetAttribute(intt_block_kernel_c<12, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ntt_smem_bytes(12)));
     ZKB_CUDA_CHECK(cudaFuncSetAttribute(ntt_cols_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ntt_smem_bytes(NTT_SM_LG)));
+    ZKB_CUDA_CHECK(cudaFuncSetAttribute(ntt_cols_staged_kernel<6, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(u64) * 128 * 64)));
+    ZKB_CUDA_CHECK(cudaFuncSetAttribute(ntt_cols_staged_kernel<6, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(u64) * 128 * 64)));
 }
 static unsigned ntt_block_threads(unsigned lg_n) {
     unsigned t = lg_n >= 4 ? (1u << (lg_n - 4)) : 1u;
@@ -567,7 +582,7 @@ static void launch_lde_block(dim3 grid, unsigned lg_n, cudaStream_t st, const u6
 }
 // Coset pre-scale tables (shift * w_N^j)^k, cached per device for the lifetime of the process. n <= 2^14: one table
 // [2^rate][n] (1 MB for the wormhole circuit). Larger n: the exponent is split k = r * n2 + b, tables [2^rate][n1], [2^rate][n2].
-struct CosetTables { u64* full = nullptr; u64* pre1 = nullptr; u64* pre2 = nullptr; };
+struct CosetTables { u64* full = nullptr; u64* pre1 = nullptr; u64* pre2 = nullptr; u64* tw = nullptr; };
 __global__ void coset_table2_kernel(u64* pre1, u64* pre2, unsigned lg_n1, unsigned lg_n2, unsigned rate_bits, u64 shift, u64 w_N) {
     const unsigned k = blockIdx.x * blockDim.x + threadIdx.x, jb = blockIdx.y;
     const u64 base = gl_mul(shift, gl_pow(w_N, bitrev32(jb, rate_bits)));
@@ -599,15 +614,67 @@ static CosetTables coset_tables(unsigned lg_n, unsigned rate_bits, u64 shift, cu
         dim3 grid((m + 127) / 128, 1u << rate_bits);
         ZKB_COUNT_LAUNCH();
         coset_table2_kernel<<<grid, 128, 0, st>>>(t.pre1, t.pre2, p.lg_n1, p.lb, rate_bits, shift, w_N);
+        if (large_in_registers(lg_n)) {        // merged s_j^b w_n^(b bitrev(p)) table: one LDE column's worth of memory per device
+            ZKB_CUDA_CHECK(cudaMalloc(&t.tw, (sizeof(u64) << lg_n) << rate_bits));
+            dim3 g((1u << p.lb) / 128, 1u << p.lg_n1, 1u << rate_bits);
+            ZKB_COUNT_LAUNCH();
+            cols_reg_table_kernel<<<g, 128, 0, st>>>(t.tw, p.lg_n1, p.lb, rate_bits, shift, w_N, gl_root_of_unity(lg_n), 1);
+        }
     }
     ZKB_CUDA_CHECK(cudaStreamSynchronize(st));       // other streams may use the tables as soon as they are in the cache
     cache[key] = t;
     return t;
 }
-// the two steps for n > 2^14; z = number of coset blocks written (block jb of dst at + jb * n)
-static void run_large_transform(const u64* src, size_t src_stride, u64* dst, size_t dst_stride, int ncols, unsigned lg_n,
-                                unsigned nblk, const u64* pre1, const u64* pre2, bool inv, cudaStream_t st, unsigned jb0 = 0) {
+// w_n^(+-b bitrev(p)) for the plain (no coset) in-register first step, cached per device
+static const u64* plain_cols_table(unsigned lg_n, bool inv, cudaStream_t st) {
+    static std::mutex mu;
+    static std::map<std::tuple<int, unsigned, bool>, u64*> cache;
+    int dev = 0;
+    ZKB_CUDA_CHECK(cudaGetDevice(&dev));
+    std::lock_guard<std::mutex> lk(mu);
+    auto key = std::make_tuple(dev, lg_n, inv);
+    auto it = cache.find(key);
+    if (it != cache.end()) return it->second;
     const LargePlan p = large_plan(lg_n);
+    u64* tw = nullptr;
+    ZKB_CUDA_CHECK(cudaMalloc(&tw, sizeof(u64) << lg_n));
+    u64 w = gl_root_of_unity(lg_n);
+    if (inv) w = gl_inv(w);
+    dim3 g((1u << p.lb) / 128, 1u << p.lg_n1, 1);
+    ZKB_COUNT_LAUNCH();
+    cols_reg_table_kernel<<<g, 128, 0, st>>>(tw, p.lg_n1, p.lb, 0, 1, 1, w, 0);
+    ZKB_CUDA_CHECK(cudaStreamSynchronize(st));
+    cache[key] = tw;
+    return tw;
+}
+template <bool INV>
+static void launch_cols_reg(dim3 grid, unsigned lg_n1, const ColsRegArgs& a, cudaStream_t st) {
+    ZKB_COUNT_LAUNCH();
+    switch (lg_n1) {
+        case 1: ntt_cols_reg_kernel<1, INV><<<grid, 128, 0, st>>>(a); break;
+        case 2: ntt_cols_reg_kernel<2, INV><<<grid, 128, 0, st>>>(a); break;
+        case 3: ntt_cols_reg_kernel<3, INV><<<grid, 128, 0, st>>>(a); break;
+        case 4: ntt_cols_reg_kernel<4, INV><<<grid, 128, 0, st>>>(a); break;
+        case 5: ntt_cols_staged_kernel<5, INV><<<grid, 128, sizeof(u64) * 128 * 32, st>>>(a); break;
+        default: ntt_cols_staged_kernel<6, INV><<<grid, 128, sizeof(u64) * 128 * 64, st>>>(a); break;
+    }
+}
+// the two steps for n > 2^14; z = number of coset blocks written (block jb of dst at + jb * n). tw: merged coset table of the
+// in-register first step (null: plain transform)
+static void run_large_transform(const u64* src, size_t src_stride, u64* dst, size_t dst_stride, int ncols, unsigned lg_n,
+                                unsigned nblk, const u64* pre1, const u64* pre2, bool inv, cudaStream_t st, unsigned jb0 = 0,
+                                const u64* tw = nullptr) {
+    const LargePlan p = large_plan(lg_n);
+    if (large_in_registers(lg_n)) {
+        ColsRegArgs a{src, src_stride, dst, dst_stride, p.lb, nblk, jb0, pre1, tw, size_t(1) << lg_n};
+        if (!pre1) { a.tw = plain_cols_table(lg_n, inv, st); a.tw_block_stride = 0; a.jb0 = 0; }
+        dim3 g1((unsigned)ncols, (1u << p.lb) / 128);
+        if (inv) launch_cols_reg<true>(g1, p.lg_n1, a, st);
+        else launch_cols_reg<false>(g1, p.lg_n1, a, st);
+        dim3 g2(nblk << p.lg_n1, (unsigned)ncols);
+        launch_lde_block(g2, p.lb, st, dst, dst_stride, dst, dst_stride, nullptr, size_t(1) << p.lb, inv ? 1 : 0, 0);
+        return;
+    }
     ColsNttArgs a{src, src_stride, dst, dst_stride, lg_n, p.lg_n1, p.lg_tb, pre1, pre2, inv ? 1 : 0, jb0};
     dim3 g1(1u << (p.lb - p.lg_tb), (unsigned)ncols, nblk);
     ZKB_COUNT_LAUNCH();
@@ -677,7 +744,7 @@ void launch_lde_blocks(const u64* coeffs, size_t coeff_stride, u64* out, size_t 
         launch_lde_block(grid, lg_n, st, coeffs, coeff_stride, out, out_stride, t.full, 0, 0, blk_lo);
         return;
     }
-    run_large_transform(coeffs, coeff_stride, out, out_stride, ncols, lg_n, blk_hi - blk_lo, t.pre1, t.pre2, false, st, blk_lo);
+    run_large_transform(coeffs, coeff_stride, out, out_stride, ncols, lg_n, blk_hi - blk_lo, t.pre1, t.pre2, false, st, blk_lo, t.tw);
 }
 void launch_lde(const u64* coeffs, size_t coeff_stride, u64* out, size_t out_stride, int ncols, unsigned lg_n,
                 unsigned rate_bits, u64 shift, cudaStream_t st) {

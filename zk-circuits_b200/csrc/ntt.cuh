@@ -13,6 +13,7 @@
 //  * field add/sub on canonical values with carry flags (5 / 7 instructions; the compiler's compare+select form is 9+).
 #pragma once
 #include "field.cuh"
+#include <utility>
 
 namespace zkb {
 
@@ -22,8 +23,8 @@ __device__ u64 d_W14[1u << NTT_SM_LG];                   // w_{2^14}^t, 0 <= t <
 ZKB_D unsigned ntt_pad(unsigned i) { return i + (i >> 4); }          // one spare word per 16: keeps small-stride passes off one bank
 inline size_t ntt_smem_bytes(unsigned lg) { return sizeof(u64) * ((size_t(1) << lg) + (size_t(1) << lg) / 16 + 1); }
 
-// in-register DIF of 2^K elements (K <= 4); r[p] ends up holding output index bitrev_K(p). The internal twiddles w_16^i are
-// powers of two: shift forms (field.cuh f_shl), no 64x64 multiply. INV: inverse twiddles.
+// in-register DIF of 2^K elements (K <= 6); r[p] ends up holding output index bitrev_K(p). The internal twiddles w_64^i = 2^(3 i)
+// are powers of two: shift forms (field.cuh f_shl), no 64x64 multiply. INV: inverse twiddles.
 template <int K, bool INV, int T, int G, int J>
 struct RadixStep {      // butterfly (g + j, g + j + half) of stage T, half = 2^(K-1-T); recursion over j, g, t at compile time
     static ZKB_D void run(u64* r) {
@@ -31,7 +32,7 @@ struct RadixStep {      // butterfly (g + j, g + j + half) of stage T, half = 2^
         const u64 a = r[G + J], b = r[G + J + half];
         r[G + J] = f_add(a, b);
         if constexpr (J == 0) r[G + J + half] = f_sub(a, b);
-        else r[G + J + half] = f_sub_twiddle16<J * (8 / half), INV>(a, b);
+        else r[G + J + half] = f_sub_twiddle64<J * (32 / half), INV>(a, b);
         if constexpr (J + 1 < half) RadixStep<K, INV, T, G, J + 1>::run(r);
         else if constexpr (G + 2 * half < (1 << K)) RadixStep<K, INV, T, G + 2 * half, 0>::run(r);
         else if constexpr (T + 1 < K) RadixStep<K, INV, T + 1, 0, 0>::run(r);
@@ -227,6 +228,125 @@ __global__ void __launch_bounds__(256) ntt_cols_kernel(ColsNttArgs a) {
         if (a.lg_n > 21) v = f_mul(v, d_rootA[E & 2047]);
         dst[(size_t)r * n2 + b] = v;
     }
+}
+
+// First step for n = n1 * 2^lg_n2 with n1 <= 64, in registers: ONE THREAD per matrix column b runs the whole n1-point DIF on
+// its n1 elements (stride n2 in memory, so a warp's loads and stores are coalesced) — every internal twiddle is a power of two
+// (w_64 = 8), no shared memory, no barrier — and multiplies entry (position p, b) by ONE table value
+//   tw[jb][p][b] = s_j^b * w_n^(+-b * bitrev(p)),   s_j = shift * w_N^j   (s_j = 1: the plain transform, one block of the table)
+// that merges the coset pre-scale's s_j^b with the step twiddle (the generic kernel above spends four multiplies per element
+// where this spends two). The thread loops over the coset blocks it writes, re-reading its n1 coefficients (L1/L2 hits: a
+// column's coefficients reach HBM once, not once per coset). src may alias dst only when nblk == 1.
+struct ColsRegArgs {
+    const u64* src; size_t src_stride;
+    u64* dst; size_t dst_stride;
+    unsigned lg_n2, nblk, jb0;
+    const u64* pre1;                        // [2^rate][n1]: (s_j^n2)^r, or null (plain transform)
+    const u64* tw; size_t tw_block_stride;  // block jb0 + jb of the table at + (jb0 + jb) * tw_block_stride (0 for the plain one)
+};
+template <int LG1, bool INV>
+__global__ void __launch_bounds__(128) ntt_cols_reg_kernel(ColsRegArgs a) {
+    constexpr int N1 = 1 << LG1;
+    const size_t n2 = size_t(1) << a.lg_n2;
+    const size_t b = (size_t)blockIdx.y * 128 + threadIdx.x;
+    const u64* src = a.src + (size_t)blockIdx.x * a.src_stride + b;
+    u64* dst0 = a.dst + (size_t)blockIdx.x * a.dst_stride + b;
+#pragma unroll 1
+    for (unsigned jb = 0; jb < a.nblk; ++jb) {
+        u64 r[N1];
+#pragma unroll
+        for (int e = 0; e < N1; ++e) r[e] = src[(size_t)e * n2];
+        if (a.pre1) {
+            const u64* p1 = a.pre1 + (size_t)(a.jb0 + jb) * N1;
+#pragma unroll
+            for (int e = 1; e < N1; ++e) r[e] = f_mul(r[e], __ldg(p1 + e));
+        }
+        RadixStep<LG1, INV, 0, 0, 0>::run(r);
+        const u64* tw = a.tw + (size_t)(a.jb0 + jb) * a.tw_block_stride + b;
+        u64* dst = dst0 + ((size_t)jb << (LG1 + a.lg_n2));
+        if (a.pre1) r[0] = f_mul(r[0], __ldg(tw));
+        dst[0] = r[0];
+#pragma unroll
+        for (int p = 1; p < N1; ++p) dst[(size_t)p * n2] = f_mul(r[p], __ldg(tw + (size_t)p * n2));
+    }
+}
+// The same first step for n1 = 32 / 64 = 8 x NB, where n1 values per thread no longer fit in registers (the 64-point form of
+// the kernel above needs 255 registers, runs 4 warps per scheduler... 12 % occupancy, 56 % instruction-cache hits: 3x slower per
+// element than the 16-point one — profiles/r02_ncu_cols_reg.md). Each thread stages its column in a PRIVATE strip of shared
+// memory (word [row][threadIdx.x]: conflict-free, no barrier):
+//   phase 1, for each residue a < 8 (unrolled, so every twiddle stays a compile-time shift): the NB-point DIF over e of the
+//            pre-scaled x[a + 8 e], times w_n1^(a q), q = the frequency left at position p;
+//   phase 2, for each p < NB (one rolled loop): the 8-point DIF over a, the merged table multiply, the store to row 8 p + p2
+//            — the position the plain n1-point DIF would have left frequency bitrev(8 p + p2) in.
+__host__ __device__ constexpr int bitrev_c(int x, int bits) {
+    int r = 0;
+    for (int i = 0; i < bits; ++i) r |= ((x >> i) & 1) << (bits - 1 - i);
+    return r;
+}
+template <int LGB, int A, int MUL, bool INV, int... P>
+ZKB_D void staged_twiddle(u64* r, std::integer_sequence<int, P...>) {
+    ((r[P] = f_mul_w64<(INV ? -1 : 1) * A * bitrev_c(P, LGB) * MUL>(r[P])), ...);
+}
+template <int LG1, bool INV, int A>
+ZKB_D void staged_phase1(const u64* src, size_t n2, const u64* p1, u64* my) {
+    constexpr int LGB = LG1 - 3, NB = 1 << LGB;
+    u64 r[NB];
+#pragma unroll
+    for (int e = 0; e < NB; ++e) r[e] = src[(size_t)(A + 8 * e) * n2];
+    if (p1) {
+#pragma unroll
+        for (int e = 0; e < NB; ++e)
+            if (A + 8 * e) r[e] = f_mul(r[e], __ldg(p1 + A + 8 * e));
+    }
+    RadixStep<LGB, INV, 0, 0, 0>::run(r);
+    staged_twiddle<LGB, A, (64 >> LG1), INV>(r, std::make_integer_sequence<int, NB>{});
+#pragma unroll
+    for (int p = 0; p < NB; ++p) my[(A + 8 * p) * 128] = r[p];
+}
+template <int LG1, bool INV, int... A>
+ZKB_D void staged_phase1_all(const u64* src, size_t n2, const u64* p1, u64* my, std::integer_sequence<int, A...>) {
+    (staged_phase1<LG1, INV, A>(src, n2, p1, my), ...);
+}
+template <int LG1, bool INV>
+__global__ void __launch_bounds__(128) ntt_cols_staged_kernel(ColsRegArgs a) {
+    constexpr int NB = 1 << (LG1 - 3);
+    extern __shared__ u64 sm[];             // [2^LG1][128]
+    u64* my = sm + threadIdx.x;
+    const size_t n2 = size_t(1) << a.lg_n2;
+    const size_t b = (size_t)blockIdx.y * 128 + threadIdx.x;
+    const u64* src = a.src + (size_t)blockIdx.x * a.src_stride + b;
+    u64* dst0 = a.dst + (size_t)blockIdx.x * a.dst_stride + b;
+#pragma unroll 1
+    for (unsigned jb = 0; jb < a.nblk; ++jb) {
+        const u64* p1 = a.pre1 ? a.pre1 + ((size_t)(a.jb0 + jb) << LG1) : nullptr;
+        staged_phase1_all<LG1, INV>(src, n2, p1, my, std::make_integer_sequence<int, 8>{});
+        const u64* tw = a.tw + (size_t)(a.jb0 + jb) * a.tw_block_stride + b;
+        u64* dst = dst0 + ((size_t)jb << (LG1 + a.lg_n2));
+#pragma unroll 1
+        for (int p = 0; p < NB; ++p) {
+            u64 r[8], w[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) w[k] = __ldg(tw + (size_t)(8 * p + k) * n2);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) r[k] = my[(k + 8 * p) * 128];
+            RadixStep<3, INV, 0, 0, 0>::run(r);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                u64 v = r[k];
+                if (a.pre1 || p + k) v = f_mul(v, w[k]);
+                dst[(size_t)(8 * p + k) * n2] = v;
+            }
+        }
+    }
+}
+// tw[jb][p][b] of the kernel above; base_j = shift * w_N^bitrev_r(jb) (1 for the plain table), w = w_n or its inverse
+__global__ void cols_reg_table_kernel(u64* tw, unsigned lg_n1, unsigned lg_n2, unsigned rate_bits, u64 shift, u64 w_N, u64 w_n, int coset) {
+    const size_t b = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    const unsigned p = blockIdx.y, jb = blockIdx.z;
+    if (b >= (size_t(1) << lg_n2)) return;
+    u64 base = gl_pow(w_n, bitrev32(p, lg_n1));
+    if (coset) base = gl_mul(base, gl_mul(shift, gl_pow(w_N, bitrev32(jb, rate_bits))));
+    tw[((((size_t)jb << lg_n1) + p) << lg_n2) + b] = gl_pow(base, b);
 }
 
 // inverse transform of one column: values on <w_n> (natural order, or bit-reversed if in_bitrev) -> coefficients

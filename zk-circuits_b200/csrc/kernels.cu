@@ -511,17 +511,21 @@ void launch_salt_fill_csprng(u64* out, size_t words, const u32 key[8], unsigned 
 // n <= 2^20: the first step runs in registers (ntt_cols_reg_kernel: n1 <= 64 points per thread, shift twiddles, one merged table
 // multiply), the second is the compile-time 2^14 block kernel. ZKB_NTT_COLS_GENERIC=1 (or n > 2^20) selects the shared-memory
 // first step.
-static bool large_in_registers(unsigned lg_n) {
+static bool large_in_registers() {
     static const bool on = [] { const char* e = std::getenv("ZKB_NTT_COLS_GENERIC"); return !(e && e[0] == '1'); }();
-    return on && lg_n <= NTT_SM_LG + 6;
+    return on;
 }
-struct LargePlan { unsigned lb, lg_n1, lg_tb; };
+// in registers: n = 2^lg_n1 x 2^lg_mid x 2^lb with lg_n1 <= 6; lg_mid = 6 for n > 2^20 (three steps: the rows the first step
+// leaves are plain 2^20-point transforms), 0 otherwise
+struct LargePlan { unsigned lb, lg_n1, lg_tb, lg_mid; };
 static LargePlan large_plan(unsigned lg_n) {
     if (lg_n > NTT_SM_LG + 10) throw std::runtime_error("NTT size too large (max 2^24)");
     LargePlan p;
-    if (large_in_registers(lg_n)) {
+    p.lg_mid = 0;
+    if (large_in_registers()) {
         p.lb = NTT_SM_LG;
-        p.lg_n1 = lg_n - NTT_SM_LG;
+        p.lg_mid = lg_n > NTT_SM_LG + 6 ? 6 : 0;
+        p.lg_n1 = lg_n - NTT_SM_LG - p.lg_mid;
         p.lg_tb = 0;
         return p;
     }
@@ -564,13 +568,13 @@ static void launch_lde_block(dim3 grid, unsigned lg_n, cudaStream_t st, const u6
                              size_t out_stride, const u64* prescale, size_t src_block_stride, int inv, unsigned jb0) {
     ZKB_COUNT_LAUNCH();
     const bool specialised = ntt_specialised();
-    if (specialised && !inv && ntt_radix8() && lg_n == 14)
+    if (specialised && ntt_radix8() && lg_n == 14)
         lde_block_kernel_t<3, 1024, 14><<<grid, 1024, ntt_smem_bytes(14), st>>>(coeffs, coeff_stride, out, out_stride, lg_n, prescale,
                                                                                src_block_stride, inv, jb0);
-    else if (specialised && !inv && ntt_radix8() && lg_n == 13)
+    else if (specialised && ntt_radix8() && lg_n == 13)
         lde_block_kernel_t<3, 1024, 13><<<grid, 1024, ntt_smem_bytes(13), st>>>(coeffs, coeff_stride, out, out_stride, lg_n, prescale,
                                                                                src_block_stride, inv, jb0);
-    else if (specialised && !inv && ntt_radix8() && lg_n == 12)
+    else if (specialised && ntt_radix8() && lg_n == 12)
         lde_block_kernel_t<3, 512, 12><<<grid, 512, ntt_smem_bytes(12), st>>>(coeffs, coeff_stride, out, out_stride, lg_n, prescale,
                                                                              src_block_stride, inv, jb0);
     else if (lg_n >= 13 && ntt_radix8())
@@ -586,7 +590,7 @@ struct CosetTables { u64* full = nullptr; u64* pre1 = nullptr; u64* pre2 = nullp
 __global__ void coset_table2_kernel(u64* pre1, u64* pre2, unsigned lg_n1, unsigned lg_n2, unsigned rate_bits, u64 shift, u64 w_N) {
     const unsigned k = blockIdx.x * blockDim.x + threadIdx.x, jb = blockIdx.y;
     const u64 base = gl_mul(shift, gl_pow(w_N, bitrev32(jb, rate_bits)));
-    if (k < (1u << lg_n2)) pre2[((size_t)jb << lg_n2) + k] = gl_pow(base, k);
+    if (pre2 && k < (1u << lg_n2)) pre2[((size_t)jb << lg_n2) + k] = gl_pow(base, k);
     if (k < (1u << lg_n1)) pre1[((size_t)jb << lg_n1) + k] = gl_pow(gl_pow(base, u64(1) << lg_n2), k);
 }
 static CosetTables coset_tables(unsigned lg_n, unsigned rate_bits, u64 shift, cudaStream_t st) {
@@ -609,40 +613,44 @@ static CosetTables coset_tables(unsigned lg_n, unsigned rate_bits, u64 shift, cu
     } else {
         const LargePlan p = large_plan(lg_n);
         ZKB_CUDA_CHECK(cudaMalloc(&t.pre1, (sizeof(u64) << p.lg_n1) << rate_bits));
-        ZKB_CUDA_CHECK(cudaMalloc(&t.pre2, (sizeof(u64) << p.lb) << rate_bits));
-        const unsigned m = 1u << (p.lb > p.lg_n1 ? p.lb : p.lg_n1);
-        dim3 grid((m + 127) / 128, 1u << rate_bits);
-        ZKB_COUNT_LAUNCH();
-        coset_table2_kernel<<<grid, 128, 0, st>>>(t.pre1, t.pre2, p.lg_n1, p.lb, rate_bits, shift, w_N);
-        if (large_in_registers(lg_n)) {        // merged s_j^b w_n^(b bitrev(p)) table: one LDE column's worth of memory per device
-            ZKB_CUDA_CHECK(cudaMalloc(&t.tw, (sizeof(u64) << lg_n) << rate_bits));
-            dim3 g((1u << p.lb) / 128, 1u << p.lg_n1, 1u << rate_bits);
+        if (large_in_registers()) {            // merged s_j^b w_n^(b bitrev(p)) table: one LDE column's worth of memory per device
+            const unsigned lg_row = lg_n - p.lg_n1;
+            dim3 grid(((1u << p.lg_n1) + 127) / 128, 1u << rate_bits);
             ZKB_COUNT_LAUNCH();
-            cols_reg_table_kernel<<<g, 128, 0, st>>>(t.tw, p.lg_n1, p.lb, rate_bits, shift, w_N, gl_root_of_unity(lg_n), 1);
+            coset_table2_kernel<<<grid, 128, 0, st>>>(t.pre1, nullptr, p.lg_n1, lg_row, rate_bits, shift, w_N);
+            ZKB_CUDA_CHECK(cudaMalloc(&t.tw, (sizeof(u64) << lg_n) << rate_bits));
+            dim3 g((1u << lg_row) / 128, 1u << p.lg_n1, 1u << rate_bits);
+            ZKB_COUNT_LAUNCH();
+            cols_reg_table_kernel<<<g, 128, 0, st>>>(t.tw, p.lg_n1, lg_row, rate_bits, shift, w_N, gl_root_of_unity(lg_n), 1);
+        } else {
+            ZKB_CUDA_CHECK(cudaMalloc(&t.pre2, (sizeof(u64) << p.lb) << rate_bits));
+            const unsigned m = 1u << (p.lb > p.lg_n1 ? p.lb : p.lg_n1);
+            dim3 grid((m + 127) / 128, 1u << rate_bits);
+            ZKB_COUNT_LAUNCH();
+            coset_table2_kernel<<<grid, 128, 0, st>>>(t.pre1, t.pre2, p.lg_n1, p.lb, rate_bits, shift, w_N);
         }
     }
     ZKB_CUDA_CHECK(cudaStreamSynchronize(st));       // other streams may use the tables as soon as they are in the cache
     cache[key] = t;
     return t;
 }
-// w_n^(+-b bitrev(p)) for the plain (no coset) in-register first step, cached per device
-static const u64* plain_cols_table(unsigned lg_n, bool inv, cudaStream_t st) {
+// w_n^(+-b bitrev(p)), p < 2^lg_n1, b < n / 2^lg_n1, for the plain (no coset) in-register step, cached per device
+static const u64* plain_cols_table(unsigned lg_n, unsigned lg_n1, bool inv, cudaStream_t st) {
     static std::mutex mu;
-    static std::map<std::tuple<int, unsigned, bool>, u64*> cache;
+    static std::map<std::tuple<int, unsigned, unsigned, bool>, u64*> cache;
     int dev = 0;
     ZKB_CUDA_CHECK(cudaGetDevice(&dev));
     std::lock_guard<std::mutex> lk(mu);
-    auto key = std::make_tuple(dev, lg_n, inv);
+    auto key = std::make_tuple(dev, lg_n, lg_n1, inv);
     auto it = cache.find(key);
     if (it != cache.end()) return it->second;
-    const LargePlan p = large_plan(lg_n);
     u64* tw = nullptr;
     ZKB_CUDA_CHECK(cudaMalloc(&tw, sizeof(u64) << lg_n));
     u64 w = gl_root_of_unity(lg_n);
     if (inv) w = gl_inv(w);
-    dim3 g((1u << p.lb) / 128, 1u << p.lg_n1, 1);
+    dim3 g((1u << (lg_n - lg_n1)) / 128, 1u << lg_n1, 1);
     ZKB_COUNT_LAUNCH();
-    cols_reg_table_kernel<<<g, 128, 0, st>>>(tw, p.lg_n1, p.lb, 0, 1, 1, w, 0);
+    cols_reg_table_kernel<<<g, 128, 0, st>>>(tw, lg_n1, lg_n - lg_n1, 0, 1, 1, w, 0);
     ZKB_CUDA_CHECK(cudaStreamSynchronize(st));
     cache[key] = tw;
     return tw;
@@ -665,13 +673,22 @@ static void run_large_transform(const u64* src, size_t src_stride, u64* dst, siz
                                 unsigned nblk, const u64* pre1, const u64* pre2, bool inv, cudaStream_t st, unsigned jb0 = 0,
                                 const u64* tw = nullptr) {
     const LargePlan p = large_plan(lg_n);
-    if (large_in_registers(lg_n)) {
-        ColsRegArgs a{src, src_stride, dst, dst_stride, p.lb, nblk, jb0, pre1, tw, size_t(1) << lg_n};
-        if (!pre1) { a.tw = plain_cols_table(lg_n, inv, st); a.tw_block_stride = 0; a.jb0 = 0; }
-        dim3 g1((unsigned)ncols, (1u << p.lb) / 128);
+    if (large_in_registers()) {
+        const unsigned lg_row = lg_n - p.lg_n1;         // 14, or 20 when a middle step follows
+        ColsRegArgs a{src, src_stride, dst, dst_stride, lg_row, nblk, jb0, pre1, tw, size_t(1) << lg_n, 1, 0};
+        if (!pre1) { a.tw = plain_cols_table(lg_n, p.lg_n1, inv, st); a.tw_block_stride = 0; a.jb0 = 0; }
+        dim3 g1((unsigned)ncols, (1u << lg_row) / 128);
         if (inv) launch_cols_reg<true>(g1, p.lg_n1, a, st);
         else launch_cols_reg<false>(g1, p.lg_n1, a, st);
-        dim3 g2(nblk << p.lg_n1, (unsigned)ncols);
+        if (p.lg_mid) {                                 // the nblk * n1 rows of a column: plain 2^20-point transforms, in place
+            const unsigned nsub = nblk << p.lg_n1;
+            ColsRegArgs m{dst, dst_stride, dst, dst_stride, p.lb, 1, 0, nullptr, plain_cols_table(lg_row, p.lg_mid, inv, st), 0,
+                          nsub, size_t(1) << lg_row};
+            dim3 gm((unsigned)ncols * nsub, (1u << p.lb) / 128);
+            if (inv) launch_cols_reg<true>(gm, p.lg_mid, m, st);
+            else launch_cols_reg<false>(gm, p.lg_mid, m, st);
+        }
+        dim3 g2(nblk << (lg_n - p.lb), (unsigned)ncols);
         launch_lde_block(g2, p.lb, st, dst, dst_stride, dst, dst_stride, nullptr, size_t(1) << p.lb, inv ? 1 : 0, 0);
         return;
     }
@@ -683,7 +700,30 @@ static void run_large_transform(const u64* src, size_t src_stride, u64* dst, siz
     launch_lde_block(g2, p.lb, st, dst, dst_stride, dst, dst_stride, nullptr, size_t(1) << p.lb, inv ? 1 : 0, 0);
 }
 
-// in-place bit-reversal permutation with scaling
+// in-place bit-reversal permutation with scaling, n >= 2^11: index = (hi : mid : lo) with 5-bit hi and lo; a CTA swaps the
+// 32 x 32 tiles of mid and bitrev(mid) through shared memory, so that reads and writes are both 256-byte row segments (the
+// element-wise kernel below scatters one side: 1.0 TB/s on 2^20-point columns)
+__global__ void __launch_bounds__(256) bitrev_scale_tiled_kernel(u64* data, size_t stride, unsigned lg_n, u64 scale) {
+    __shared__ u64 ta[32][33], tb[32][33];
+    const unsigned lg_mid = lg_n - 10, mid = blockIdx.x, rmid = bitrev32(mid, lg_mid);
+    if (mid > rmid) return;
+    u64* col = data + (size_t)blockIdx.y * stride;
+    const unsigned lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const unsigned sh_hi = lg_n - 5;
+#pragma unroll
+    for (unsigned hi = w; hi < 32; hi += 8) {
+        ta[hi][lane] = col[((size_t)hi << sh_hi) | ((size_t)mid << 5) | lane];
+        if (mid != rmid) tb[hi][lane] = col[((size_t)hi << sh_hi) | ((size_t)rmid << 5) | lane];
+    }
+    __syncthreads();
+    const unsigned rl = __brev(lane) >> 27;
+#pragma unroll
+    for (unsigned hi = w; hi < 32; hi += 8) {           // new[hi][bitrev(mid)][lane] = old[bitrev(lane)][mid][bitrev(hi)]
+        const unsigned rh = __brev(hi) >> 27;
+        col[((size_t)hi << sh_hi) | ((size_t)rmid << 5) | lane] = gl_mul(ta[rl][rh], scale);
+        if (mid != rmid) col[((size_t)hi << sh_hi) | ((size_t)mid << 5) | lane] = gl_mul(tb[rl][rh], scale);
+    }
+}
 __global__ void bitrev_scale_kernel(u64* data, size_t stride, unsigned lg_n, u64 scale) {
     size_t k = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
     if (k >= (size_t(1) << lg_n)) return;
@@ -698,8 +738,13 @@ __global__ void bitrev_scale_kernel(u64* data, size_t stride, unsigned lg_n, u64
     }
 }
 static void run_bitrev_scale(u64* data, size_t stride, int ncols, unsigned lg_n, u64 scale, cudaStream_t st) {
-    dim3 grid((unsigned)(((size_t(1) << lg_n) + 255) / 256), (unsigned)ncols);
     ZKB_COUNT_LAUNCH();
+    if (lg_n >= 11) {
+        dim3 tiles(1u << (lg_n - 10), (unsigned)ncols);
+        bitrev_scale_tiled_kernel<<<tiles, 256, 0, st>>>(data, stride, lg_n, scale);
+        return;
+    }
+    dim3 grid((unsigned)(((size_t(1) << lg_n) + 255) / 256), (unsigned)ncols);
     bitrev_scale_kernel<<<grid, 256, 0, st>>>(data, stride, lg_n, scale);
 }
 void launch_bitrev_permute(u64* data, size_t stride, int ncols, unsigned lg_n, cudaStream_t st) {

@@ -149,7 +149,7 @@ ZKB_D void ntt_dif_smem_c_from(u64* sm) {       // radix-8 passes from position 
 // coset LDE of one column block: out[jb * n + i] = sum_k coeff[k] (shift w_N^j)^k w_n^(k bitrev(i)),  j = bitrev_r(jb)
 // prescale: [2^rate_bits][n] table of (shift w_N^j)^k, or null for the plain transform (shift 1, rate 0)
 // src_block_stride = 0: every block jb transforms the same n coefficients (LDE); = n: block jb transforms its own
-// contiguous run (second step of the two-step transform for n > 2^14; coeffs may alias out). inv: inverse twiddles.
+// contiguous run (second step of the two-step transform for n > 2^14; coeffs may alias out). inv: inverse transform.
 template <int KMAX, int THREADS, int LGN = 0>      // LGN != 0: forward transform of exactly 2^LGN points, compile-time passes
 __global__ void __launch_bounds__(THREADS) lde_block_kernel_t(const u64* coeffs, size_t coeff_stride, u64* out,
                                                               size_t out_stride, unsigned lg_n, const u64* __restrict__ prescale,
@@ -172,14 +172,15 @@ __global__ void __launch_bounds__(THREADS) lde_block_kernel_t(const u64* coeffs,
 #pragma unroll
                 for (int u = 0; u < U; ++u) v[u] = f_mul(v[u], w[u]);
             }
+            // compile-time passes are forward only: the inverse transform is the forward one of the index-negated input
 #pragma unroll
-            for (int u = 0; u < U; ++u) sm[ntt_pad(i0 + u * THREADS)] = v[u];
+            for (int u = 0; u < U; ++u) sm[ntt_pad(LGN && inv ? (n - (i0 + u * THREADS)) & (n - 1) : i0 + u * THREADS)] = v[u];
         }
     } else {
         for (unsigned i = threadIdx.x; i < n; i += blockDim.x) {
             u64 v = src[i];
             if (ps) v = f_mul(v, ps[i]);
-            sm[ntt_pad(i)] = v;
+            sm[ntt_pad(LGN && inv ? (n - i) & (n - 1) : i)] = v;
         }
     }
     __syncthreads();
@@ -243,14 +244,22 @@ struct ColsRegArgs {
     unsigned lg_n2, nblk, jb0;
     const u64* pre1;                        // [2^rate][n1]: (s_j^n2)^r, or null (plain transform)
     const u64* tw; size_t tw_block_stride;  // block jb0 + jb of the table at + (jb0 + jb) * tw_block_stride (0 for the plain one)
-};
+    unsigned nsub; size_t sub_stride;       // blockIdx.x = column * nsub + sub: transform number `sub` of a column at + sub * sub_stride
+};                                          // (the middle step of a three-step transform; nsub = 1 otherwise)
+struct ColsRegBase { const u64* src; u64* dst; };
+ZKB_D ColsRegBase cols_reg_base(const ColsRegArgs& a) {
+    const unsigned col = blockIdx.x / a.nsub, sub = blockIdx.x - col * a.nsub;
+    const size_t b = (size_t)blockIdx.y * 128 + threadIdx.x, off = (size_t)sub * a.sub_stride + b;
+    return ColsRegBase{a.src + (size_t)col * a.src_stride + off, a.dst + (size_t)col * a.dst_stride + off};
+}
 template <int LG1, bool INV>
 __global__ void __launch_bounds__(128) ntt_cols_reg_kernel(ColsRegArgs a) {
     constexpr int N1 = 1 << LG1;
     const size_t n2 = size_t(1) << a.lg_n2;
     const size_t b = (size_t)blockIdx.y * 128 + threadIdx.x;
-    const u64* src = a.src + (size_t)blockIdx.x * a.src_stride + b;
-    u64* dst0 = a.dst + (size_t)blockIdx.x * a.dst_stride + b;
+    const ColsRegBase base = cols_reg_base(a);
+    const u64* src = base.src;
+    u64* dst0 = base.dst;
 #pragma unroll 1
     for (unsigned jb = 0; jb < a.nblk; ++jb) {
         u64 r[N1];
@@ -314,8 +323,9 @@ __global__ void __launch_bounds__(128) ntt_cols_staged_kernel(ColsRegArgs a) {
     u64* my = sm + threadIdx.x;
     const size_t n2 = size_t(1) << a.lg_n2;
     const size_t b = (size_t)blockIdx.y * 128 + threadIdx.x;
-    const u64* src = a.src + (size_t)blockIdx.x * a.src_stride + b;
-    u64* dst0 = a.dst + (size_t)blockIdx.x * a.dst_stride + b;
+    const ColsRegBase base = cols_reg_base(a);
+    const u64* src = base.src;
+    u64* dst0 = base.dst;
 #pragma unroll 1
     for (unsigned jb = 0; jb < a.nblk; ++jb) {
         const u64* p1 = a.pre1 ? a.pre1 + ((size_t)(a.jb0 + jb) << LG1) : nullptr;

@@ -185,3 +185,12 @@ def test_c_client_proof_is_accepted_and_byte_identical(zkb, oracle, tmp_path):
     oc = oracle.Circuit(s.common, s.const_sigma_values)
     assert oc.verify(proof) == ""
     assert proof == oc.prove(s.wires, s.public_inputs, salt_seed=7)
+
+
+@pytest.mark.parametrize("zk,min_degree_bits", [(False, 15), (True, 16)])
+def test_proof_bytes_above_the_single_block_transform_size(zkb, oracle, zk, min_degree_bits):
+    """n = 2^15 / 2^16 (larger than any circuit of the reference, which stop at 2^14): every transform of the proof takes the
+    multi-step path — plain and coset LDEs with the in-register first step, in-place inverse transforms with the tiled bit
+    reversal, the quotient's coset iNTT at 8n and the FRI extension-field LDE — and the bytes still equal the oracle's."""
+    s, oc, gc, proof = run_case(zkb, oracle, oracle.Synth.VOTING, zk, seed=11, min_degree_bits=min_degree_bits)
+    assert s.info["degree_bits"] == min_degree_bits

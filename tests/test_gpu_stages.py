@@ -216,8 +216,21 @@ def test_coset_sharded_commit_parts_concatenate_to_the_full_cap(zkb, oracle, lg_
         zkb.commit_cosets(vals, 3, 2, 0, 4)          # cap_height < rate_bits
 
 
+@pytest.mark.parametrize("lg_n", [19, 20, 21])
+def test_coset_sharded_commit_parts_at_the_staged_and_three_step_sizes(zkb, lg_n):
+    """The same identity where the first transform step runs in the staged kernels (n1 = 32, 64) and in three steps (2^21),
+    with a non-zero first coset and fewer than 8 blocks per call; the unsharded cap at 2^20 is pinned by the golden test."""
+    rng = np.random.default_rng(lg_n)
+    vals = rand_felts(rng, (1, 1 << lg_n))
+    want, _ = zkb.commit_batch(vals, 3, 4)
+    for G in (2, 8):
+        per = 8 // G
+        parts = [zkb.commit_cosets(vals, 3, 4, r * per, (r + 1) * per)[0] for r in range(G)]
+        assert np.array_equal(np.concatenate(parts), want)
+
+
 def test_lde_max_microbench_size_properties(zkb, oracle):
-    """BASELINE config #3's largest degree, n = 2^22 (two-step transform with n1 = 256, n2 = 2^14): linearity of the
+    """BASELINE config #3's largest degree, n = 2^22 (three-step transform, 4 x 64 x 2^14): linearity of the
     whole from_values map, and one leaf + one subgroup value re-evaluated from the returned coefficients by Horner."""
     rng = np.random.default_rng(22)
     lg_n, rb = 22, 3

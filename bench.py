@@ -413,9 +413,12 @@ def main():
         qn = 1 << 20
         qv = synth_columns(np, 20, 2 * (8 // world)).reshape(2, (8 // world) * qn)
         comm.quotient_chunks(qv, qn, 3)                      # untimed: NCCL sets up its point-to-point channels on first use
-        barrier()
-        _, qt = comm.quotient_chunks(qv, qn, 3)
-        qi, qx = zbatch.max_over_ranks([qt["interpolate_ms"], qt["exchange_ms"]], device="cuda")
+        qi = qx = float("inf")
+        for _ in range(3):                                   # best of three (max over ranks each): one call's exchange time
+            barrier()                                        # also holds whatever skew the ranks arrive with
+            _, qt = comm.quotient_chunks(qv, qn, 3)
+            a, b = zbatch.max_over_ranks([qt["interpolate_ms"], qt["exchange_ms"]], device="cuda")
+            qi, qx = min(qi, a), min(qx, b)
         sharded_line["quotient_chunks_n2^20"] = {"coset_intt_ms": qi, "all_to_all_plus_solve_ms": qx,
                                                  "bytes_exchanged_per_rank": int(2 * (8 // world) * qn * 8 * (world - 1) / world)}
         comm.close()

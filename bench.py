@@ -506,7 +506,7 @@ def main():
                      "bound": "hbm", "achieved": lde_gbs, "peak": peak, "unit": "GB/s", "frac": lde_gbs / peak,
                      "traffic": NCU_LDE_TRAFFIC_BYTES,
                      "note": "integer-issue bound in practice (322 thread instructions per element and transform = 36 per algorithmic byte vs "
-                             "5.7 the chip can issue per HBM byte; operation-count floor ~32: DESIGN.md 4.2); traffic = dram read + write of one "
+                             "5.7 the chip can issue per HBM byte; operation-count floor ~32: DESIGN.md 4.2; measured bound of the arithmetic alone, no data movement: 0.218 ms = 11.2 % of HBM on this shape, profiles/r02_ntt_floor.md); traffic = dram read + write of one "
                              "launch from profiles/r02_ncu_lde_block_v2.md (output partly still in L2)",
                      "from_values_gbs": 80 * n * nw / ((stages["wires_intt"] + lde_ms) * 1e-3) / 1e9,
                      "peak_source": peak_src, "algorithmic_bytes_per_launch": lde_bytes, "avg_ms": lde_ms},

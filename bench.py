@@ -401,11 +401,15 @@ def main():
         lde_ms, merkle_ms, gather_ms, t_wall = zbatch.max_over_ranks([tm["lde_ms"], tm["merkle_ms"], tm["gather_ms"], t_wall], device="cuda")
         nn = 1 << lg_n
         sharded_line = {"lg_n": lg_n, "cols": cols, "ranks": world, "blocks_per_rank": 8 // world, "lde_ms": lde_ms,
-                        "merkle_ms": merkle_ms, "coeff_allgather_ms_overlapped": gather_ms,
+                        "merkle_ms": merkle_ms, "peer_windows": tm["peer_windows"],
+                        ("peer_copies_ms_overlapped" if tm["peer_windows"] else "coeff_allgather_ms_overlapped"): gather_ms,
                         "lde_gbs_aggregate": 80 * nn * cols / (lde_ms * 1e-3) / 1e9,
                         "perms_per_sec_aggregate": (8 * nn * ((cols + 7) // 8) + 8 * nn - 16) / (merkle_ms * 1e-3),
-                        "collectives": "NCCL inside libzkb200.so: all-gather of the coefficients (column-sharded iNTT, 8 n cols bytes, "
-                                       "4 chunks pipelined behind the LDE) + all-gather of 16 x 32 B cap digests",
+                        "collectives": ("inside libzkb200.so: column-sharded iNTT into CUDA-IPC windows, each rank pulls the peers' "
+                                        "coefficients (8 n cols bytes) over NVLink with its copy engines, one slice ahead of the LDE; NCCL: one barrier + the all-gather of 16 x 32 B cap digests"
+                                        if tm["peer_windows"] else
+                                        "NCCL inside libzkb200.so: all-gather of the coefficients (column-sharded iNTT, 8 n cols bytes, "
+                                        "4 chunks pipelined behind the LDE) + all-gather of 16 x 32 B cap digests"),
                         "wall_ms_3_passes_incl_h2d_of_the_rank_slice": 1000 * t_wall,
                         "cap_word0": int(cap[0, 0]), "cap_equals_oracle_golden": cap_matches(np, cap, lg_n, cols)}
         # quotient chunks from coset-local evaluations: one all-to-all (2 challenges, n = 2^20); input = random field elements

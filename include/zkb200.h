@@ -169,12 +169,18 @@ int zkb_comm_unique_id(uint8_t id_out[ZKB_COMM_ID_BYTES]);
 int zkb_comm_create(const uint8_t id[ZKB_COMM_ID_BYTES], int nranks, int rank, int device, zkb_comm** out);
 int zkb_comm_destroy(zkb_comm* c);
 /* PolynomialBatch::from_values of ONE batch across the ranks of `c` (nranks | 2^rate_bits, cap_height >= rate_bits): every rank
- * passes the same values [ncols][n] but uploads and interpolates only ITS column slice; the coefficients are all-gathered over
- * NVLink in column chunks behind the LDE; the rank extends and hashes its own leaf blocks and builds their subtrees; one
- * all-gather of the cap digests. cap_out (all 2^cap_height digests) is identical on every rank and equals the single-GPU
- * commitment's cap. times_ms (may be NULL): {lde_ms (iNTT + gather + LDE), merkle_ms, coefficient all-gather ms (overlapped)} */
+ * passes the same values [ncols][n] but uploads and interpolates only ITS column slice, into a window of its memory that the
+ * peers have mapped (CUDA IPC); after one barrier each rank pulls the other slices out of their owners' windows with its copy
+ * engines over NVLink and starts the LDE of a slice as soon as its copy has landed; the rank extends and hashes its own
+ * leaf blocks and builds their subtrees; one all-gather of the cap digests. Where the peer mapping is unavailable (or with
+ * ZKB_SHARDED_P2P=0) the coefficients are all-gathered with NCCL in column chunks behind the LDE instead. cap_out (all
+ * 2^cap_height digests) is identical on every rank and equals the single-GPU commitment's cap. times_ms (may be NULL):
+ * {lde_ms (iNTT + exchange + LDE), merkle_ms, exchange ms alone (barrier + peer copies, or the NCCL gather; overlapped)} */
 int zkb_commit_sharded(zkb_comm* c, const uint64_t* values, size_t ncols, size_t n, unsigned rate_bits, unsigned cap_height, int reps,
                        uint64_t* cap_out, float* times_ms);
+/* 1 if this communicator's sharded commits pull from peer memory (windows mapped), 0 if they use the NCCL gather
+ * (also before the first zkb_commit_sharded call, which is where the windows are set up) */
+int zkb_comm_peer_windows(zkb_comm* c);
 /* Chunks of the quotient polynomial from COSET-LOCAL evaluations (compute_quotient_polys sharded by coset): q_values
  * [num_challenges][B n] = t on this rank's B = 2^rate_bits / nranks leaf blocks (leaf order); one coset iNTT per block, ONE
  * all-to-all of coefficient slices, an R x R Vandermonde solve per coefficient index. chunks_out [num_challenges][2^rate_bits][n / nranks]:

@@ -66,6 +66,7 @@ extern "C" {
     pub fn zkb_comm_destroy(c: *mut zkb_comm) -> c_int;
     pub fn zkb_commit_sharded(c: *mut zkb_comm, values: *const u64, ncols: usize, n: usize, rate_bits: c_uint, cap_height: c_uint,
                               reps: c_int, cap_out: *mut u64, times_ms: *mut c_float) -> c_int;
+    pub fn zkb_comm_peer_windows(c: *mut zkb_comm) -> c_int;
     pub fn zkb_quotient_chunks_sharded(c: *mut zkb_comm, q_values: *const u64, num_challenges: usize, n: usize, rate_bits: c_uint,
                                        chunks_out: *mut u64, times_ms: *mut c_float) -> c_int;
     pub fn zkb_last_timings(c: *const zkb_circuit, ms_out: *mut c_float, cap: c_int) -> c_int;

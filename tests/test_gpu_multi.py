@@ -30,12 +30,18 @@ comm = Z.Comm(uid, world, rank, device=rank)
 rng = np.random.default_rng(4)                      # same data on every rank
 P = O.P
 # 1. sharded commitment: odd column count (padding of the column slices), both NTT paths
-for lg_n, cols in ((10, 37), (15, 5)):
+# (the second shape makes the peer windows grow and be re-mapped, the third re-uses them, reps = 2 overwrites a window in place)
+modes = []
+for lg_n, cols, reps in ((10, 37, 1), (15, 5, 1), (12, 9, 2)):
     vals = rng.integers(0, P, size=(cols, 1 << lg_n), dtype=np.uint64)
-    cap, tm = comm.commit(vals, 3, 4, reps=1)
+    cap, tm = comm.commit(vals, 3, 4, reps=reps)
     _, lde = O.lde_batch(vals, 3)
     _, want = O.merkle_commit(lde, 4)
     assert np.array_equal(cap, want), (lg_n, cols)
+    modes.append(tm["peer_windows"])
+assert len(set(modes)) == 1
+if os.environ.get("ZKB_SHARDED_P2P") == "0":
+    assert not modes[0]
 # 2. quotient chunks from coset-local evaluations
 n, R = 1 << 8, 8
 chunks = rng.integers(0, P, size=(2, R, n), dtype=np.uint64)
@@ -57,12 +63,15 @@ for ch in range(2):
 got, _ = comm.quotient_chunks(q, n, 3)
 assert np.array_equal(got, chunks[:, :, rank * sl:(rank + 1) * sl])
 comm.close()
-open(os.path.join(tmp, f"ok{rank}"), "w").write("ok")
+open(os.path.join(tmp, f"ok{rank}"), "w").write("ok peer_windows=%s" % modes[0])
 '''
 
 
+@pytest.mark.parametrize("p2p", ["1", "0"])
 @pytest.mark.parametrize("world", [2, 4])
-def test_nccl_sharded_commit_and_quotient_exchange_across_gpus(tmp_path, world):
+def test_nccl_sharded_commit_and_quotient_exchange_across_gpus(tmp_path, world, p2p):
+    """p2p = 1: the LDE kernels read the coefficients out of the peers' CUDA-IPC windows (falls back by itself where the mapping
+    is unavailable; the mode used is printed); p2p = 0: the NCCL all-gather form of the same exchange."""
     sys.path.insert(0, os.path.join(ROOT, "zk-circuits_b200"))
     import zkb200
 
@@ -70,9 +79,11 @@ def test_nccl_sharded_commit_and_quotient_exchange_across_gpus(tmp_path, world):
         pytest.skip(f"needs {world} GPUs on one box")
     script = tmp_path / "worker.py"
     script.write_text(WORKER)
+    env = dict(os.environ, ZKB_SHARDED_P2P=p2p)
     procs = [subprocess.Popen([sys.executable, str(script), ROOT, str(r), str(world), str(tmp_path)], stdout=subprocess.PIPE,
-                              stderr=subprocess.STDOUT, text=True) for r in range(world)]
+                              stderr=subprocess.STDOUT, text=True, env=env) for r in range(world)]
     outs = [p.communicate(timeout=600)[0] for p in procs]
     for r, (p, o) in enumerate(zip(procs, outs)):
         assert p.returncode == 0, f"rank {r}:\n{o[-3000:]}"
-        assert (tmp_path / f"ok{r}").read_text() == "ok"
+        assert (tmp_path / f"ok{r}").read_text().startswith("ok")
+    print(f"world {world} ZKB_SHARDED_P2P={p2p}: {(tmp_path / 'ok0').read_text()}")

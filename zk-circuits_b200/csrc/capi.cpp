@@ -373,6 +373,12 @@ int zkb_commit_sharded(zkb_comm* c, const uint64_t* values, size_t ncols, size_t
         return (int)ZKB_OK;
     });
 }
+int zkb_comm_peer_windows(zkb_comm* c) {
+    return guarded([&] {
+        if (!c) throw ArgError("comm is null");
+        return c->impl->peer_windows() ? 1 : 0;
+    });
+}
 int zkb_quotient_chunks_sharded(zkb_comm* c, const uint64_t* q_values, size_t num_challenges, size_t n, unsigned rate_bits,
                                 uint64_t* chunks_out, float* times_ms) {
     return guarded([&] {

@@ -88,8 +88,78 @@ Comm::Comm(const uint8_t id_bytes[COMM_ID_BYTES], int nranks, int rank, int devi
         throw;
     }
 }
+// ---- peer windows: every rank's coefficient buffer mapped into every other rank (CUDA IPC over NVLink) ----
+void Comm::barrier() {
+    if (!sync_words_) CK(cudaMalloc(&sync_words_, sizeof(u64) * (size_t)nranks_));
+    NK(nccl().AllGather(sync_words_ + rank_, sync_words_, 1, ncclUint64, static_cast<ncclComm_t>(comm_), st_));
+}
+void Comm::release_window() {
+    if (!win_) return;
+    for (int r = 0; r < nranks_; ++r)
+        if (r != rank_ && r < (int)peer_win_.size() && peer_win_[r]) cudaIpcCloseMemHandle(peer_win_[r]);
+    peer_win_.clear();
+    try {                                   // nobody may still have this window mapped when it is freed
+        barrier();
+        cudaStreamSynchronize(st_);
+    } catch (...) {}
+    cudaFree(win_);
+    win_ = nullptr;
+    win_words_ = 0;
+}
+bool Comm::ensure_window(size_t words) {
+    static const bool enabled = [] { const char* e = std::getenv("ZKB_SHARDED_P2P"); return !(e && e[0] == '0'); }();
+    if (!enabled || nranks_ < 2) return false;
+    if (p2p_tried_ && !p2p_ok_) return false;
+    if (words <= win_words_) return p2p_ok_;
+    // every rank takes the same path: the shapes of a sharded call are the same on all of them
+    release_window();
+    p2p_tried_ = true;
+    const size_t G = (size_t)nranks_, HW = sizeof(cudaIpcMemHandle_t) / sizeof(u64) + 1;      // handle words + one flag word
+    ncclComm_t comm = static_cast<ncclComm_t>(comm_);
+    std::vector<u64> mine(HW, 0), all(G * HW, 0);
+    cudaIpcMemHandle_t h;
+    if (cudaMalloc(&win_, words * sizeof(u64)) == cudaSuccess && cudaIpcGetMemHandle(&h, win_) == cudaSuccess) {
+        std::memcpy(mine.data(), &h, sizeof h);
+        mine[HW - 1] = 1;
+    } else {
+        cudaGetLastError();
+    }
+    DevBuf hb(G * HW);
+    CK(cudaMemcpyAsync(hb.get() + (size_t)rank_ * HW, mine.data(), HW * 8, cudaMemcpyHostToDevice, st_));
+    NK(nccl().AllGather(hb.get() + (size_t)rank_ * HW, hb.get(), HW, ncclUint64, comm, st_));
+    CK(cudaMemcpyAsync(all.data(), hb.get(), G * HW * 8, cudaMemcpyDeviceToHost, st_));
+    CK(cudaStreamSynchronize(st_));
+    u64 ok = 1;
+    for (size_t r = 0; r < G; ++r) ok &= all[r * HW + HW - 1];
+    peer_win_.assign(G, nullptr);
+    if (ok) {
+        for (size_t r = 0; r < G && ok; ++r) {
+            if ((int)r == rank_) { peer_win_[r] = win_; continue; }
+            cudaIpcMemHandle_t ph;
+            std::memcpy(&ph, &all[r * HW], sizeof ph);
+            void* ptr = nullptr;
+            if (cudaIpcOpenMemHandle(&ptr, ph, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { cudaGetLastError(); ok = 0; }
+            peer_win_[r] = static_cast<u64*>(ptr);
+        }
+    }
+    // agree: one rank that could not map a peer sends everybody to the NCCL gather
+    if (!sync_words_) CK(cudaMalloc(&sync_words_, sizeof(u64) * G));
+    CK(cudaMemcpyAsync(sync_words_ + rank_, &ok, 8, cudaMemcpyHostToDevice, st_));
+    NK(nccl().AllGather(sync_words_ + rank_, sync_words_, 1, ncclUint64, comm, st_));
+    std::vector<u64> oks(G);
+    CK(cudaMemcpyAsync(oks.data(), sync_words_, G * 8, cudaMemcpyDeviceToHost, st_));
+    CK(cudaStreamSynchronize(st_));
+    for (u64 v : oks) ok &= v;
+    p2p_ok_ = ok != 0;
+    if (p2p_ok_) win_words_ = words;
+    else release_window();
+    return p2p_ok_;
+}
+
 Comm::~Comm() {
     cudaSetDevice(device_);
+    release_window();
+    if (sync_words_) cudaFree(sync_words_);
     if (st_) { cudaStreamSynchronize(st_); cudaStreamDestroy(st_); }
     if (comm_st_) { cudaStreamSynchronize(comm_st_); cudaStreamDestroy(comm_st_); }
     if (comm_) nccl().CommDestroy(static_cast<ncclComm_t>(comm_));
@@ -111,7 +181,8 @@ void Comm::commit(const u64* values, size_t ncols, size_t n, unsigned rate_bits,
     const unsigned cap_local = cap_height - rate_bits + lg2u(B);
     // columns in chunks of G * w: rank r interpolates columns [k G w + r w, + w) of chunk k (zero padding past ncols)
     const size_t per_rank = (ncols + G - 1) / G;
-    const size_t nchunks = per_rank >= 8 ? 4 : 1, w = (per_rank + nchunks - 1) / nchunks, padded = nchunks * G * w;
+    const bool p2p = ensure_window(per_rank * n);          // peers pull my coefficients out of my window: one chunk per rank
+    const size_t nchunks = (!p2p && per_rank >= 8) ? 4 : 1, w = (per_rank + nchunks - 1) / nchunks, padded = nchunks * G * w;
     DevBuf coeffs(padded * n), lde(ncols * L), dg(merkle_digest_count(L, cap_local) * 4), cap_all((size_t(4) << cap_height));
     DevBuf vals(nchunks * w * n);
     CK(cudaMemsetAsync(vals.get(), 0, nchunks * w * n * 8, st_));
@@ -121,10 +192,43 @@ void Comm::commit(const u64* values, size_t ncols, size_t n, unsigned rate_bits,
         const size_t cnt = std::min(w, ncols - c0);
         CK(cudaMemcpyAsync(vals.get() + k * w * n, values + c0 * n, cnt * n * 8, cudaMemcpyHostToDevice, st_));
     }
-    Events tm(5), chain(2 * nchunks, false);
+    Events tm(5), chain(std::max<size_t>(2 * nchunks, G), false);
     float t_lde = 0, t_merkle = 0, t_gather = 0;
     size_t cap_off = 0;
-    auto pass = [&] {
+    auto pass_p2p = [&] {
+        CK(cudaEventRecord(tm[0], st_));
+        launch_intt_natural(vals.get(), n, win_, n, (int)w, lg_n, nullptr, st_);
+        CK(cudaEventRecord(tm[3], st_));
+        barrier();                                         // every window holds its owner's coefficients
+        CK(cudaEventRecord(chain[rank_], st_));
+        CK(cudaStreamWaitEvent(comm_st_, chain[rank_], 0));
+        // pull the other ranks' slices out of their windows with the copy engines (NVLink), nearest rank first so that no window
+        // is read by every peer at once; the LDE of a slice starts when its copy has landed, the rank's own slice needs none
+        for (unsigned s1 = 1; s1 < G; ++s1) {
+            const size_t r = ((size_t)rank_ + s1) % G, c0 = r * w;
+            if (c0 >= ncols) continue;
+            const size_t cnt = std::min(w, ncols - c0);
+            CK(cudaMemcpyAsync(coeffs.get() + c0 * n, peer_win_[r], cnt * n * 8, cudaMemcpyDefault, comm_st_));
+            CK(cudaEventRecord(chain[r], comm_st_));
+        }
+        CK(cudaEventRecord(tm[4], comm_st_));
+        for (unsigned s1 = 0; s1 < G; ++s1) {
+            const size_t r = ((size_t)rank_ + s1) % G, c0 = r * w;
+            if (c0 >= ncols) continue;
+            const size_t cnt = std::min(w, ncols - c0);
+            if (s1) CK(cudaStreamWaitEvent(st_, chain[r], 0));
+            launch_lde_blocks(s1 ? coeffs.get() + c0 * n : win_, n, lde.get() + c0 * L, L, (int)cnt, lg_n, rate_bits, GL_GEN, blk_lo,
+                              blk_lo + B, st_);
+        }
+        CK(cudaEventRecord(tm[1], st_));
+        cap_off = launch_merkle_tree(lde.get(), L, (int)ncols, L, dg.get(), cap_local, st_);
+        // the cap gather is also the barrier after which a window may be overwritten: a rank contributes once its copies have run
+        NK(nccl().AllGather(dg.get() + cap_off * 4, cap_all.get(), (size_t(4) << cap_local), ncclUint64, comm, st_));
+        CK(cudaEventRecord(tm[2], st_));
+        CK(cudaEventSynchronize(tm[2]));
+        CK(cudaStreamSynchronize(comm_st_));
+    };
+    auto pass_gather = [&] {
         CK(cudaEventRecord(tm[0], st_));
         for (size_t k = 0; k < nchunks; ++k) {             // interpolate my slice of chunk k, then gather the chunk (comm stream)
             u64* mine = coeffs.get() + (k * G * w + (size_t)rank_ * w) * n;
@@ -150,6 +254,7 @@ void Comm::commit(const u64* values, size_t ncols, size_t n, unsigned rate_bits,
         CK(cudaEventSynchronize(tm[2]));
         CK(cudaStreamSynchronize(comm_st_));
     };
+    auto pass = [&] { if (p2p) pass_p2p(); else pass_gather(); };
     if (reps > 1) pass();                                  // untimed: twiddle / coset tables, NCCL channel setup
     for (int r = 0; r < reps; ++r) {
         pass();

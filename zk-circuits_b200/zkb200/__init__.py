@@ -34,7 +34,7 @@ EXPORTS = ["zkb_version", "zkb_last_error", "zkb_device_count", "zkb_kernel_laun
            "zkb_commit_cosets",
            "zkb_partial_products", "zkb_quotient", "zkb_engine_create", "zkb_engine_destroy", "zkb_engine_proof_size",
            "zkb_engine_acquire", "zkb_engine_release", "zkb_engine_submit", "zkb_engine_wait", "zkb_comm_unique_id", "zkb_comm_create",
-           "zkb_comm_destroy", "zkb_commit_sharded", "zkb_quotient_chunks_sharded"]
+           "zkb_comm_destroy", "zkb_commit_sharded", "zkb_comm_peer_windows", "zkb_quotient_chunks_sharded"]
 # `flags` of the prove calls (include/zkb200.h)
 POW_MIN, SALTS_FROM_SEED, CHECK_WITNESS, WITNESS_RESIDENT = 0, 0x100, 0x200, 0x400
 SYNTH_LIB_PATH = os.path.join(_ROOT, "libzkb200_synth.so")
@@ -102,6 +102,7 @@ def lib():
         L.zkb_comm_destroy.argtypes = [ctypes.c_void_p]
         L.zkb_commit_sharded.argtypes = [ctypes.c_void_p, u64p, ctypes.c_size_t, ctypes.c_size_t, ctypes.c_uint, ctypes.c_uint, ctypes.c_int,
                                          u64p, f32p]
+        L.zkb_comm_peer_windows.argtypes = [ctypes.c_void_p]
         L.zkb_quotient_chunks_sharded.argtypes = [ctypes.c_void_p, u64p, ctypes.c_size_t, ctypes.c_size_t, ctypes.c_uint, u64p, f32p]
         _lib = L
     return _lib
@@ -338,7 +339,8 @@ class Comm:
         cap = np.zeros((1 << cap_height, 4), dtype=np.uint64)
         t = np.zeros(3, dtype=np.float32)
         _check(lib().zkb_commit_sharded(self._h, p, ncols, n, rate_bits, cap_height, reps, cap.ctypes.data_as(u64p), t.ctypes.data_as(f32p)))
-        return cap, {"lde_ms": float(t[0]), "merkle_ms": float(t[1]), "gather_ms": float(t[2])}
+        return cap, {"lde_ms": float(t[0]), "merkle_ms": float(t[1]), "gather_ms": float(t[2]),
+                     "peer_windows": bool(lib().zkb_comm_peer_windows(self._h) == 1)}
 
     def quotient_chunks(self, q_values, n, rate_bits=3):
         """q_values [nch][B n]: the quotient's evaluations on this rank's leaf blocks -> [nch][2^rate_bits][n / nranks]."""

@@ -21,5 +21,14 @@ for it in range(2):
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     if rank == 0:
         print(f"ranks {world} 2^{lg_n} x {cols} peer_windows={tm['peer_windows']} lde {t[0]:.3f} ms merkle {t[1]:.3f} ms exchange {t[2]:.3f} ms cap0 {int(cap[0,0]):#x}", flush=True)
+qn = 1 << 20
+qv = rng.integers(0, 0xFFFFFFFF00000001, size=(2, (8 // world) * qn), dtype=np.uint64)
+for it in range(4):
+    dist.barrier()
+    _, qt = comm.quotient_chunks(qv, qn, 3)
+    t = torch.tensor([qt["interpolate_ms"], qt["exchange_ms"]], device="cuda")
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    if rank == 0:
+        print(f"ranks {world} quotient chunks n=2^20 x 2: coset iNTT {t[0]:.3f} ms, exchange + solve {t[1]:.3f} ms", flush=True)
 comm.close()
 dist.destroy_process_group()

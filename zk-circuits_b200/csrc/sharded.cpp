@@ -280,9 +280,11 @@ void Comm::quotient_chunks(const u64* q_values, size_t nch, size_t n, unsigned r
     const unsigned lg_n = lg2u(n), B = R / G;
     const size_t sl = n / G;                                  // coefficient indices per rank
     const u64 w_N = gl_root_of_unity(lg_n + rate_bits);
-    DevBuf u(nch * B * n), all((size_t)nch * R * sl), out((size_t)nch * R * sl), mat((size_t)R * R);
+    const bool p2p = ensure_window(nch * B * n);              // the interpolants live in the window the peers have mapped
+    DevBuf u_local(p2p ? 1 : nch * B * n), all((size_t)nch * R * sl), out((size_t)nch * R * sl), mat((size_t)R * R);
+    u64* const u = p2p ? win_ : u_local.get();
     Events tm(3);
-    CK(cudaMemcpyAsync(u.get(), q_values, nch * B * n * 8, cudaMemcpyHostToDevice, st_));
+    CK(cudaMemcpyAsync(u, q_values, nch * B * n * 8, cudaMemcpyHostToDevice, st_));
     // V^-1[m][j] = c_0^-m w_R^(-j m) / R with c_j = (g w_N^j)^n = c_0 w_R^j
     std::vector<u64> vinv((size_t)R * R);
     const u64 c0_inv = gl_inv(gl_pow(GL_GEN, n)), wR_inv = gl_inv(gl_pow(w_N, n)), r_inv = gl_inv(R);
@@ -295,19 +297,33 @@ void Comm::quotient_chunks(const u64* q_values, size_t nch, size_t n, unsigned r
     for (size_t ch = 0; ch < nch; ++ch)
         for (unsigned i = 0; i < B; ++i) {
             const unsigned jb = (unsigned)rank_ * B + i, j = bitrev32(jb, rate_bits);
-            launch_coset_intt_bitrev(u.get() + (ch * B + i) * n, n, 1, lg_n, gl_mul(GL_GEN, gl_pow(w_N, j)), st_);
+            launch_coset_intt_bitrev(u + (ch * B + i) * n, n, 1, lg_n, gl_mul(GL_GEN, gl_pow(w_N, j)), st_);
         }
     CK(cudaEventRecord(tm[1], st_));
-    // all-to-all: peer p gets coefficient slice p of every (challenge, block) interpolant of this rank; placed by coset index
-    NK(nccl().GroupStart());
-    for (unsigned p = 0; p < G; ++p)
-        for (size_t ch = 0; ch < nch; ++ch)
-            for (unsigned i = 0; i < B; ++i) {
-                NK(nccl().Send(u.get() + (ch * B + i) * n + (size_t)p * sl, sl, ncclUint64, (int)p, comm, st_));
-                const unsigned j = bitrev32(p * B + i, rate_bits);
-                NK(nccl().Recv(all.get() + (ch * R + j) * sl, sl, ncclUint64, (int)p, comm, st_));
-            }
-    NK(nccl().GroupEnd());
+    // all-to-all: this rank needs coefficient slice `rank` of every (challenge, block) interpolant of every peer, placed by coset
+    if (p2p) {                      // pulled out of the peers' windows over NVLink (copy engines), nearest rank first
+        barrier();                  // every window holds its interpolants
+        for (unsigned s1 = 0; s1 < G; ++s1) {
+            const unsigned p = ((unsigned)rank_ + s1) % G;
+            for (size_t ch = 0; ch < nch; ++ch)
+                for (unsigned i = 0; i < B; ++i) {
+                    const unsigned j = bitrev32(p * B + i, rate_bits);
+                    CK(cudaMemcpyAsync(all.get() + (ch * R + j) * sl, peer_win_[p] + (ch * B + i) * n + (size_t)rank_ * sl, sl * 8,
+                                       cudaMemcpyDefault, st_));
+                }
+        }
+        barrier();                  // nobody overwrites its window while a peer still reads it
+    } else {
+        NK(nccl().GroupStart());
+        for (unsigned p = 0; p < G; ++p)
+            for (size_t ch = 0; ch < nch; ++ch)
+                for (unsigned i = 0; i < B; ++i) {
+                    NK(nccl().Send(u + (ch * B + i) * n + (size_t)p * sl, sl, ncclUint64, (int)p, comm, st_));
+                    const unsigned j = bitrev32(p * B + i, rate_bits);
+                    NK(nccl().Recv(all.get() + (ch * R + j) * sl, sl, ncclUint64, (int)p, comm, st_));
+                }
+        NK(nccl().GroupEnd());
+    }
     for (size_t ch = 0; ch < nch; ++ch)
         launch_vandermonde_solve(all.get() + ch * R * sl, out.get() + ch * R * sl, sl, R, mat.get(), st_);
     CK(cudaEventRecord(tm[2], st_));

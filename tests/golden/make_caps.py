@@ -19,7 +19,8 @@ sys.path.insert(0, os.path.join(ROOT, "oracle"))
 
 SEED = 0xB200000000000001
 P = 0xFFFFFFFF00000001
-SHAPES = [(14, 100), (14, 135), (14, 200), (14, 400), (16, 100), (16, 135), (16, 200), (18, 100), (18, 135), (20, 100)]
+SHAPES = [(14, 100), (14, 135), (14, 200), (14, 400), (16, 100), (16, 135), (16, 200), (18, 100), (18, 135), (20, 100),
+          (19, 5), (21, 5), (22, 5)]      # narrow batches at the sizes of the staged first NTT step and of the three-step transform
 
 
 def synth_columns(lg_n, cols):

@@ -269,11 +269,12 @@ def _config3_columns(lg_n, cols):
     return np.where(z >= np.uint64(P), z - np.uint64(P), z).reshape(cols, nn)
 
 
-@pytest.mark.parametrize("lg_n,cols", [(14, 135), (14, 400), (16, 135), (16, 200), (18, 100), (20, 100)])
+@pytest.mark.parametrize("lg_n,cols", [(14, 135), (14, 400), (16, 135), (16, 200), (18, 100), (20, 100), (19, 5), (21, 5), (22, 5)])
 def test_commit_cap_matches_the_oracle_golden_at_microbench_sizes(zkb, lg_n, cols):
     """Exact parity at BASELINE.json config #3's sizes: the 16 cap digests of the fused from_values commitment (iNTT + coset
-    LDE, single-block and two-step transforms, fused Merkle trees up to 2^23 leaves) equal the caps the CPU oracle computed once
-    for the same seeded columns (tests/golden/make_caps.py -> config3_caps.json)."""
+    LDE, single-block, two-step and — above 2^20 — three-step transforms, fused Merkle trees up to 2^25 leaves) equal the caps the
+    CPU oracle computed once for the same seeded columns (tests/golden/make_caps.py -> config3_caps.json); the narrow shapes
+    pin the staged 32-point first step (2^19) and the largest microbenchmark degree (2^22) exactly."""
     import json
     import os
 

@@ -1,4 +1,5 @@
-// Proof engine: several prover contexts of ONE circuit on ONE GPU, driven by a single host thread, behind an asynchronous
+// Proof engine: several prover contexts of ONE circuit on ONE GPU, driven by a single host thread (up to four for small
+// circuits, whose proofs are launch-bound: see Engine::Engine), behind an asynchronous
 // submit / wait interface with pinned witness buffers the caller fills directly.
 //
 // Why (SURVEY.md §8f rank 3, and the host side of §8e(1)): a proof is ~10 short GPU stages separated by serial Fiat-Shamir
@@ -58,7 +59,7 @@ private:
         int status = 0;
         std::string error;
     };
-    void run();
+    void run(int driver, int n_drivers);
     void finish(int ctx, int status, const std::string& err);
 
     int device_;
@@ -69,7 +70,7 @@ private:
     std::mutex mu_;
     std::condition_variable cv_driver_, cv_client_;
     bool stop_ = false;
-    std::thread driver_;
+    std::vector<std::thread> drivers_;   // driver t owns contexts t, t + n_drivers, ...
 };
 
 // maps the library's exceptions to zkb_status codes (shared with capi.cpp)

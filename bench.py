@@ -155,7 +155,7 @@ def reference_arm(args, rank):
         "parallelism": "host cores (OpenMP); GPUs unused",
         "cpu_baseline": {"value": val, "unit": UNIT, "cores": O.num_threads(), "kind": "port",
                          "sample": f"{steps} full proofs of the bench circuit (one proof per step = 1/{B} of the GPU arm's step) with the "
-                                   "oracle's restated Plonky2 prover, AVX2 Poseidon + OpenMP"},
+                                   "oracle's restated Plonky2 prover, AVX2 Poseidon + 4-lane AVX2 gate evaluation + OpenMP"},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     emit(line)
@@ -639,7 +639,7 @@ def main():
         ref = oc.prove(os_.wires, os_.public_inputs, salt_seed=3000 + K - 1)   # same seed as stream 0's last e2e proof
         dt = time.perf_counter() - t0
         line["cpu_baseline"] = {"value": 1.0 / dt, "unit": UNIT, "cores": O.num_threads(), "kind": "port",
-                                "sample": "1 full proof of the bench circuit, oracle's restated Plonky2 prover (AVX2 Poseidon, OpenMP)",
+                                "sample": "1 full proof of the bench circuit, oracle's restated Plonky2 prover (AVX2 Poseidon, 4-lane AVX2 gate evaluation, OpenMP)",
                                 "bytes_identical_to_gpu_proof": bool(ref == proof)}
     emit(line)
     if dist is not None:

@@ -1,6 +1,7 @@
 // ORACLE — TEST INFRASTRUCTURE ONLY (see prover.hpp header for scope, citations and parity status).
 #include "prover.hpp"
 #include "gates.hpp"
+#include "vec_ops.hpp"
 #include <algorithm>
 #include <chrono>
 #include <cstdio>
@@ -132,6 +133,43 @@ std::vector<std::vector<u64>> compute_quotient_chunks(const CircuitData& cd, con
     size_t next_step = qdf;
     std::vector<std::vector<u64>> q(nch, std::vector<u64>(N));
     size_t ncs = c.num_constants;
+#if defined(__AVX2__)
+    if (g_fast_poseidon && N % 4 == 0) {
+        // CPU-baseline arm: the same generic constraint code (gates.hpp) instantiated over four lanes (vec_ops.hpp), four LDE
+        // points per call; rows are gathered into lane vectors first
+        const size_t nzs = nch * (1 + c.num_partial_products);
+#pragma omp parallel
+        {
+            std::vector<V4> vcs(ncs + c.num_routed_wires), vw(c.num_wires), vz(nzs), vzn(nch);
+#pragma omp for schedule(static)
+            for (long i4 = 0; i4 < (long)(N / 4); ++i4) {
+                const size_t i = (size_t)i4 * 4;
+                const u64 *cs[4], *wr[4], *zr[4], *zn[4];
+                u64 l0[4];
+                for (int k = 0; k < 4; ++k) {
+                    cs[k] = cd.constants_sigmas.lde_row(i + k);
+                    wr[k] = wires_b.lde_row(i + k);
+                    zr[k] = zs_b.lde_row(i + k);
+                    zn[k] = zs_b.lde_row((i + k + next_step) % N);
+                    l0[k] = fmul(zh[(i + k) % qdf], finv(fmul(n_f, fsub(xs[i + k], 1))));
+                }
+                for (size_t j = 0; j < vcs.size(); ++j) vcs[j] = VecOps::lanes(cs[0][j], cs[1][j], cs[2][j], cs[3][j]);
+                for (size_t j = 0; j < vw.size(); ++j) vw[j] = VecOps::lanes(wr[0][j], wr[1][j], wr[2][j], wr[3][j]);
+                for (size_t j = 0; j < vz.size(); ++j) vz[j] = VecOps::lanes(zr[0][j], zr[1][j], zr[2][j], zr[3][j]);
+                for (size_t j = 0; j < nch; ++j) vzn[j] = VecOps::lanes(zn[0][j], zn[1][j], zn[2][j], zn[3][j]);
+                auto van = eval_vanishing<VecOps>(c, VecOps::lanes(xs[i], xs[i + 1], xs[i + 2], xs[i + 3]),
+                                                  VecOps::lanes(l0[0], l0[1], l0[2], l0[3]), vcs.data(), vcs.data() + ncs, vw.data(),
+                                                  vz.data(), vzn.data(), vz.data() + nch, pi_hash, betas.data(), gammas.data(),
+                                                  alphas.data());
+                for (size_t ch = 0; ch < nch; ++ch) {
+                    u64 out[4];
+                    VecOps::store(van[ch], out);
+                    for (int k = 0; k < 4; ++k) q[ch][i + k] = fmul(out[k], zh_inv[(i + k) % qdf]);
+                }
+            }
+        }
+    } else
+#endif
 #pragma omp parallel for schedule(static)
     for (long i = 0; i < (long)N; ++i) {
         u64 x = xs[i];

@@ -103,9 +103,12 @@ def test_lde_definition(oracle):
             assert acc == int(lde[c, l])
 
 
-def test_fast_mode_proof_is_byte_identical(oracle):
-    """The CPU-baseline arm (oracle.set_fast(True): AVX2 Poseidon) emits the same proof bytes as the readable restatement."""
-    s = oracle.Synth(zk=True, seed=5, **oracle.Synth.TINY)
+@pytest.mark.parametrize("spec,zk", [("TINY", True), ("VOTING", False), ("RECURSION_TINY", True)])
+def test_fast_mode_proof_is_byte_identical(oracle, spec, zk):
+    """The CPU-baseline arm (oracle.set_fast(True): AVX2 Poseidon, coset-wise LDE, the gate constraints evaluated four LDE points
+    per call through the 4-lane Ops of oracle/vec_ops.hpp) emits the same proof bytes as the readable restatement — on the
+    6-gate set and on the 14-gate recursion set (every gate's generic code instantiated over the vector type)."""
+    s = oracle.Synth(zk=zk, seed=5, **getattr(oracle.Synth, spec))
     c = oracle.Circuit(s.common, s.const_sigma_values)
     try:
         oracle.set_fast(False)

@@ -2,6 +2,7 @@
 // Flat C entry points over the oracle so tests/, __graft_entry__.smoke() and bench.py's CPU-baseline
 // legs can drive it through ctypes. All matrices are column-major [col][row] u64 unless noted.
 #include "prover.hpp"
+#include "vec_ops.hpp"
 #include <cstring>
 #include <chrono>
 #include <omp.h>
@@ -329,6 +330,42 @@ int orc_quotient(const OrcCircuit* c, const u64* wires, const u64* zs_pp, const 
 }
 
 u64 orc_salt_value(u64 seed, unsigned batch, unsigned s, u64 leaf) { return salt_value(seed, batch, s, leaf); }
+
+// the 4-lane field operations of the CPU-baseline arm's gate evaluator (vec_ops.hpp), for a direct check against big-integer
+// arithmetic on corner values: a, b [count] canonical (count a multiple of 4) -> add, sub, mul, mds-free sbox input products
+int orc_vecops_check(const u64* a, const u64* b, size_t count, u64 c, u64* add, u64* sub, u64* mul, u64* mulc) {
+#if defined(__AVX2__)
+    if (count % 4) { g_err = "count must be a multiple of 4"; return -1; }
+    for (size_t i = 0; i < count; i += 4) {
+        V4 x = VecOps::lanes(a[i], a[i + 1], a[i + 2], a[i + 3]), y = VecOps::lanes(b[i], b[i + 1], b[i + 2], b[i + 3]);
+        VecOps::store(VecOps::add(x, y), add + i);
+        VecOps::store(VecOps::sub(x, y), sub + i);
+        VecOps::store(VecOps::mul(x, y), mul + i);
+        VecOps::store(VecOps::mulc(x, c), mulc + i);
+    }
+    return 0;
+#else
+    g_err = "built without AVX2";
+    return -1;
+#endif
+}
+// mds_layer<VecOps> on four states [4][12] (row = one state) against mds_layer<BaseOps>
+int orc_vecops_mds(const u64* states, u64* out) {
+#if defined(__AVX2__)
+    V4 st[12];
+    for (int j = 0; j < 12; ++j) st[j] = VecOps::lanes(states[j], states[12 + j], states[24 + j], states[36 + j]);
+    mds_layer<VecOps>(st);
+    for (int j = 0; j < 12; ++j) {
+        u64 l[4];
+        VecOps::store(st[j], l);
+        for (int k = 0; k < 4; ++k) out[12 * k + j] = l[k];
+    }
+    return 0;
+#else
+    g_err = "built without AVX2";
+    return -1;
+#endif
+}
 
 #pragma GCC visibility pop
 }  // extern "C"

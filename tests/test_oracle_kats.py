@@ -102,3 +102,46 @@ def test_fast_poseidon_equals_the_definition(oracle):
         assert [int(x) for x in oracle.hash_pad([])] == [0xF9AD7EFEEE338AC6, 0x70014F06AE45AC42, 0x393D1B035A725D35, 0x2A6CE778AA4FB823]
     finally:
         oracle.set_fast(False)
+
+
+def test_vector_field_ops_of_the_fast_gate_evaluator(oracle):
+    """oracle/vec_ops.hpp (the 4-lane AVX2 Ops the CPU-baseline arm instantiates the gate code over): add, sub, mul, mulc and
+    the MDS layer against Python big-integer arithmetic on corner values (0, 1, p - 1, 2^32 +- 1, 2^64 - 2^32, sums that wrap
+    64 bits, products that reduce to exactly p - 1 or 0) and random ones."""
+    import ctypes
+
+    import numpy as np
+
+    P = oracle.P
+    L = oracle.lib()
+    u64p = ctypes.POINTER(ctypes.c_uint64)
+    corners = [0, 1, 2, P - 1, P - 2, 0xFFFFFFFF, 0x100000000, 0x100000001, 0xFFFFFFFF00000000, 0xFFFFFFFEFFFFFFFF,
+               0x8000000000000000, 0x7FFFFFFF80000001, (P + 1) // 2, (P - 1) // 2, pow(7, (P - 1) // 2 - 1, P), 0xFFFFFFFE00000002]
+    rng = np.random.default_rng(11)
+    a = np.array([x for x in corners for _ in corners] + [int(v) for v in rng.integers(0, P, size=4096, dtype=np.uint64)], dtype=np.uint64)
+    b = np.array([y for _ in corners for y in corners] + [int(v) for v in rng.integers(0, P, size=4096, dtype=np.uint64)], dtype=np.uint64)
+    n = len(a)
+    assert n % 4 == 0
+    outs = [np.zeros(n, dtype=np.uint64) for _ in range(4)]
+    for c in (0, 1, 7, 41, P - 1, 0xFFFFFFFF00000000):
+        rc = L.orc_vecops_check(a.ctypes.data_as(u64p), b.ctypes.data_as(u64p), ctypes.c_size_t(n), ctypes.c_uint64(c),
+                                *[o.ctypes.data_as(u64p) for o in outs])
+        assert rc == 0, oracle.last_error() if hasattr(oracle, "last_error") else rc
+        ai, bi = [int(x) for x in a], [int(x) for x in b]
+        assert [int(x) for x in outs[0]] == [(x + y) % P for x, y in zip(ai, bi)]
+        assert [int(x) for x in outs[1]] == [(x - y) % P for x, y in zip(ai, bi)]
+        assert [int(x) for x in outs[2]] == [(x * y) % P for x, y in zip(ai, bi)]
+        assert [int(x) for x in outs[3]] == [(x * c) % P for x in ai]
+    # MDS layer, four states per call
+    C = [17, 15, 41, 16, 2, 28, 13, 13, 39, 18, 34, 20]
+    states = rng.integers(0, P, size=(8, 4, 12), dtype=np.uint64)
+    states[0, 0] = P - 1
+    states[0, 1] = 0
+    states[0, 2, ::2] = P - 1
+    for blk in states:
+        out = np.zeros((4, 12), dtype=np.uint64)
+        assert L.orc_vecops_mds(np.ascontiguousarray(blk).ctypes.data_as(u64p), out.ctypes.data_as(u64p)) == 0
+        for k in range(4):
+            x = [int(v) for v in blk[k]]
+            want = [(sum(x[(i + r) % 12] * C[i] for i in range(12)) + (8 * x[0] if r == 0 else 0)) % P for r in range(12)]
+            assert [int(v) for v in out[k]] == want
